@@ -1,0 +1,220 @@
+/*
+ * ipp_b200.h — C ABI of the B200-native batched IPP environment engine.
+ *
+ * Drop-in boundary for the per-step hot path of dmar-bonn/ipp-rl.  The reference has no FFI of
+ * its own (it is pure Python); each entry point below names the reference interface it replaces
+ * (path:line under the reference tree) and is what a ctypes binding on the reference side binds
+ * (see INTEGRATION.md).  Plain pointers and sizes only — no torch / numpy types.
+ *
+ * One engine <-> one CUDA device <-> one stream.  Not thread-safe, not fork-safe.  An engine owns
+ * `batch` independent environment instances ("envs"), each with three row-major (y_dim, x_dim)
+ * fp32 maps resident in HBM: ground truth, belief mean, belief variance (the diagonal of the
+ * reference's covariance matrix, mapping/grid_maps.py:10-11).
+ *
+ * Conventions (reference): pose = [x, y, h] metres; x <-> column, y <-> row; flat cell index
+ * x_dim*row + col (sensors/models/sensor_models.py:85).
+ *
+ * All functions return IPP_OK (0) or a negative error code; ipp_last_error() gives the message.
+ * "host" entry points take host pointers, copy in/out and return after the work has completed;
+ * "_device" entry points take device pointers, enqueue on the engine stream and return at once.
+ */
+#ifndef IPP_B200_H
+#define IPP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPP_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define IPP_OK 0
+#define IPP_ERR_INVALID (-1)     /* bad argument / configuration (reference: logger.error + ValueError) */
+#define IPP_ERR_CUDA (-2)        /* CUDA runtime failure (sticky errors surface at ipp_sync) */
+#define IPP_ERR_NOMEM (-3)       /* device or pinned-host allocation failed */
+#define IPP_ERR_UNSUPPORTED (-4) /* e.g. INTER_AREA footprint with an up-sampling axis */
+
+/* ---- step flags -------------------------------------------------------------------------- */
+#define IPP_REWARD_TRACE 0u          /* planning/common/rewards.py:15-31  (reference, pinned) */
+#define IPP_REWARD_GAUSS_ENTROPY 1u  /* 0.5*sum ln(v/v') / (cost+1)       (extension, unpinned) */
+#define IPP_REWARD_MASK 3u
+#define IPP_FLAG_ADAPTIVE 4u         /* adaptive mask, planning/common/rewards.py:8-12 */
+#define IPP_FLAG_NO_DSIZE_QUIRK 8u   /* un-swap cv2 dsize (simulations/sensor_manipulations.py:20-22) */
+#define IPP_FLAG_LOGODDS 16u         /* log-odds occupancy fusion + Shannon entropy (extension) */
+#define IPP_FLAG_NO_COMMIT 32u       /* predict: compute rewards only, leave the variance untouched */
+#define IPP_FLAG_KEEP_PREV 64u       /* do not advance the stored previous action */
+
+/* ---- memory layouts of the belief in HBM --------------------------------------------------- */
+#define IPP_LAYOUT_PLANES 0 /* mean[B][Y][X], var[B][Y][X], gt[B][Y][X] */
+#define IPP_LAYOUT_MV 1     /* {mean,var}[B][Y][X] interleaved float2, gt[B][Y][X] */
+
+/* ---- cost model (planning/common/actions.py:8-41) ---------------------------------------- */
+#define IPP_COST_DISTANCE 0    /* uav_specifications is None -> Euclidean distance */
+#define IPP_COST_FLIGHT_TIME 1 /* trapezoidal velocity profile */
+
+#define IPP_MAX_ALTITUDE_LEVELS 32
+#define IPP_NUM_METRICS 8
+
+typedef struct ipp_engine ipp_engine;
+
+/* Configuration = the keys of the reference's YAML that the hot path consumes
+ * (config/example.yaml; SURVEY.md section 5 "Config / flags"). */
+typedef struct ipp_config {
+    uint32_t struct_bytes; /* = sizeof(ipp_config): ABI guard */
+    uint32_t abi_version;  /* = IPP_ABI_VERSION */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t batch;         /* number of envs on this device */
+    int32_t x_dim;         /* environment.x_dim  [cells]  (mapping/grid_maps.py:13-24) */
+    int32_t y_dim;         /* environment.y_dim  [cells]  (mapping/grid_maps.py:26-37) */
+    int32_t layout;        /* IPP_LAYOUT_* */
+    int32_t cost_mode;     /* IPP_COST_* */
+    double resolution;     /* environment.resolution [m/cell] (mapping/grid_maps.py:39-50) */
+    double angle_x_deg;    /* sensor.field_of_view.angle_x (sensors/cameras.py:25-27) */
+    double angle_y_deg;    /* sensor.field_of_view.angle_y (sensors/cameras.py:29-31) */
+    double tan_half_x;     /* tan(0.5*radians(angle_x)); 0 -> computed here with libm.  The Python
+                              host passes NumPy's value so floor() never flips (cameras.py:44-45) */
+    double tan_half_y;
+    double coeff_a;        /* sensor.model.coeff_a (sensors/models/sensor_models.py:27-30) */
+    double coeff_b;        /* sensor.model.coeff_b */
+    double rf_altitude;    /* resolution factor 2 above this altitude; reference hard-codes 10.0
+                              (sensors/cameras.py:122-125) */
+    double min_altitude;   /* experiment.constraints.* -> action table (planning/common/actions.py:73-91) */
+    double max_altitude;
+    double altitude_spacing;
+    double max_v;          /* experiment.uav.max_v  (planning/common/actions.py:32-41) */
+    double max_a;          /* experiment.uav.max_a */
+    double value_threshold; /* experiment.scenario.value_threshold (planning/common/rewards.py:8-12) */
+    double interval_factor; /* experiment.scenario.interval_factor */
+    uint64_t seed;         /* counter-based device RNG seed (throughput mode) */
+    int64_t env_id_offset; /* global id of local env 0 (env-batch sharding: the RNG stream of an env
+                              does not depend on how the batch is split across GPUs) */
+    void *stream;          /* optional caller-owned cudaStream_t; NULL -> the engine creates one */
+} ipp_config;
+
+typedef struct ipp_info {
+    int32_t batch, x_dim, y_dim, layout;
+    int32_t num_altitude_levels; /* int((max-min)/spacing)+1 */
+    int32_t num_actions;         /* levels * x_dim * y_dim */
+    int32_t max_measurements;    /* upper bound of measurements per step (noise row length) */
+    int32_t sm_count;
+    uint64_t launches;           /* kernels launched by this engine so far */
+    uint64_t steps;              /* ipp_step calls so far (RNG counter) */
+    uint64_t device_bytes;       /* HBM held by the engine */
+    double altitude[IPP_MAX_ALTITUDE_LEVELS];
+    int32_t radius_x[IPP_MAX_ALTITUDE_LEVELS]; /* footprint half-width in cells per level */
+    int32_t radius_y[IPP_MAX_ALTITUDE_LEVELS];
+} ipp_info;
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+
+/* Replaces GridMap(params) + SensorModelFactory/SensorFactory/SimulationFactory/Mapping
+ * construction (experiments/experiments.py:154-168) for `batch` envs.  Allocates HBM; maps are
+ * uninitialised until ipp_reset + ipp_set_ground_truth / ipp_synth_ground_truth. */
+int ipp_create(const ipp_config *cfg, ipp_engine **out);
+void ipp_destroy(ipp_engine *e);
+const char *ipp_last_error(const ipp_engine *e); /* e == NULL: message of the last failed ipp_create */
+int ipp_get_info(const ipp_engine *e, ipp_info *out);
+int ipp_sync(ipp_engine *e);
+
+/* Replaces Mapping.init_priors (mapping/mappings.py:217-261) in its diagonal restriction:
+ * mean <- prior_mean (reference: 0.5), var <- prior_var (diag of the GP prior = signal_variance),
+ * or per-env prior_var_per_env[batch] (host, shuffle_prior_cov) when not NULL.  Also sets every
+ * env's previous action to init_pose[3] (host; NULL -> [2, 2, 14], planning/missions.py:69) and
+ * zeroes the step counter. */
+int ipp_reset(ipp_engine *e, float prior_mean, float prior_var, const float *prior_var_per_env,
+              const double *init_pose);
+
+/* Replaces Simulation.ground_truth_map assignment (simulations/__init__.py:15-16,
+ * simulations/simulations.py:41): upload n_env maps [n_env][y_dim][x_dim] fp32 for envs
+ * [first_env, first_env+n_env).  src_is_device != 0 -> gt is a device pointer. */
+int ipp_set_ground_truth(ipp_engine *e, const float *gt, int32_t first_env, int32_t n_env,
+                         int32_t src_is_device);
+
+/* Synthetic ground truth generated on the device for benchmarking (smooth random harmonic field in
+ * [0,1] per env, a stand-in for simulations/ground_truths.py:14-33; not a parity item). */
+int ipp_synth_ground_truth(ipp_engine *e, uint64_t seed);
+
+/* Read / write belief state as dense [n_env][y_dim][x_dim] fp32 arrays (either may be NULL).
+ * Replaces reads/writes of grid_map.mean / np.diag(grid_map.cov_matrix)
+ * (mapping/grid_maps.py:10-11). */
+int ipp_get_state(ipp_engine *e, float *mean, float *var, int32_t first_env, int32_t n_env,
+                  int32_t dst_is_device);
+int ipp_set_state(ipp_engine *e, const float *mean, const float *var, int32_t first_env,
+                  int32_t n_env, int32_t src_is_device);
+int ipp_get_ground_truth(ipp_engine *e, float *gt, int32_t first_env, int32_t n_env,
+                         int32_t dst_is_device);
+int ipp_set_prev_pose(ipp_engine *e, const double *poses /* [batch][3] host */);
+int ipp_get_prev_pose(ipp_engine *e, double *poses /* [batch][3] host */);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+
+/* One executed step for every env, ONE fused kernel:
+ *   Camera.project_field_of_view            sensors/cameras.py:49-75
+ *   ScalarFieldSimulation.take_measurement  simulations/simulations.py:26-34
+ *     (+ downsample_measurement / add_model_dependent_gaussian_noise,
+ *        simulations/sensor_manipulations.py:7-26,44-57)
+ *   Mapping.update_grid_map                 mapping/mappings.py:114-153 (diagonal restriction)
+ *   compute_adaptive_msk / compute_reward   planning/common/rewards.py:8-31
+ *   action_costs                            planning/common/actions.py:8-41
+ * Exactly one of action_ids[batch] (ids of planning/common/actions.py:73-91:
+ * id = level*N + x_dim*col + row) and poses[batch][3] (fp64 metres) must be non-NULL.
+ * noise: standard normals, row b holds the measurement noise of env b in C order of the
+ * measurement array (row stride noise_stride floats); NULL -> counter-based Philox4x32-10 on the
+ * device.  reward[batch] receives the information-gain reward of the step.  flags: IPP_REWARD_*,
+ * IPP_FLAG_*.  measurements (optional, may be NULL): z of every env, row stride noise_stride. */
+int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise,
+             int32_t noise_stride, float *reward, float *measurements, uint32_t flags);
+int ipp_step_device(ipp_engine *e, const int32_t *action_ids, const double *poses,
+                    const float *noise, int32_t noise_stride, float *reward, float *measurements,
+                    uint32_t flags);
+
+/* The two halves of ipp_step as separate calls (host pointers), for callers that keep the
+ * reference's two-call protocol (planning/greedy_mission.py:101-102):
+ *   ipp_measure = Sensor.take_measurement(position)            sensors/cameras.py:108-116
+ *   ipp_update  = Mapping.update_grid_map(position, data)      mapping/mappings.py:114-153
+ * measurements: [batch][stride] fp32, row b = z of env b flattened in C order. */
+int ipp_measure(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise,
+                int32_t stride, float *measurements, uint32_t flags);
+int ipp_update(ipp_engine *e, const int32_t *action_ids, const double *poses,
+               const float *measurements, int32_t stride, float *reward, uint32_t flags);
+
+/* Rollout / prediction step — replaces simulate_prediction_step
+ * (planning/common/optimization.py:14-30): covariance-only update, no ground truth, no noise.
+ * n_jobs independent jobs; job j acts on env env_index[j] (NULL -> j, requires n_jobs == batch)
+ * with action action_ids[j] / poses[j] and previous action prev_poses[j] (NULL -> the env's
+ * stored previous action).  With IPP_FLAG_NO_COMMIT the variance is left untouched (the
+ * reference's predict_only=True contract: greedy_search evaluates every candidate from the same
+ * state, optimization.py:82-98); otherwise the env's variance advances (rollout descent) and jobs
+ * must reference distinct envs. */
+int ipp_predict(ipp_engine *e, int32_t n_jobs, const int32_t *env_index, const int32_t *action_ids,
+                const double *poses, const double *prev_poses, float *reward, uint32_t flags);
+int ipp_predict_device(ipp_engine *e, int32_t n_jobs, const int32_t *env_index,
+                       const int32_t *action_ids, const double *poses, const double *prev_poses,
+                       float *reward, uint32_t flags);
+
+/* Evaluation metrics per env — replaces Mission.eval (planning/missions.py:176-203) over
+ * planning/evaluation_metrics.py:4-58.  metrics[batch][IPP_NUM_METRICS] =
+ * {rmse, wrmse, mll, wmll, trace, uncertainty_difference, rmse_masked, trace_masked}; the mask is
+ * gt >= value_threshold as in missions.py:179. */
+int ipp_eval(ipp_engine *e, float *metrics);
+int ipp_eval_device(ipp_engine *e, float *metrics);
+
+/* ---- interop ----------------------------------------------------------------------------------- */
+#define IPP_PTR_MEAN 0   /* PLANES: float[B][Y][X];  MV: float2[B][Y][X] base (mean at .x) */
+#define IPP_PTR_VAR 1    /* PLANES: float[B][Y][X];  MV: same base + 1 float (stride 2) */
+#define IPP_PTR_GT 2
+#define IPP_PTR_REWARD 3 /* engine-owned float[batch] staging of the last host-API step */
+#define IPP_PTR_STREAM 4 /* the cudaStream_t the engine launches on */
+void *ipp_device_ptr(ipp_engine *e, int32_t which);
+
+/* Pinned host memory for the host entry points (cudaHostAlloc). */
+int ipp_host_alloc(void **ptr, size_t bytes);
+int ipp_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPP_B200_H */

@@ -1,0 +1,873 @@
+// ipp_engine.cu — C-ABI implementation of include/ipp_b200.h for sm_100a.
+//
+// Host-side runtime of the batched IPP environment engine: HBM layout, reset / ground-truth /
+// state transfer, the fused step launch (step_kernel.cuh), the evaluation-metric reduction and the
+// error / stream plumbing.  No PyTorch, no Python: plain CUDA runtime behind extern "C".
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "step_kernel.cuh"
+
+using namespace ipp;
+
+// ------------------------------------------------------------------------------------------------
+// engine object
+// ------------------------------------------------------------------------------------------------
+struct ipp_engine {
+    ipp_config cfg{};
+    int n_levels = 0;
+    AltLevel lut[IPP_MAX_ALTITUDE_LEVELS]{};
+    int max_meas = 0;
+    int sm_count = 0;
+    size_t plane = 0;
+    // HBM
+    float *d_mean = nullptr;  // PLANES: float[B*plane]; MV: float2[B*plane]
+    float *d_var = nullptr;   // PLANES only
+    float *d_gt = nullptr;
+    double *d_prev = nullptr;  // [B][3]
+    int *d_status = nullptr;
+    // staging for the host entry points
+    int32_t *d_actions = nullptr;  // [cap_jobs]
+    double *d_poses = nullptr;     // [cap_jobs][3]
+    double *d_prev_in = nullptr;   // [cap_jobs][3]
+    int32_t *d_env_index = nullptr;
+    float *d_reward = nullptr;  // [cap_jobs]
+    size_t cap_jobs = 0;
+    float *d_noise = nullptr;
+    float *d_z = nullptr;
+    size_t cap_noise = 0, cap_z = 0;
+    float *d_metrics = nullptr;
+    float *d_scratch = nullptr;  // dense [n][plane] staging for MV get/set
+    size_t cap_scratch = 0;
+    int *h_status = nullptr;  // pinned
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    uint64_t steps = 0;
+    uint64_t device_bytes = 0;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(ipp_engine *e, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e)
+        e->err = buf;
+    else
+        g_create_err = buf;
+    return code;
+}
+
+#define CU(e, call)                                                                                  \
+    do {                                                                                             \
+        cudaError_t _s = (call);                                                                     \
+        if (_s != cudaSuccess) {                                                                     \
+            const int _code = (_s == cudaErrorMemoryAllocation) ? IPP_ERR_NOMEM : IPP_ERR_CUDA;      \
+            return fail((e), _code, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_s), __FILE__, __LINE__); \
+        }                                                                                            \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(ipp_engine *e, T **p, size_t n) {
+    CU(e, cudaMalloc((void **)p, n * sizeof(T)));
+    e->device_bytes += n * sizeof(T);
+    return IPP_OK;
+}
+
+template <typename T>
+static int ensure(ipp_engine *e, T **p, size_t *cap, size_t n) {
+    if (*cap >= n && *p) return IPP_OK;
+    if (*p) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        CU(e, cudaFree(*p));
+        e->device_bytes -= *cap * sizeof(T);
+        *p = nullptr;
+        *cap = 0;
+    }
+    int rc = dev_alloc(e, p, n);
+    if (rc == IPP_OK) *cap = n;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// auxiliary kernels (full-map streaming passes; trivially HBM-bound, coalesced)
+// ------------------------------------------------------------------------------------------------
+__global__ void reset_kernel(float *mean, float *var, int layout, size_t plane, int batch, float prior_mean, float prior_var,
+                             const float *prior_var_env) {
+    const size_t total = plane * (size_t)batch;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float pv = prior_var_env ? prior_var_env[i / plane] : prior_var;
+        if (layout == IPP_LAYOUT_MV) {
+            reinterpret_cast<float2 *>(mean)[i] = make_float2(prior_mean, pv);
+        } else {
+            mean[i] = prior_mean;
+            var[i] = pv;
+        }
+    }
+}
+
+__global__ void fill_prev_kernel(double *prev, int batch, double x, double y, double h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch) {
+        prev[3 * (size_t)i + 0] = x;
+        prev[3 * (size_t)i + 1] = y;
+        prev[3 * (size_t)i + 2] = h;
+    }
+}
+
+// dense [n][plane] <-> interleaved float2 (MV layout)
+__global__ void mv_unpack_kernel(const float2 *mv, float *mean, float *var, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float2 t = mv[i];
+        if (mean) mean[i] = t.x;
+        if (var) var[i] = t.y;
+    }
+}
+__global__ void mv_pack_kernel(float2 *mv, const float *mean, const float *var, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float2 t = mv[i];
+        if (mean) t.x = mean[i];
+        if (var) t.y = var[i];
+        mv[i] = t;
+    }
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
+// Smooth synthetic field in [0,1]: normalised sum of 6 random plane waves per env.
+__global__ void synth_gt_kernel(float *gt, size_t plane, int X, int batch, uint32_t seed, uint32_t env_off) {
+    const int env = blockIdx.y;
+    __shared__ float fx[6], fy[6], ph[6], am[6];
+    if (threadIdx.x < 6) {
+        const uint32_t h0 = mix32(seed ^ mix32((uint32_t)env + env_off) ^ (0x9E3779B9u * (threadIdx.x + 1)));
+        const uint32_t h1 = mix32(h0 + 0x85ebca6bu), h2 = mix32(h1 + 0xc2b2ae35u);
+        const float k = 0.02f + 0.10f * (float)threadIdx.x / 6.0f;
+        const float ang = 6.2831853f * (h0 * 2.3283064e-10f);
+        fx[threadIdx.x] = k * cosf(ang) * 6.2831853f;
+        fy[threadIdx.x] = k * sinf(ang) * 6.2831853f;
+        ph[threadIdx.x] = 6.2831853f * (h1 * 2.3283064e-10f);
+        am[threadIdx.x] = (0.5f + 0.5f * (h2 * 2.3283064e-10f)) / (1.0f + threadIdx.x);
+    }
+    __syncthreads();
+    float norm = 0.f;
+    for (int k = 0; k < 6; ++k) norm += am[k];
+    float *g = gt + (size_t)env * plane;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = (float)(i % X), y = (float)(i / X);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += am[k] * __sinf(fx[k] * x + fy[k] * y + ph[k]);
+        g[i] = fminf(fmaxf(0.5f + 0.5f * s / norm, 0.0f), 1.0f);
+    }
+}
+
+// Evaluation metrics: one CTA per env, two streaming passes, fp64 block reduction.
+// planning/evaluation_metrics.py:4-58 as called by planning/missions.py:176-203.
+constexpr int kEvalThreads = 256;
+
+template <int N>
+__device__ __forceinline__ void block_reduce(double (&v)[N], double *smem, bool is_min_first2, bool is_max_third) {
+    // v[0], v[1] reduced with min, v[2] with max when flagged; everything else summed
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const double y = __shfl_xor_sync(0xffffffffu, x, s);
+            if (is_min_first2 && k < 2)
+                x = fmin(x, y);
+            else if (is_max_third && k == 2)
+                x = fmax(x, y);
+            else
+                x += y;
+        }
+        if (lane == 0) smem[warp * N + k] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int nw = kEvalThreads / 32;
+            double x = lane < nw ? smem[lane * N + k] : ((is_min_first2 && k < 2) ? 1e300 : ((is_max_third && k == 2) ? -1e300 : 0.0));
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const double y = __shfl_xor_sync(0xffffffffu, x, s);
+                if (is_min_first2 && k < 2)
+                    x = fmin(x, y);
+                else if (is_max_third && k == 2)
+                    x = fmax(x, y);
+                else
+                    x += y;
+            }
+            if (lane == 0) smem[k] = x;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = smem[k];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, const float *var, const float *gt, int layout, size_t plane,
+                                                            float thr, float *metrics) {
+    __shared__ double smem[(kEvalThreads / 32) * 10];
+    const int env = blockIdx.x;
+    const float *g = gt + (size_t)env * plane;
+    const float *m = mean + (size_t)env * plane * (layout == IPP_LAYOUT_MV ? 2 : 1);
+    const float *v = layout == IPP_LAYOUT_MV ? m + 1 : var + (size_t)env * plane;
+    const int es = layout == IPP_LAYOUT_MV ? 2 : 1;
+
+    // pass 1: min(gt), min(mean), max(gt), sum(gt)
+    double a[4] = {1e300, 1e300, -1e300, 0.0};
+    for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
+        const double gi = g[i], mi = m[i * es];
+        a[0] = fmin(a[0], gi);
+        a[1] = fmin(a[1], mi);
+        a[2] = fmax(a[2], gi);
+        a[3] += gi;
+    }
+    block_reduce<4>(a, smem, true, true);
+    const double gmin = a[0], mmin = a[1], gmax = a[2], gsum = a[3];
+    const double range = gmax - gmin;
+    const double n = (double)plane;
+    const double wsum = (gsum - n * mmin) / range;  // sum of un-normalised weights (evaluation_metrics.py:34-35)
+
+    // pass 2
+    double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
+        const double gi = g[i], mi = m[i * es], vi = v[i * es];
+        const double sq = (gi - mi) * (gi - mi);
+        const double w = ((gi - mmin) / range) / wsum;
+        const double ll = 0.5 * log(2.0 * 3.141592653589793 * vi) + sq / 2.0 * vi;  // (:44) multiplies by P_ii
+        const bool in = g[i] >= thr;
+        s[0] += sq;
+        s[1] += w * sq;
+        s[2] += ll;
+        s[3] += w * ll;
+        s[4] += vi;
+        s[5] += in ? vi : 0.0;
+        s[6] += in ? 0.0 : vi;
+        s[7] += in ? 1.0 : 0.0;
+        s[8] += in ? sq : 0.0;
+    }
+    block_reduce<10>(s, smem, false, false);
+    if (threadIdx.x == 0) {
+        float *o = metrics + (size_t)env * IPP_NUM_METRICS;
+        const double n_in = s[7], n_out = n - s[7];
+        o[0] = (float)sqrt(s[0] / n);
+        o[1] = (float)sqrt(s[1] / n);
+        o[2] = (float)(s[2] / n);
+        o[3] = (float)(s[3] / n);
+        o[4] = (float)s[4];
+        const double mu_in = s[5] / n_in, mu_out = s[6] / n_out;
+        o[5] = (float)((mu_out - mu_in) / mu_out);
+        o[6] = (float)sqrt(s[8] / n_in);
+        o[7] = (float)s[5];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// configuration -> altitude LUT (fp64, same operation order as the reference)
+// ------------------------------------------------------------------------------------------------
+static void footprint_radius(const ipp_config &c, double h, int *rx, int *ry) {
+    // sensors/cameras.py:44-45, 62-66
+    const double xm = 2 * h * c.tan_half_x, ym = 2 * h * c.tan_half_y;
+    const double wx = std::floor(xm / c.resolution), wy = std::floor(ym / c.resolution);
+    *rx = (int)std::floor(0.5 * wx);
+    *ry = (int)std::floor(0.5 * wy);
+}
+
+static int build_lut(ipp_engine *e) {
+    ipp_config &c = e->cfg;
+    // planning/common/actions.py:74: linspace(min, max, int((max-min)/spacing)+1)
+    const int n = (int)((c.max_altitude - c.min_altitude) / c.altitude_spacing) + 1;
+    if (n < 1 || n > IPP_MAX_ALTITUDE_LEVELS) return fail(e, IPP_ERR_INVALID, "altitude levels %d outside [1,%d]", n, IPP_MAX_ALTITUDE_LEVELS);
+    e->n_levels = n;
+    int max_cells_rf1 = 1, max_blocks_rf2 = 1;
+    for (int k = 0; k < n; ++k) {
+        // numpy.linspace: start + k*step with step = (stop-start)/(n-1); last point forced to stop
+        const double step = n > 1 ? (c.max_altitude - c.min_altitude) / (double)(n - 1) : 0.0;
+        double h = c.min_altitude + (double)k * step;
+        if (k == n - 1 && n > 1) h = c.max_altitude;
+        AltLevel &L = e->lut[k];
+        L.alt = h;
+        footprint_radius(c, h, &L.rx, &L.ry);
+        L.rf = h > c.rf_altitude ? 2 : 1;
+        const double s2 = c.coeff_a * (1 - std::exp(-c.coeff_b * h));
+        L.s2 = (float)s2;
+        L.R = (float)((double)(L.rf * L.rf * L.rf) * s2);
+        L.pad = 0;
+    }
+    // bound of measurements per step for any altitude in (0, max_altitude] (pose mode included)
+    {
+        int rx, ry;
+        const double h1 = std::fmin(c.max_altitude, c.rf_altitude);
+        footprint_radius(c, h1, &rx, &ry);
+        const int nx = std::min(2 * rx + 1, c.x_dim), ny = std::min(2 * ry + 1, c.y_dim);
+        max_cells_rf1 = nx * ny;
+        footprint_radius(c, c.max_altitude, &rx, &ry);
+        const int nx2 = std::min(2 * rx + 1, c.x_dim), ny2 = std::min(2 * ry + 1, c.y_dim);
+        max_blocks_rf2 = ((nx2 + 1) / 2) * ((ny2 + 1) / 2);
+        if (c.max_altitude <= c.rf_altitude) max_blocks_rf2 = 0;
+    }
+    e->max_meas = std::max(max_cells_rf1, max_blocks_rf2);
+    return IPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// life cycle
+// ------------------------------------------------------------------------------------------------
+extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
+    if (!cfg || !out) return fail(nullptr, IPP_ERR_INVALID, "ipp_create: NULL argument");
+    *out = nullptr;
+    if (cfg->struct_bytes != sizeof(ipp_config) || cfg->abi_version != IPP_ABI_VERSION)
+        return fail(nullptr, IPP_ERR_INVALID, "ipp_create: ABI mismatch (struct_bytes %u vs %zu, version %u vs %d)", cfg->struct_bytes,
+                    sizeof(ipp_config), cfg->abi_version, IPP_ABI_VERSION);
+    if (cfg->batch < 1 || cfg->x_dim < 1 || cfg->y_dim < 1) return fail(nullptr, IPP_ERR_INVALID, "ipp_create: batch/x_dim/y_dim must be >= 1");
+    if ((double)cfg->x_dim * cfg->y_dim > 1.0e9) return fail(nullptr, IPP_ERR_INVALID, "ipp_create: grid too large");
+    if (!(cfg->resolution > 0)) return fail(nullptr, IPP_ERR_INVALID, "ipp_create: environment.resolution must be > 0");
+    if (!(cfg->angle_x_deg > 0 && cfg->angle_x_deg < 180 && cfg->angle_y_deg > 0 && cfg->angle_y_deg < 180))
+        return fail(nullptr, IPP_ERR_INVALID, "ipp_create: field_of_view angles must be in (0, 180)");
+    if (cfg->layout != IPP_LAYOUT_PLANES && cfg->layout != IPP_LAYOUT_MV) return fail(nullptr, IPP_ERR_INVALID, "ipp_create: unknown layout %d", cfg->layout);
+    if (cfg->cost_mode != IPP_COST_DISTANCE && cfg->cost_mode != IPP_COST_FLIGHT_TIME)
+        return fail(nullptr, IPP_ERR_INVALID, "ipp_create: unknown cost_mode %d", cfg->cost_mode);
+    if (cfg->cost_mode == IPP_COST_FLIGHT_TIME && !(cfg->max_v > 0 && cfg->max_a > 0))
+        return fail(nullptr, IPP_ERR_INVALID, "ipp_create: uav max_v / max_a must be > 0");
+    if (!(cfg->altitude_spacing > 0) || !(cfg->max_altitude >= cfg->min_altitude) || !(cfg->min_altitude > 0))
+        return fail(nullptr, IPP_ERR_INVALID, "ipp_create: need 0 < min_altitude <= max_altitude and altitude_spacing > 0");
+
+    ipp_engine *e = new (std::nothrow) ipp_engine();
+    if (!e) return fail(nullptr, IPP_ERR_NOMEM, "ipp_create: out of host memory");
+    e->cfg = *cfg;
+    const double kPi = 3.14159265358979323846;
+    if (e->cfg.tan_half_x == 0) e->cfg.tan_half_x = std::tan(0.5 * (e->cfg.angle_x_deg * (kPi / 180.0)));
+    if (e->cfg.tan_half_y == 0) e->cfg.tan_half_y = std::tan(0.5 * (e->cfg.angle_y_deg * (kPi / 180.0)));
+    e->plane = (size_t)cfg->x_dim * cfg->y_dim;
+
+    auto bail = [&](int rc) {
+        g_create_err = e->err;
+        ipp_destroy(e);
+        return rc;
+    };
+    int rc = build_lut(e);
+    if (rc != IPP_OK) return bail(rc);
+
+    cudaError_t s = cudaSetDevice(cfg->device);
+    if (s != cudaSuccess) return bail(fail(e, IPP_ERR_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(s)));
+    cudaDeviceProp prop;
+    s = cudaGetDeviceProperties(&prop, cfg->device);
+    if (s != cudaSuccess) return bail(fail(e, IPP_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(s)));
+    e->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) return bail(fail(e, IPP_ERR_UNSUPPORTED, "device %d is sm_%d%d; this engine is built for sm_100a only", cfg->device, prop.major, prop.minor));
+
+    if (cfg->stream) {
+        e->stream = (cudaStream_t)cfg->stream;
+    } else {
+        s = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (s != cudaSuccess) return bail(fail(e, IPP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(s)));
+        e->own_stream = true;
+    }
+    const size_t cells = e->plane * (size_t)cfg->batch;
+    if (cfg->layout == IPP_LAYOUT_MV) {
+        if ((rc = dev_alloc(e, &e->d_mean, 2 * cells)) != IPP_OK) return bail(rc);
+    } else {
+        if ((rc = dev_alloc(e, &e->d_mean, cells)) != IPP_OK) return bail(rc);
+        if ((rc = dev_alloc(e, &e->d_var, cells)) != IPP_OK) return bail(rc);
+    }
+    if ((rc = dev_alloc(e, &e->d_gt, cells)) != IPP_OK) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_prev, 3 * (size_t)cfg->batch)) != IPP_OK) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_status, 1)) != IPP_OK) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_metrics, (size_t)cfg->batch * IPP_NUM_METRICS)) != IPP_OK) return bail(rc);
+    s = cudaMemsetAsync(e->d_status, 0, sizeof(int), e->stream);
+    if (s == cudaSuccess) s = cudaHostAlloc((void **)&e->h_status, sizeof(int), cudaHostAllocDefault);
+    if (s != cudaSuccess) return bail(fail(e, IPP_ERR_CUDA, "status init: %s", cudaGetErrorString(s)));
+    *e->h_status = 0;
+    *out = e;
+    return IPP_OK;
+}
+
+extern "C" void ipp_destroy(ipp_engine *e) {
+    if (!e) return;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    void *ptrs[] = {e->d_mean, e->d_var, e->d_gt, e->d_prev, e->d_status, e->d_actions, e->d_poses, e->d_prev_in, e->d_env_index,
+                    e->d_reward, e->d_noise, e->d_z, e->d_metrics, e->d_scratch};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (e->h_status) cudaFreeHost(e->h_status);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" const char *ipp_last_error(const ipp_engine *e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int ipp_get_info(const ipp_engine *e, ipp_info *out) {
+    if (!e || !out) return IPP_ERR_INVALID;
+    memset(out, 0, sizeof *out);
+    out->batch = e->cfg.batch;
+    out->x_dim = e->cfg.x_dim;
+    out->y_dim = e->cfg.y_dim;
+    out->layout = e->cfg.layout;
+    out->num_altitude_levels = e->n_levels;
+    out->num_actions = (int32_t)((size_t)e->n_levels * e->plane);
+    out->max_measurements = e->max_meas;
+    out->sm_count = e->sm_count;
+    out->launches = e->launches;
+    out->steps = e->steps;
+    out->device_bytes = e->device_bytes;
+    for (int k = 0; k < e->n_levels; ++k) {
+        out->altitude[k] = e->lut[k].alt;
+        out->radius_x[k] = e->lut[k].rx;
+        out->radius_y[k] = e->lut[k].ry;
+    }
+    return IPP_OK;
+}
+
+static int check_status(ipp_engine *e) {
+    // device status word -> host (after a synchronising copy)
+    CU(e, cudaMemcpyAsync(e->h_status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    if (*e->h_status & 1) {
+        CU(e, cudaMemsetAsync(e->d_status, 0, sizeof(int), e->stream));
+        *e->h_status = 0;
+        return fail(e, IPP_ERR_UNSUPPORTED,
+                    "footprint needs cv2 INTER_AREA with an up-sampling axis (non-square FoV/grid corner case); not supported");
+    }
+    return IPP_OK;
+}
+
+extern "C" int ipp_sync(ipp_engine *e) {
+    if (!e) return IPP_ERR_INVALID;
+    return check_status(e);
+}
+
+static int ensure_job_buffers(ipp_engine *e, size_t n);
+
+static int grid_for(size_t n, int threads, int sm_count) {
+    const size_t want = (n + threads - 1) / threads;
+    const size_t cap = (size_t)sm_count * 16;
+    return (int)std::max<size_t>(1, std::min(want, cap));
+}
+
+extern "C" int ipp_reset(ipp_engine *e, float prior_mean, float prior_var, const float *prior_var_per_env, const double *init_pose) {
+    if (!e) return IPP_ERR_INVALID;
+    if (!(prior_var > 0) && !prior_var_per_env) return fail(e, IPP_ERR_INVALID, "ipp_reset: prior variance must be > 0");
+    const int B = e->cfg.batch;
+    float *d_pv = nullptr;
+    if (prior_var_per_env) {
+        int rc = ensure_job_buffers(e, (size_t)B);  // borrow the reward staging as a [B] float buffer
+        if (rc != IPP_OK) return rc;
+        CU(e, cudaMemcpyAsync(e->d_reward, prior_var_per_env, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        d_pv = e->d_reward;
+    }
+    reset_kernel<<<grid_for(e->plane * (size_t)B, 256, e->sm_count), 256, 0, e->stream>>>(e->d_mean, e->d_var, e->cfg.layout, e->plane, B,
+                                                                                          prior_mean, prior_var, d_pv);
+    const double dflt[3] = {2.0, 2.0, 14.0};  // planning/missions.py:69
+    const double *ip = init_pose ? init_pose : dflt;
+    fill_prev_kernel<<<(B + 255) / 256, 256, 0, e->stream>>>(e->d_prev, B, ip[0], ip[1], ip[2]);
+    e->launches += 2;
+    e->steps = 0;
+    CU(e, cudaGetLastError());
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
+static int check_range(ipp_engine *e, int32_t first, int32_t n, const char *who) {
+    if (first < 0 || n < 0 || (int64_t)first + n > e->cfg.batch) return fail(e, IPP_ERR_INVALID, "%s: env range [%d, %d) outside batch %d", who, first, first + n, e->cfg.batch);
+    return IPP_OK;
+}
+
+extern "C" int ipp_set_ground_truth(ipp_engine *e, const float *gt, int32_t first_env, int32_t n_env, int32_t src_is_device) {
+    if (!e || !gt) return IPP_ERR_INVALID;
+    int rc = check_range(e, first_env, n_env, "ipp_set_ground_truth");
+    if (rc != IPP_OK) return rc;
+    CU(e, cudaMemcpyAsync(e->d_gt + (size_t)first_env * e->plane, gt, (size_t)n_env * e->plane * sizeof(float),
+                          src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
+extern "C" int ipp_get_ground_truth(ipp_engine *e, float *gt, int32_t first_env, int32_t n_env, int32_t dst_is_device) {
+    if (!e || !gt) return IPP_ERR_INVALID;
+    int rc = check_range(e, first_env, n_env, "ipp_get_ground_truth");
+    if (rc != IPP_OK) return rc;
+    CU(e, cudaMemcpyAsync(gt, e->d_gt + (size_t)first_env * e->plane, (size_t)n_env * e->plane * sizeof(float),
+                          dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
+extern "C" int ipp_synth_ground_truth(ipp_engine *e, uint64_t seed) {
+    if (!e) return IPP_ERR_INVALID;
+    dim3 grid((unsigned)std::min<size_t>((e->plane + 255) / 256, 64), (unsigned)e->cfg.batch);
+    if (e->cfg.batch > 65535) {
+        // grid.y limit: launch in slabs
+        for (int first = 0; first < e->cfg.batch; first += 65535) {
+            const int n = std::min(65535, e->cfg.batch - first);
+            dim3 g2(grid.x, (unsigned)n);
+            synth_gt_kernel<<<g2, 256, 0, e->stream>>>(e->d_gt + (size_t)first * e->plane, e->plane, e->cfg.x_dim, n, (uint32_t)seed,
+                                                       (uint32_t)(e->cfg.env_id_offset + first));
+            e->launches++;
+        }
+    } else {
+        synth_gt_kernel<<<grid, 256, 0, e->stream>>>(e->d_gt, e->plane, e->cfg.x_dim, e->cfg.batch, (uint32_t)seed, (uint32_t)e->cfg.env_id_offset);
+        e->launches++;
+    }
+    CU(e, cudaGetLastError());
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
+extern "C" int ipp_get_state(ipp_engine *e, float *mean, float *var, int32_t first_env, int32_t n_env, int32_t dst_is_device) {
+    if (!e) return IPP_ERR_INVALID;
+    int rc = check_range(e, first_env, n_env, "ipp_get_state");
+    if (rc != IPP_OK) return rc;
+    const size_t n = (size_t)n_env * e->plane, off = (size_t)first_env * e->plane;
+    const cudaMemcpyKind kind = dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (e->cfg.layout == IPP_LAYOUT_PLANES) {
+        if (mean) CU(e, cudaMemcpyAsync(mean, e->d_mean + off, n * sizeof(float), kind, e->stream));
+        if (var) CU(e, cudaMemcpyAsync(var, e->d_var + off, n * sizeof(float), kind, e->stream));
+    } else {
+        float *dm = mean, *dv = var;
+        if (!dst_is_device) {
+            if ((rc = ensure(e, &e->d_scratch, &e->cap_scratch, 2 * n)) != IPP_OK) return rc;
+            dm = mean ? e->d_scratch : nullptr;
+            dv = var ? e->d_scratch + n : nullptr;
+        }
+        mv_unpack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(reinterpret_cast<const float2 *>(e->d_mean) + off, dm, dv, n);
+        e->launches++;
+        if (!dst_is_device) {
+            if (mean) CU(e, cudaMemcpyAsync(mean, dm, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+            if (var) CU(e, cudaMemcpyAsync(var, dv, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        }
+    }
+    CU(e, cudaGetLastError());
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
+extern "C" int ipp_set_state(ipp_engine *e, const float *mean, const float *var, int32_t first_env, int32_t n_env, int32_t src_is_device) {
+    if (!e) return IPP_ERR_INVALID;
+    int rc = check_range(e, first_env, n_env, "ipp_set_state");
+    if (rc != IPP_OK) return rc;
+    const size_t n = (size_t)n_env * e->plane, off = (size_t)first_env * e->plane;
+    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (e->cfg.layout == IPP_LAYOUT_PLANES) {
+        if (mean) CU(e, cudaMemcpyAsync(e->d_mean + off, mean, n * sizeof(float), kind, e->stream));
+        if (var) CU(e, cudaMemcpyAsync(e->d_var + off, var, n * sizeof(float), kind, e->stream));
+    } else {
+        const float *dm = mean, *dv = var;
+        if (!src_is_device) {
+            if ((rc = ensure(e, &e->d_scratch, &e->cap_scratch, 2 * n)) != IPP_OK) return rc;
+            if (mean) {
+                CU(e, cudaMemcpyAsync(e->d_scratch, mean, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+                dm = e->d_scratch;
+            }
+            if (var) {
+                CU(e, cudaMemcpyAsync(e->d_scratch + n, var, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+                dv = e->d_scratch + n;
+            }
+        }
+        mv_pack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(reinterpret_cast<float2 *>(e->d_mean) + off, dm, dv, n);
+        e->launches++;
+    }
+    CU(e, cudaGetLastError());
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
+extern "C" int ipp_set_prev_pose(ipp_engine *e, const double *poses) {
+    if (!e || !poses) return IPP_ERR_INVALID;
+    CU(e, cudaMemcpyAsync(e->d_prev, poses, 3 * (size_t)e->cfg.batch * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+extern "C" int ipp_get_prev_pose(ipp_engine *e, double *poses) {
+    if (!e || !poses) return IPP_ERR_INVALID;
+    CU(e, cudaMemcpyAsync(poses, e->d_prev, 3 * (size_t)e->cfg.batch * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the hot path
+// ------------------------------------------------------------------------------------------------
+static void fill_params(const ipp_engine *e, StepParams &p) {
+    const ipp_config &c = e->cfg;
+    memset(&p, 0, sizeof p);
+    p.mean = e->d_mean;
+    p.var = e->d_var;
+    p.gt = e->d_gt;
+    p.plane = e->plane;
+    p.X = c.x_dim;
+    p.Y = c.y_dim;
+    p.batch = c.batch;
+    p.prev_state = e->d_prev;
+    p.status = e->d_status;
+    p.res = c.resolution;
+    p.tan_x = c.tan_half_x;
+    p.tan_y = c.tan_half_y;
+    p.coeff_a = c.coeff_a;
+    p.coeff_b = c.coeff_b;
+    p.rf_alt = c.rf_altitude;
+    p.max_v = c.max_v;
+    p.max_a = c.max_a;
+    p.thr = (float)c.value_threshold;
+    p.kappa = (float)c.interval_factor;
+    p.cost_mode = c.cost_mode;
+    p.n_levels = e->n_levels;
+    p.seed_lo = (uint32_t)(c.seed & 0xffffffffu);
+    p.seed_hi = (uint32_t)(c.seed >> 32);
+    p.step_lo = (uint32_t)(e->steps & 0xffffffffu);
+    p.step_hi = (uint32_t)(e->steps >> 32);
+    p.env_id_offset = (uint32_t)c.env_id_offset;
+    memcpy(p.lut, e->lut, sizeof p.lut);
+}
+
+template <int MODE>
+static void launch_mode(ipp_engine *e, const StepParams &p) {
+    const int blocks = (p.n_jobs + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (e->cfg.layout == IPP_LAYOUT_MV)
+        ipp_step_kernel<IPP_LAYOUT_MV, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
+    else
+        ipp_step_kernel<IPP_LAYOUT_PLANES, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
+    e->launches++;
+}
+
+static int launch_step(ipp_engine *e, StepParams &p, int mode) {
+    if (p.n_jobs <= 0) return IPP_OK;
+    if (mode == MODE_KALMAN)
+        launch_mode<MODE_KALMAN>(e, p);
+    else if (mode == MODE_PREDICT)
+        launch_mode<MODE_PREDICT>(e, p);
+    else
+        launch_mode<MODE_LOGODDS>(e, p);
+    CU(e, cudaGetLastError());
+    return IPP_OK;
+}
+
+static int validate_step_args(ipp_engine *e, const void *ids, const void *poses, const char *who) {
+    if (!e) return IPP_ERR_INVALID;
+    if ((ids == nullptr) == (poses == nullptr)) return fail(e, IPP_ERR_INVALID, "%s: exactly one of action_ids / poses must be given", who);
+    return IPP_OK;
+}
+
+extern "C" int ipp_step_device(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise, int32_t noise_stride,
+                               float *reward, float *measurements, uint32_t flags) {
+    int rc = validate_step_args(e, action_ids, poses, "ipp_step_device");
+    if (rc != IPP_OK) return rc;
+    if ((noise || measurements) && noise_stride < e->max_meas)
+        return fail(e, IPP_ERR_INVALID, "ipp_step: noise_stride %d < max_measurements %d", noise_stride, e->max_meas);
+    StepParams p;
+    fill_params(e, p);
+    p.n_jobs = e->cfg.batch;
+    p.action_ids = action_ids;
+    p.poses = poses;
+    p.noise = noise;
+    p.noise_stride = noise_stride;
+    p.reward = reward;
+    p.z_out = measurements;
+    p.flags = flags;
+    rc = launch_step(e, p, (flags & IPP_FLAG_LOGODDS) ? MODE_LOGODDS : MODE_KALMAN);
+    if (rc == IPP_OK) e->steps++;
+    return rc;
+}
+
+static int ensure_job_buffers(ipp_engine *e, size_t n) {
+    if (e->cap_jobs >= n && e->d_actions && e->d_poses && e->d_prev_in && e->d_env_index && e->d_reward) return IPP_OK;
+    CU(e, cudaStreamSynchronize(e->stream));
+    void **ps[] = {(void **)&e->d_actions, (void **)&e->d_poses, (void **)&e->d_prev_in, (void **)&e->d_env_index, (void **)&e->d_reward};
+    for (void **pp : ps)
+        if (*pp) {
+            cudaFree(*pp);
+            *pp = nullptr;
+        }
+    e->cap_jobs = 0;
+    int rc;
+    if ((rc = dev_alloc(e, &e->d_actions, n)) != IPP_OK) return rc;
+    if ((rc = dev_alloc(e, &e->d_poses, 3 * n)) != IPP_OK) return rc;
+    if ((rc = dev_alloc(e, &e->d_prev_in, 3 * n)) != IPP_OK) return rc;
+    if ((rc = dev_alloc(e, &e->d_env_index, n)) != IPP_OK) return rc;
+    if ((rc = dev_alloc(e, &e->d_reward, n)) != IPP_OK) return rc;
+    e->cap_jobs = n;
+    return IPP_OK;
+}
+
+extern "C" int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise, int32_t noise_stride, float *reward,
+                        float *measurements, uint32_t flags) {
+    int rc = validate_step_args(e, action_ids, poses, "ipp_step");
+    if (rc != IPP_OK) return rc;
+    const size_t B = (size_t)e->cfg.batch;
+    if ((rc = ensure_job_buffers(e, B)) != IPP_OK) return rc;
+    if ((noise || measurements) && noise_stride < e->max_meas)
+        return fail(e, IPP_ERR_INVALID, "ipp_step: noise_stride %d < max_measurements %d", noise_stride, e->max_meas);
+    if (action_ids) CU(e, cudaMemcpyAsync(e->d_actions, action_ids, B * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    if (poses) CU(e, cudaMemcpyAsync(e->d_poses, poses, 3 * B * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (noise) {
+        if ((rc = ensure(e, &e->d_noise, &e->cap_noise, B * (size_t)noise_stride)) != IPP_OK) return rc;
+        CU(e, cudaMemcpyAsync(e->d_noise, noise, B * (size_t)noise_stride * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    }
+    if (measurements)
+        if ((rc = ensure(e, &e->d_z, &e->cap_z, B * (size_t)noise_stride)) != IPP_OK) return rc;
+    rc = ipp_step_device(e, action_ids ? e->d_actions : nullptr, poses ? e->d_poses : nullptr, noise ? e->d_noise : nullptr, noise_stride,
+                         e->d_reward, measurements ? e->d_z : nullptr, flags);
+    if (rc != IPP_OK) return rc;
+    if (reward) CU(e, cudaMemcpyAsync(reward, e->d_reward, B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (measurements) CU(e, cudaMemcpyAsync(measurements, e->d_z, B * (size_t)noise_stride * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    return check_status(e);
+}
+
+// Measurement only (Sensor.take_measurement, sensors/cameras.py:108-116) and update with a
+// caller-supplied measurement (Mapping.update_grid_map(pos, data), mapping/mappings.py:114-153):
+// the two halves of ipp_step for the B=1 facade, same kernel.
+extern "C" int ipp_measure(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise, int32_t stride,
+                           float *measurements, uint32_t flags) {
+    int rc = validate_step_args(e, action_ids, poses, "ipp_measure");
+    if (rc != IPP_OK) return rc;
+    if (!measurements) return fail(e, IPP_ERR_INVALID, "ipp_measure: measurements == NULL");
+    if (stride < e->max_meas) return fail(e, IPP_ERR_INVALID, "ipp_measure: stride %d < max_measurements %d", stride, e->max_meas);
+    const size_t B = (size_t)e->cfg.batch;
+    if ((rc = ensure_job_buffers(e, B)) != IPP_OK) return rc;
+    if ((rc = ensure(e, &e->d_z, &e->cap_z, B * (size_t)stride)) != IPP_OK) return rc;
+    if (action_ids) CU(e, cudaMemcpyAsync(e->d_actions, action_ids, B * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    if (poses) CU(e, cudaMemcpyAsync(e->d_poses, poses, 3 * B * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (noise) {
+        if ((rc = ensure(e, &e->d_noise, &e->cap_noise, B * (size_t)stride)) != IPP_OK) return rc;
+        CU(e, cudaMemcpyAsync(e->d_noise, noise, B * (size_t)stride * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    }
+    StepParams p;
+    fill_params(e, p);
+    p.n_jobs = e->cfg.batch;
+    p.action_ids = action_ids ? e->d_actions : nullptr;
+    p.poses = poses ? e->d_poses : nullptr;
+    p.noise = noise ? e->d_noise : nullptr;
+    p.noise_stride = stride;
+    p.z_out = e->d_z;
+    p.flags = flags;
+    p.measure_only = 1;
+    if ((rc = launch_step(e, p, MODE_KALMAN)) != IPP_OK) return rc;
+    if (!noise) e->steps++;  // a Philox draw was consumed
+    CU(e, cudaMemcpyAsync(measurements, e->d_z, B * (size_t)stride * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    return check_status(e);
+}
+
+extern "C" int ipp_update(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *measurements, int32_t stride,
+                          float *reward, uint32_t flags) {
+    int rc = validate_step_args(e, action_ids, poses, "ipp_update");
+    if (rc != IPP_OK) return rc;
+    if (!measurements) return fail(e, IPP_ERR_INVALID, "ipp_update: measurements == NULL");
+    if (stride < e->max_meas) return fail(e, IPP_ERR_INVALID, "ipp_update: stride %d < max_measurements %d", stride, e->max_meas);
+    const size_t B = (size_t)e->cfg.batch;
+    if ((rc = ensure_job_buffers(e, B)) != IPP_OK) return rc;
+    if ((rc = ensure(e, &e->d_z, &e->cap_z, B * (size_t)stride)) != IPP_OK) return rc;
+    if (action_ids) CU(e, cudaMemcpyAsync(e->d_actions, action_ids, B * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    if (poses) CU(e, cudaMemcpyAsync(e->d_poses, poses, 3 * B * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaMemcpyAsync(e->d_z, measurements, B * (size_t)stride * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    StepParams p;
+    fill_params(e, p);
+    p.n_jobs = e->cfg.batch;
+    p.action_ids = action_ids ? e->d_actions : nullptr;
+    p.poses = poses ? e->d_poses : nullptr;
+    p.z_in = e->d_z;
+    p.noise_stride = stride;
+    p.reward = e->d_reward;
+    p.flags = flags;
+    if ((rc = launch_step(e, p, (flags & IPP_FLAG_LOGODDS) ? MODE_LOGODDS : MODE_KALMAN)) != IPP_OK) return rc;
+    if (reward) CU(e, cudaMemcpyAsync(reward, e->d_reward, B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    return check_status(e);
+}
+
+extern "C" int ipp_predict_device(ipp_engine *e, int32_t n_jobs, const int32_t *env_index, const int32_t *action_ids, const double *poses,
+                                  const double *prev_poses, float *reward, uint32_t flags) {
+    int rc = validate_step_args(e, action_ids, poses, "ipp_predict_device");
+    if (rc != IPP_OK) return rc;
+    if (n_jobs < 0) return fail(e, IPP_ERR_INVALID, "ipp_predict: n_jobs < 0");
+    if (!env_index && n_jobs != e->cfg.batch) return fail(e, IPP_ERR_INVALID, "ipp_predict: env_index == NULL requires n_jobs == batch");
+    StepParams p;
+    fill_params(e, p);
+    p.n_jobs = n_jobs;
+    p.env_index = env_index;
+    p.action_ids = action_ids;
+    p.poses = poses;
+    p.prev_in = prev_poses;
+    p.reward = reward;
+    p.flags = flags;
+    return launch_step(e, p, MODE_PREDICT);
+}
+
+extern "C" int ipp_predict(ipp_engine *e, int32_t n_jobs, const int32_t *env_index, const int32_t *action_ids, const double *poses,
+                           const double *prev_poses, float *reward, uint32_t flags) {
+    int rc = validate_step_args(e, action_ids, poses, "ipp_predict");
+    if (rc != IPP_OK) return rc;
+    if (n_jobs < 0) return fail(e, IPP_ERR_INVALID, "ipp_predict: n_jobs < 0");
+    if (n_jobs == 0) return IPP_OK;
+    const size_t J = (size_t)n_jobs;
+    if (env_index) {
+        for (size_t j = 0; j < J; ++j)
+            if (env_index[j] < 0 || env_index[j] >= e->cfg.batch) return fail(e, IPP_ERR_INVALID, "ipp_predict: env_index[%zu] = %d outside batch", j, env_index[j]);
+    }
+    if ((rc = ensure_job_buffers(e, std::max(J, (size_t)e->cfg.batch))) != IPP_OK) return rc;
+    if (env_index) CU(e, cudaMemcpyAsync(e->d_env_index, env_index, J * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    if (action_ids) CU(e, cudaMemcpyAsync(e->d_actions, action_ids, J * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    if (poses) CU(e, cudaMemcpyAsync(e->d_poses, poses, 3 * J * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (prev_poses) CU(e, cudaMemcpyAsync(e->d_prev_in, prev_poses, 3 * J * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    rc = ipp_predict_device(e, n_jobs, env_index ? e->d_env_index : nullptr, action_ids ? e->d_actions : nullptr, poses ? e->d_poses : nullptr,
+                            prev_poses ? e->d_prev_in : nullptr, e->d_reward, flags);
+    if (rc != IPP_OK) return rc;
+    if (reward) CU(e, cudaMemcpyAsync(reward, e->d_reward, J * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    return check_status(e);
+}
+
+extern "C" int ipp_eval_device(ipp_engine *e, float *metrics) {
+    if (!e || !metrics) return IPP_ERR_INVALID;
+    eval_kernel<<<e->cfg.batch, kEvalThreads, 0, e->stream>>>(e->d_mean, e->d_var, e->d_gt, e->cfg.layout, e->plane, (float)e->cfg.value_threshold,
+                                                              metrics);
+    e->launches++;
+    CU(e, cudaGetLastError());
+    return IPP_OK;
+}
+
+extern "C" int ipp_eval(ipp_engine *e, float *metrics) {
+    if (!e || !metrics) return IPP_ERR_INVALID;
+    int rc = ipp_eval_device(e, e->d_metrics);
+    if (rc != IPP_OK) return rc;
+    CU(e, cudaMemcpyAsync(metrics, e->d_metrics, (size_t)e->cfg.batch * IPP_NUM_METRICS * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
+extern "C" void *ipp_device_ptr(ipp_engine *e, int32_t which) {
+    if (!e) return nullptr;
+    switch (which) {
+        case IPP_PTR_MEAN: return e->d_mean;
+        case IPP_PTR_VAR: return e->cfg.layout == IPP_LAYOUT_MV ? (void *)(e->d_mean + 1) : (void *)e->d_var;
+        case IPP_PTR_GT: return e->d_gt;
+        case IPP_PTR_REWARD:
+            if (ensure_job_buffers(e, (size_t)e->cfg.batch) != IPP_OK) return nullptr;
+            return e->d_reward;
+        case IPP_PTR_STREAM: return (void *)e->stream;
+        default: return nullptr;
+    }
+}
+
+extern "C" int ipp_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return IPP_ERR_INVALID;
+    return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? IPP_OK : IPP_ERR_NOMEM;
+}
+extern "C" int ipp_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? IPP_OK : IPP_ERR_CUDA; }
