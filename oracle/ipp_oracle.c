@@ -112,13 +112,13 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 static void device_normals(uint64_t seed, uint32_t env, uint64_t step, uint32_t group, double out[4]) {
     uint32_t c[4] = {group, env, (uint32_t)(step & 0xffffffffu), (uint32_t)(step >> 32)};
     philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
-    const double k = 1.0 / 4294967296.0, two_pi = 6.283185307179586476925286766559;
+    const double k = 1.0 / 4294967296.0, pi = 3.14159265358979323846;
     const double u0 = (c[0] + 0.5) * k, u1 = (c[1] + 0.5) * k, u2 = (c[2] + 0.5) * k, u3 = (c[3] + 0.5) * k;
     const double r0 = sqrt(-2.0 * log(u0)), r1 = sqrt(-2.0 * log(u2));
-    out[0] = r0 * cos(two_pi * u1);
-    out[1] = r0 * sin(two_pi * u1);
-    out[2] = r1 * cos(two_pi * u3);
-    out[3] = r1 * sin(two_pi * u3);
+    out[0] = r0 * cos(pi * (2.0 * u1 - 1.0));
+    out[1] = r0 * sin(pi * (2.0 * u1 - 1.0));
+    out[2] = r1 * cos(pi * (2.0 * u3 - 1.0));
+    out[3] = r1 * sin(pi * (2.0 * u3 - 1.0));
 }
 
 /*

@@ -554,8 +554,9 @@ def device_normals(seed: int, env: int, step: int, n_groups: int) -> np.ndarray:
     Group g (one 2x2 cell quad at rf=1, one measurement block at rf=2 — see
     ``device_noise_field``) draws ``philox4x32_10(counter=(g, env, step, 0), key=seed)``;
     uniforms ``u = (x + 0.5) * 2^-32`` in (0, 1); Box-Muller pairs:
-    ``n0, n1 = r(u0) * (cos, sin)(2 pi u1)``, ``n2, n3 = r(u2) * (cos, sin)(2 pi u3)``,
-    ``r(u) = sqrt(-2 ln u)``."""
+    ``n0, n1 = r(u0) * (cos, sin)(pi (2 u1 - 1))``, ``n2, n3 = r(u2) * (cos, sin)(pi (2 u3 - 1))``,
+    ``r(u) = sqrt(-2 ln u)`` (angle in [-pi, pi): the range where the GPU's SFU sin/cos are most
+    accurate)."""
     ctr = np.zeros((n_groups, 4), dtype=np.uint32)
     ctr[:, 0] = np.arange(n_groups, dtype=np.uint32)
     ctr[:, 1] = np.uint32(env)
@@ -565,8 +566,8 @@ def device_normals(seed: int, env: int, step: int, n_groups: int) -> np.ndarray:
     u = (x + 0.5) * (2.0 ** -32)
     r0 = np.sqrt(-2.0 * np.log(u[:, 0]))
     r1 = np.sqrt(-2.0 * np.log(u[:, 2]))
-    a0 = 2.0 * np.pi * u[:, 1]
-    a1 = 2.0 * np.pi * u[:, 3]
+    a0 = np.pi * (2.0 * u[:, 1] - 1.0)
+    a1 = np.pi * (2.0 * u[:, 3] - 1.0)
     return np.stack([r0 * np.cos(a0), r0 * np.sin(a0), r1 * np.cos(a1), r1 * np.sin(a1)], axis=-1)
 
 
