@@ -210,6 +210,25 @@ int ipp_eval_device(ipp_engine *e, float *metrics);
 #define IPP_PTR_STREAM 4 /* the cudaStream_t the engine launches on */
 void *ipp_device_ptr(ipp_engine *e, int32_t which);
 
+/* Runtime options.
+ * IPP_OPT_STEP_PATH selects the kernel ipp_step uses for Kalman steps on action ids:
+ *   IPP_PATH_ASYNC (default) persistent kernel, footprints staged with cp.async, double buffered
+ *                            per warp (MV layout; falls back to LSU otherwise)
+ *   IPP_PATH_LSU             general warp-per-env gather kernel (every mode / input form)
+ *   IPP_PATH_TMA             persistent kernel with TMA box copies (MV layout, x_dim % 4 == 0;
+ *                            kept for reference — slower on these narrow footprints)
+ * ipp_get_option(IPP_OPT_STEP_PATH) returns the path in effect; IPP_OPT_LAUNCHES_* (read only) count
+ * the step launches per path.  The environment variable IPP_STEP_PATH=lsu|async|tma sets the default. */
+#define IPP_PATH_LSU 0
+#define IPP_PATH_ASYNC 1
+#define IPP_PATH_TMA 2
+#define IPP_OPT_STEP_PATH 1
+#define IPP_OPT_LAUNCHES_LSU 2
+#define IPP_OPT_LAUNCHES_ASYNC 3
+#define IPP_OPT_LAUNCHES_TMA 4
+int ipp_set_option(ipp_engine *e, int32_t option, int64_t value);
+int64_t ipp_get_option(const ipp_engine *e, int32_t option);
+
 /* Pinned host memory for the host entry points (cudaHostAlloc). */
 int ipp_host_alloc(void **ptr, size_t bytes);
 int ipp_host_free(void *ptr);

@@ -35,6 +35,9 @@ MAX_ALTITUDE_LEVELS = 32
 NUM_METRICS = 8
 
 PTR_MEAN, PTR_VAR, PTR_GT, PTR_REWARD, PTR_STREAM = range(5)
+PATH_LSU, PATH_ASYNC, PATH_TMA = 0, 1, 2
+OPT_STEP_PATH = 1
+OPT_LAUNCHES_LSU, OPT_LAUNCHES_ASYNC, OPT_LAUNCHES_TMA = 2, 3, 4
 
 
 class IppLibraryError(RuntimeError):
@@ -124,6 +127,8 @@ SIGNATURES = {
     "ipp_eval": (C.c_int, [_P, _P]),
     "ipp_eval_device": (C.c_int, [_P, _P]),
     "ipp_device_ptr": (_P, [_P, _I32]),
+    "ipp_set_option": (C.c_int, [_P, _I32, C.c_int64]),
+    "ipp_get_option": (C.c_int64, [_P, _I32]),
     "ipp_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "ipp_host_free": (C.c_int, [_P]),
 }

@@ -1,0 +1,333 @@
+// quad_math.cuh — device helpers shared by the two step kernels (step_kernel.cuh: LSU gather,
+// step_tma.cuh: TMA-staged persistent pipeline): parameters, action decode / footprint, sensor
+// model, counter-based RNG, cv2 INTER_AREA taps, the per-quad Kalman fusion and the cost model.
+//
+// Reference semantics reproduced here (paths under the reference tree):
+//   footprint            sensors/cameras.py:34-75
+//   resolution factor    sensors/cameras.py:122-125
+//   sigma2(h), R         sensors/models/sensor_models.py:27-36
+//   measurement blocks   sensors/models/sensor_models.py:54-81  (partial block weight 1/rf)
+//   measurement          simulations/simulations.py:26-34, simulations/sensor_manipulations.py:7-57
+//                        (cv2 INTER_AREA incl. the dsize swap; noise variance used as std; clip)
+//   Kalman update        mapping/mappings.py:155-197 restricted to a diagonal covariance
+//   adaptive mask/reward planning/common/rewards.py:8-31
+//   cost                 planning/common/actions.py:8-41
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/ipp_b200.h"
+
+namespace ipp {
+
+// kernel modes (template parameter)
+constexpr int MODE_KALMAN = 0;   // full step: measure + mean/var update + reward
+constexpr int MODE_PREDICT = 1;  // covariance-only (simulate_prediction_step)
+constexpr int MODE_LOGODDS = 2;  // extension: log-odds fusion + Shannon entropy
+
+struct AltLevel {
+    double alt;   // altitude [m]
+    int rx, ry;   // footprint radius in cells
+    int rf;       // resolution factor
+    float s2;     // sigma2(h)
+    float R;      // rf^3 * sigma2(h)
+    int pad;
+};
+
+struct StepParams {
+    // belief / world (layout PLANES: mean, var separate; layout MV: mean points at float2 base)
+    float *mean;
+    float *var;
+    const float *gt;
+    size_t plane;  // y_dim * x_dim
+    int X, Y;
+    int n_jobs;
+    int batch;
+    // per-job inputs
+    const int32_t *env_index;   // nullable
+    const int32_t *action_ids;  // one of action_ids / poses
+    const double *poses;
+    const double *prev_in;      // nullable: explicit previous actions [n_jobs][3]
+    double *prev_state;         // engine previous actions [batch][3]
+    const float *noise;         // nullable -> Philox
+    const float *z_in;          // nullable: measurements supplied by the caller
+    float *z_out;               // nullable
+    int noise_stride;
+    float *reward;              // nullable (measure-only)
+    int *status;                // device status word (bit 0: unsupported up-sampling footprint)
+    // configuration
+    double res, tan_x, tan_y, coeff_a, coeff_b, rf_alt;
+    float inv_v, inv_a, d_acc_max;  // 1/max_v, 1/max_a, max_v^2 / (2 max_a)
+    float thr, kappa;
+    int cost_mode;
+    int n_levels;
+    float inv_N, inv_X;  // 1/(X*Y), 1/X for the action-id decode
+    uint32_t flags;
+    uint32_t measure_only;
+    uint32_t seed_lo, seed_hi, step_lo, step_hi;
+    uint32_t env_id_offset;
+    AltLevel lut[IPP_MAX_ALTITUDE_LEVELS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// counter-based RNG: Philox4x32-10 (Random123) + Box-Muller.  Mirrored in oracle/ipp_oracle.py
+// (device_normals / device_noise_field) and oracle/ipp_oracle.c.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// u = (x + 0.5) * 2^-32 in (0, 1)
+__device__ __forceinline__ float u01(uint32_t x) { return fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+// n0, n1 = sqrt(-2 ln u(a)) * (cos, sin)(pi * (2 u(b) - 1)); the angle lies in [-pi, pi) where the
+// SFU sin/cos have their best absolute accuracy (2^-21.4).
+// ln(u) on the SFU: lg2 is accurate to ~2^-22 ABSOLUTE, which is not enough next to u = 1 where ln u
+// itself is tiny, so that corner uses the series of ln(1 + t), t = u - 1 (exact in fp32 for u >= 0.5).
+__device__ __forceinline__ float fast_ln01(float u) {
+    const float t = u - 1.0f;
+    const float series = t * fmaf(t, fmaf(t, fmaf(t, -0.25f, 0.33333334f), -0.5f), 1.0f);
+    return t > -0.03125f ? series : 0.69314718f * __log2f(u);
+}
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, float &n1) {
+    const float r2 = fmaxf(-2.0f * fast_ln01(u01(a)), 1.0e-30f);
+    const float r = r2 * rsqrtf(r2);
+    const float th = 3.14159265358979f * fmaf(2.0f, u01(b), -1.0f);
+    n0 = r * __cosf(th);
+    n1 = r * __sinf(th);
+}
+
+// floor(n / d) for 0 <= n < 2^31, d >= 1 and n/d < 2^20: float estimate (error < 1) + one correction.
+__device__ __forceinline__ int fdiv(int n, int d, float inv_d) {
+    int q = (int)(__int2float_rz(n) * inv_d);
+    const int r = n - q * d;
+    q += (r >= d) ? 1 : 0;
+    q -= (r < 0) ? 1 : 0;
+    return q;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ---------------------------------------------------------------------------------------------
+// per-job geometry (footprint, sensor model) — computed redundantly by every lane (SIMT: one
+// issue slot either way); integer / fp64 so that floor() and the clip agree with NumPy bit for bit.
+// ---------------------------------------------------------------------------------------------
+struct Geom {
+    int xl, yu, nx, ny, rf;
+    float s2, R;
+    double px, py, ph;
+};
+
+// planning/common/actions.py:73-91: id = level*N + x_dim*col + row
+__device__ __forceinline__ void decode_id(const StepParams &p, int id_raw, int &lvl, int &col, int &row) {
+    const int N = p.X * p.Y;
+    const int id = clampi(id_raw, 0, p.n_levels * N - 1);
+    lvl = fdiv(id, N, p.inv_N);
+    const int i = id - lvl * N;
+    col = fdiv(i, p.X, p.inv_X);
+    row = i - col * p.X;
+    col = min(col, p.X - 1);
+    row = min(row, p.Y - 1);
+}
+
+__device__ __forceinline__ void clip_footprint(const StepParams &p, int cx, int cy, int rx, int ry, Geom &g) {
+    const long long xl = (long long)cx - rx, xr = (long long)cx + rx;
+    const long long yu = (long long)cy - ry, yd = (long long)cy + ry;
+    const int xli = (int)(xl < 0 ? 0 : (xl > p.X - 1 ? p.X - 1 : xl));
+    const int xri = (int)(xr < 0 ? 0 : (xr > p.X - 1 ? p.X - 1 : xr));
+    const int yui = (int)(yu < 0 ? 0 : (yu > p.Y - 1 ? p.Y - 1 : yu));
+    const int ydi = (int)(yd < 0 ? 0 : (yd > p.Y - 1 ? p.Y - 1 : yd));
+    g.xl = xli;
+    g.yu = yui;
+    g.nx = xri - xli + 1;
+    g.ny = ydi - yui + 1;
+}
+
+__device__ __forceinline__ Geom geom_from_cell(const StepParams &p, int lvl, int col, int row) {
+    Geom g;
+    const AltLevel &L = p.lut[lvl];
+    g.rf = L.rf;
+    g.s2 = L.s2;
+    g.R = L.R;
+    // pose = res*idx + res/2 (actions.py:80-83), same operation order as NumPy
+    g.px = __dadd_rn(__dmul_rn(p.res, (double)col), __dmul_rn(0.5, p.res));
+    g.py = __dadd_rn(__dmul_rn(p.res, (double)row), __dmul_rn(0.5, p.res));
+    g.ph = L.alt;
+    clip_footprint(p, col, row, L.rx, L.ry, g);
+    return g;
+}
+
+__device__ __forceinline__ Geom decode(const StepParams &p, int job) {
+    if (p.action_ids != nullptr) {
+        int lvl, col, row;
+        decode_id(p, __ldg(p.action_ids + job), lvl, col, row);
+        return geom_from_cell(p, lvl, col, row);
+    }
+    Geom g;
+    g.px = p.poses[3 * (size_t)job + 0];
+    g.py = p.poses[3 * (size_t)job + 1];
+    g.ph = p.poses[3 * (size_t)job + 2];
+    // sensors/cameras.py:44-45,62-66 — same operation order, no fma contraction.
+    const double xm = __dmul_rn(__dmul_rn(2.0, g.ph), p.tan_x);
+    const double ym = __dmul_rn(__dmul_rn(2.0, g.ph), p.tan_y);
+    const double wx = floor(__ddiv_rn(xm, p.res));
+    const double wy = floor(__ddiv_rn(ym, p.res));
+    const double fcx = floor(__ddiv_rn(g.px, p.res));
+    const double fcy = floor(__ddiv_rn(g.py, p.res));
+    const double frx = floor(__dmul_rn(0.5, wx));
+    const double fry = floor(__dmul_rn(0.5, wy));
+    const double lim = 1.0e9;
+    const int cx = (int)fmin(fmax(fcx, -lim), lim);
+    const int cy = (int)fmin(fmax(fcy, -lim), lim);
+    const int rx = (int)fmin(fmax(frx, 0.0), lim);
+    const int ry = (int)fmin(fmax(fry, 0.0), lim);
+    g.rf = g.ph > p.rf_alt ? 2 : 1;
+    const double s2 = p.coeff_a * (1.0 - exp(-p.coeff_b * g.ph));
+    g.s2 = (float)s2;
+    g.R = (float)((double)(g.rf * g.rf * g.rf) * s2);
+    clip_footprint(p, cx, cy, rx, ry, g);
+    return g;
+}
+
+// planning/common/actions.py:15-16 / 32-41.  The pose difference is formed in fp64; the norm and the
+// trapezoidal-profile time are fp32 (relative error ~1e-7, two orders below the parity tolerance).
+__device__ __forceinline__ float fast_sqrt(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
+
+__device__ __forceinline__ float job_cost(const StepParams &p, double px, double py, double ph, double qx, double qy, double qh) {
+    const float dx = (float)(px - qx), dy = (float)(py - qy), dz = (float)(ph - qh);
+    const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    if (p.cost_mode == IPP_COST_DISTANCE) return d;
+    const float d_acc = fminf(d * 0.5f, p.d_acc_max);  // min(d/2, v^2 / (2a))
+    const float d_const = d - 2.0f * d_acc;
+    return fmaf(d_const, p.inv_v, 2.0f * fast_sqrt(2.0f * d_acc * p.inv_a));
+}
+
+// One axis of cv2 INTER_AREA decimation: output sample o of n_out integrates the input over
+// [o*s, (o+1)*s), s = n_in/n_out.  Exact integer overlaps in units of 1/n_out; weight =
+// overlap / n_in.  (opencv resize.cpp computeResizeAreaTab; reference call site
+// simulations/sensor_manipulations.py:20-22.)  Entry = {first input index, w0, w1, w2}; count > 3
+// (scale > 2, only for clipped non-square footprints) is flagged with a negative start.
+__device__ __forceinline__ float4 make_tap_entry(int o, int n_in, int n_out) {
+    const int a1 = o * n_in, a2 = a1 + n_in;
+    const int start = a1 / n_out;
+    const int end = (a2 + n_out - 1) / n_out;  // exclusive
+    const float inv = 1.0f / (float)n_in;
+    float w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = start + k;
+        const int lo = max(a1, i * n_out), hi = min(a2, (i + 1) * n_out);
+        w[k] = hi > lo ? (float)(hi - lo) * inv : 0.0f;
+    }
+    return make_float4(__int_as_float(end - start > 3 ? -1 - start : start), w[0], w[1], w[2]);
+}
+
+// generic weight of input i for output o (slow path)
+__device__ __forceinline__ float tap_weight_generic(int o, int i, int n_in, int n_out) {
+    const int a1 = o * n_in, a2 = a1 + n_in;
+    const int lo = max(a1, i * n_out), hi = min(a2, (i + 1) * n_out);
+    return hi > lo ? (float)(hi - lo) / (float)n_in : 0.0f;
+}
+
+// Build the row / column tap tables of a rf=2 footprint in shared memory (one warp).  Returns true
+// when the fast 3-tap tables cannot be used (table overflow or an axis with scale > 2).
+template <int CAP>
+__device__ __forceinline__ bool build_tap_tables(float4 *tab /* [2*CAP] */, int lane, int ny, int nx, int out_r, int out_c) {
+    bool bad = out_r > CAP || out_c > CAP;
+    if (!bad) {
+        for (int idx = lane; idx < out_r + out_c; idx += 32) {
+            const bool is_row = idx < out_r;
+            const float4 e = is_row ? make_tap_entry(idx, ny, out_r) : make_tap_entry(idx - out_r, nx, out_c);
+            tab[is_row ? idx : CAP + idx - out_r] = e;
+            bad |= __float_as_int(e.x) < 0;
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+    return bad;
+}
+
+// Shannon entropy [nats] of Bernoulli(sigmoid(l)):  log1p(e^-|l|) + |l| e^-|l| / (1 + e^-|l|)
+__device__ __forceinline__ float bernoulli_entropy(float l) {
+    const float a = fabsf(l);
+    const float e = __expf(-a);
+    return log1pf(e) + a * e * __frcp_rn(1.0f + e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-quad fusion.  A quad = 2x2 cells {(r0,c0), (r0,c0+1), (r0+1,c0), (r0+1,c0+1)}; cells outside
+// the footprint carry m = v = 0 and ok = false.  rf = 1: four scalar Kalman updates; rf = 2: one
+// block update with the reference's weight 1/4 (full block) or 1/2 (partial block).
+// Returns the quad's information gain (trace reduction, or 0.5*ln prod v/v' for the entropy mode)
+// over the cells selected by msk[].
+// ---------------------------------------------------------------------------------------------
+struct FuseCtx {
+    int rf;
+    float R, invR;
+    bool entropy;
+};
+
+__device__ __forceinline__ float kalman_quad(const FuseCtx &c, bool cok, bool rok, const float (&m)[4], const float (&v)[4],
+                                             const float (&z)[4], const bool (&msk)[4], float (&mn)[4], float (&vn)[4]) {
+    float gain_q = 0.0f;
+    if (c.rf == 1) {
+        float prod = 1.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float S = v[k] + c.R;
+            const float gain = v[k] * __frcp_rn(S);
+            vn[k] = gain * c.R;  // v R / (v + R)  ==  v - v^2/S, cancellation-free
+            mn[k] = fmaf(gain, z[k] - m[k], m[k]);
+            if (c.entropy)
+                prod *= msk[k] ? S * c.invR : 1.0f;  // v/v' = S/R
+            else
+                gain_q += msk[k] ? v[k] * gain : 0.0f;
+        }
+        if (c.entropy) gain_q = 0.5f * __logf(prod);
+    } else {
+        const int cnt = 1 + (int)cok + (int)rok + (int)(cok && rok);
+        const float w = cnt == 4 ? 0.25f : 0.5f;  // sensor_models.py:76-79
+        const float w2 = w * w;
+        const float sv = (v[0] + v[1]) + (v[2] + v[3]);
+        const float sm = (m[0] + m[1]) + (m[2] + m[3]);
+        const float S = fmaf(w2, sv, c.R);
+        const float invS = __frcp_rn(S);
+        const float innov = z[0] - w * sm;
+        float rest[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            rest[k] = fmaf(-w2, v[k], S);  // w^2 * sum_{j != k} v_j + R  > 0
+            const float vk_invS = v[k] * invS;
+            vn[k] = vk_invS * rest[k];
+            mn[k] = fmaf(w * vk_invS, innov, m[k]);
+            if (!c.entropy) gain_q += msk[k] ? w2 * v[k] * vk_invS : 0.0f;
+        }
+        if (c.entropy) {
+            // prod_k v_k / v'_k = prod_k S / rest_k over the masked cells
+            const float a = (msk[0] ? rest[0] : S) * (msk[1] ? rest[1] : S);
+            const float b = (msk[2] ? rest[2] : S) * (msk[3] ? rest[3] : S);
+            const float S2 = S * S;
+            gain_q = 0.5f * __logf((S2 * __frcp_rn(a)) * (S2 * __frcp_rn(b)));
+        }
+    }
+    return gain_q;
+}
+
+}  // namespace ipp

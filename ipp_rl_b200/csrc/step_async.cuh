@@ -1,0 +1,345 @@
+// step_async.cuh — the throughput path of the fused step (sm_100a): a persistent kernel whose warps
+// stage whole footprints in shared memory with asynchronous copies (cp.async / LDGSTS), double
+// buffered per warp, for the discrete action set (action ids, MV layout).
+//
+// Why: the footprint gather is latency bound when a warp waits for its own loads quad by quad
+// (ncu, v1: 21 % of HBM peak, 17 resident warps/SM, one third of a footprint in flight per warp).
+// Here every warp keeps the COMPLETE footprint of its next env in flight — {mean,var} tile with 8-byte
+// and ground-truth tile with 4-byte asynchronous copies, all 32 lanes issuing, no registers held —
+// while it fuses the env whose tiles have already landed.  Two slots per warp, cp.async group
+// accounting, no block-level synchronisation at all.  Work is handed out through a global ticket
+// counter (dynamic load balance: footprints are 81 / 289 / 529 cells), fetched one env ahead so that
+// neither the atomic nor the action-id load is ever waited for.  Up to 2 x 16 footprints (~140 KB)
+// are in flight per SM independent of register pressure.  Results go back with 64-bit stores.
+//
+// The loop body is kept small on purpose (ncu: the first version, 63 KB of SASS, spent most of its
+// time in instruction-fetch stalls): per-slot state lives in shared memory so that the body exists
+// once, rarely used paths are out of line, and index divisions use a 16-bit magic multiplier.
+//
+// (A TMA variant of the same pipeline — 3-D tensor-map box copies, step_tma.cuh — is kept for
+// reference: the TMA unit spends ~40 cycles per 100-200 B box row, which makes it slower than even
+// the plain LSU kernel on these narrow footprints; see profiles/ and DESIGN.md.)
+//
+//   grid  = #SMs (persistent, 1 CTA / SM), block = up to 16 warps, dynamic smem ~ 225 KB
+//   smem  = [warp][slot]{mv tile, gt tile} | [warp][slot] SlotCtl | [warp] INTER_AREA tap tables
+#pragma once
+#include "step_kernel.cuh"
+
+namespace ipp {
+
+constexpr int kAsyncSlots = 2;     // footprints in flight per warp
+constexpr int kAsyncTapCap = 16;   // tap-table entries per axis (footprints up to 32 cells wide)
+constexpr int kAsyncMaxWarps = 16;
+constexpr int kTicketChunk = 4;    // tickets taken per atomic
+
+struct AsyncParams {
+    StepParams base;
+    unsigned int *tickets;     // [2] ping-pong work counters
+    const float4 *level_taps;  // [n_levels][2 * kAsyncTapCap] tap tables of the unclipped footprints (nullable entries flagged)
+    int parity;                // counter consumed by this launch; the other one is zeroed for the next
+    int warps;                 // warps per CTA
+    int mv_tile_bytes;         // per-slot tile capacities (multiples of 16 B)
+    int gt_tile_bytes;
+    uint32_t level_taps_ok;    // bit k: level k has a usable 3-tap table
+};
+
+// per-(warp, slot) control block, written when the slot is filled, read when it is fused
+struct __align__(16) SlotCtl {
+    int job, lvl, col, row;
+    int xl, yu, nx, ny;
+    double prev[3];  // the env's previous action (cost term), fetched with cp.async
+    int pad[2];
+};
+static_assert(sizeof(SlotCtl) == 64, "SlotCtl layout");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// per-level tap tables of the unclipped (interior) footprints, built once at engine creation
+__global__ void build_level_taps_kernel(float4 *tabs, const int *out_dims /* [levels][4] = ny, nx, out_r, out_c */, uint32_t *ok_mask) {
+    const int k = blockIdx.x;
+    const int ny = out_dims[4 * k], nx = out_dims[4 * k + 1], out_r = out_dims[4 * k + 2], out_c = out_dims[4 * k + 3];
+    bool bad = true;
+    if (out_r >= 1 && out_c >= 1 && out_r <= ny && out_c <= nx)
+        bad = build_tap_tables<kAsyncTapCap>(tabs + (size_t)k * 2 * kAsyncTapCap, (int)threadIdx.x, ny, nx, out_r, out_c);
+    if (threadIdx.x == 0 && !bad) atomicOr(ok_mask, 1u << k);
+}
+
+// rarely taken: a clipped, non-square rf=2 footprint with a decimation scale above 2 (more than 3 taps)
+__device__ __noinline__ float downsample_generic(const float *gt_t, int pitch, int pr, int pc, int ny, int nx, int out_r, int out_c) {
+    const int rs = (pr * ny) / out_r, re = ((pr + 1) * ny + out_r - 1) / out_r;
+    const int cs = (pc * nx) / out_c, ce = ((pc + 1) * nx + out_c - 1) / out_c;
+    float d = 0.0f;
+    for (int a = rs; a < re; ++a) {
+        const float *rowp = gt_t + min(a, ny - 1) * pitch;
+        float rowsum = 0.0f;
+        for (int b = cs; b < ce; ++b) rowsum = fmaf(tap_weight_generic(pc, b, nx, out_c), rowp[min(b, nx - 1)], rowsum);
+        d = fmaf(tap_weight_generic(pr, a, ny, out_r), rowsum, d);
+    }
+    return d;
+}
+
+__global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(const __grid_constant__ AsyncParams ap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const StepParams &p = ap.base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int stage_bytes = ap.mv_tile_bytes + ap.gt_tile_bytes;
+    unsigned char *my_stages = smem_raw + (size_t)w * kAsyncSlots * stage_bytes;
+    unsigned char *after = smem_raw + (size_t)ap.warps * kAsyncSlots * stage_bytes;
+    SlotCtl *ctl = reinterpret_cast<SlotCtl *>(after) + w * kAsyncSlots;
+    float4 *taps = reinterpret_cast<float4 *>(after + (size_t)ap.warps * kAsyncSlots * sizeof(SlotCtl)) + w * 2 * kAsyncTapCap;
+
+    unsigned int *ticket = ap.tickets + ap.parity;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ap.tickets[ap.parity ^ 1] = 0u;  // for the next launch
+
+    const int n_jobs = p.n_jobs;
+    const bool quirk = (p.flags & IPP_FLAG_NO_DSIZE_QUIRK) == 0;
+    const bool adaptive = (p.flags & IPP_FLAG_ADAPTIVE) != 0;
+    const bool entropy = (p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY;
+    const bool keep_prev = (p.flags & IPP_FLAG_KEEP_PREV) != 0;
+    const int X = p.X;
+    float2 *mv_base = reinterpret_cast<float2 *>(p.mean);
+
+    // Start the asynchronous copies of job's footprint into slot s (all lanes), one commit group.
+    auto fill = [&](int s, int job, int id) {
+        if (job >= 0) {
+            int lvl, col, row;
+            decode_id(p, id, lvl, col, row);
+            const AltLevel &L = p.lut[lvl];
+            const int xl = max(col - L.rx, 0), xr = min(col + L.rx, X - 1);
+            const int yu = max(row - L.ry, 0), yd = min(row + L.ry, p.Y - 1);
+            const int nx = xr - xl + 1, ny = yd - yu + 1;
+            const int pitch = (nx + 1) & ~1;
+            SlotCtl *c = ctl + s;
+            if (lane == 0) {
+                *reinterpret_cast<int4 *>(&c->job) = make_int4(job, lvl, col, row);
+                *reinterpret_cast<int4 *>(&c->xl) = make_int4(xl, yu, nx, ny);
+            }
+            if (lane < 3) cp_async_8(smem_u32(&c->prev[lane]), p.prev_state + 3 * (size_t)job + lane);
+            // lanes are laid out as RP row-segments of W columns: a warp instruction covers RP rows of the
+            // footprint, each a coalesced run of 32 B sectors; addresses advance by constant strides
+            const int W = nx <= 8 ? 8 : (nx <= 16 ? 16 : 32);
+            const int RP = 32 / W;
+            const int lr = lane / W, lc = lane - lr * W;
+            const size_t org = (size_t)job * p.plane + (size_t)(yu * X + xl);
+            for (int c0 = lc; c0 < nx; c0 += 32) {  // one pass unless the footprint is wider than 32 cells
+                const float2 *src_mv = mv_base + org + (size_t)(lr * X + c0);
+                const float *src_gt = p.gt + org + (size_t)(lr * X + c0);
+                uint32_t dst_mv = smem_u32(my_stages + (size_t)s * stage_bytes) + 8u * (uint32_t)(lr * pitch + c0);
+                uint32_t dst_gt = smem_u32(my_stages + (size_t)s * stage_bytes) + (uint32_t)ap.mv_tile_bytes + 4u * (uint32_t)(lr * pitch + c0);
+                for (int r = lr; r < ny; r += RP) {
+                    cp_async_8(dst_mv, src_mv);
+                    cp_async_4(dst_gt, src_gt);
+                    src_mv += RP * X;
+                    src_gt += RP * X;
+                    dst_mv += 8u * (uint32_t)(RP * pitch);
+                    dst_gt += 4u * (uint32_t)(RP * pitch);
+                }
+            }
+        }
+        cp_async_commit();  // always: keeps the group count in step with the slot rotation
+    };
+
+    // ---- prologue: one ticket chunk; fill both slots ---------------------------------------------
+    unsigned int chunk_base = 0;
+    if (lane == 0) chunk_base = atomicAdd(ticket, (unsigned)kTicketChunk);
+    chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
+    int chunk_used = 3;
+    int next_job[kAsyncSlots];  // job resident in each slot (-1: none); mirrors SlotCtl::job
+#pragma unroll
+    for (int s = 0; s < kAsyncSlots; ++s) {
+        const unsigned int t = chunk_base + s;
+        next_job[s] = t < (unsigned)n_jobs ? (int)t : -1;
+        const int id = next_job[s] >= 0 ? __ldg(p.action_ids + next_job[s]) : 0;
+        fill(s, next_job[s], id);
+    }
+    int cur_job = next_job[0], other_job = next_job[1];
+    unsigned int tk = chunk_base + 2;  // ticket whose action id has not been loaded yet
+    int s = 0;
+
+#pragma unroll 1
+    while (cur_job >= 0) {
+        // (A) start the next fetches early: action id of ticket tk and, when the chunk is used up, a fresh
+        //     chunk of tickets — both are consumed only after this env has been fused
+        const int job_n = tk < (unsigned)n_jobs ? (int)tk : -1;
+        const int id_n = job_n >= 0 ? __ldg(p.action_ids + job_n) : 0;
+        const bool need_chunk = chunk_used == kTicketChunk;
+        unsigned int fresh = 0;
+        if (need_chunk && lane == 0) fresh = atomicAdd(ticket, (unsigned)kTicketChunk);
+
+        cp_async_wait<kAsyncSlots - 1>();  // this lane's copies into slot s have landed
+        __syncwarp();                      // ... and so have every other lane's (and lane 0's SlotCtl)
+
+        // (B) fuse the env whose tiles sit in slot s
+        const SlotCtl *c = ctl + s;
+        const int4 c0v = *reinterpret_cast<const int4 *>(&c->job);
+        const int4 c1v = *reinterpret_cast<const int4 *>(&c->xl);
+        const int job = c0v.x, lvl = c0v.y;
+        const int xl = c1v.x, yu = c1v.y, nx = c1v.z, ny = c1v.w;
+        const AltLevel &L = p.lut[lvl];
+        const int rf = L.rf;
+        const float s2 = L.s2;
+        const int pitch = (nx + 1) & ~1;
+        const int nqx = (nx + 1) >> 1, nqy = (ny + 1) >> 1;
+        const int nq = nqx * nqy;
+        const int out_r = quirk ? nqx : nqy, out_c = quirk ? nqy : nqx;
+        const unsigned char *st = my_stages + (size_t)s * stage_bytes;
+        const float2 *mv_t = reinterpret_cast<const float2 *>(st);
+        const float *gt_t = reinterpret_cast<const float *>(st + ap.mv_tile_bytes);
+
+        // INTER_AREA tap tables: the per-level table when the footprint is unclipped, else built here
+        const float4 *tapr = taps, *tapc = taps + kAsyncTapCap;
+        bool generic_taps = false, unsupported = false;
+        if (rf == 2) {
+            unsupported = out_r > ny || out_c > nx;
+            const bool interior = nx == 2 * L.rx + 1 && ny == 2 * L.ry + 1 && ((ap.level_taps_ok >> lvl) & 1u) && (quirk || nqx == nqy);
+            if (interior) {
+                tapr = ap.level_taps + (size_t)lvl * 2 * kAsyncTapCap;
+                tapc = tapr + kAsyncTapCap;
+            } else if (!unsupported) {
+                generic_taps = build_tap_tables<kAsyncTapCap>(taps, lane, ny, nx, out_r, out_c);
+            }
+        }
+
+        FuseCtx fc;
+        fc.rf = rf;
+        fc.R = L.R;
+        fc.invR = __frcp_rn(L.R);
+        fc.entropy = entropy;
+        // q / nqx and q / out_c with a 16-bit magic multiplier (exact for q * d < 65536), else float path
+        const bool small = nq * max(nqx, out_c) < 65536;
+        const uint32_t magic_x = 65536u / (uint32_t)nqx + 1u, magic_c = 65536u / (uint32_t)out_c + 1u;
+        const float inv_nqx = __frcp_rn((float)nqx), inv_outc = __frcp_rn((float)out_c);
+        float2 *mv_g = mv_base + (size_t)job * p.plane + (size_t)(yu * X + xl);
+        const size_t nrow = (size_t)job * (size_t)p.noise_stride;
+        float acc = 0.0f;
+
+        if (unsupported) {
+            if (lane == 0) atomicOr(p.status, 1);
+        } else {
+            for (int q = lane; q < nq; q += 32) {
+                const int qy = small ? (int)(((uint32_t)q * magic_x) >> 16) : fdiv(q, nqx, inv_nqx);
+                const int qx = q - qy * nqx;
+                const int r0 = 2 * qy, c0 = 2 * qx;
+                const bool cok = c0 + 1 < nx, rok = r0 + 1 < ny;
+                const bool ok[4] = {true, cok, rok, cok && rok};
+
+                // ---- belief from the staged tile: two 128-bit shared loads (pitch is even) -------
+                const float4 top = *reinterpret_cast<const float4 *>(mv_t + r0 * pitch + c0);
+                const float4 bot = *reinterpret_cast<const float4 *>(mv_t + (r0 + 1) * pitch + c0);
+                const float m[4] = {top.x, cok ? top.z : 0.0f, rok ? bot.x : 0.0f, ok[3] ? bot.z : 0.0f};
+                const float v[4] = {top.y, cok ? top.w : 0.0f, rok ? bot.y : 0.0f, ok[3] ? bot.w : 0.0f};
+
+                // ---- measurement -----------------------------------------------------------------
+                float z[4] = {0.f, 0.f, 0.f, 0.f};
+                float eps[4];
+                if (p.noise != nullptr) {
+                    if (rf == 1) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) eps[k] = ok[k] ? __ldg(p.noise + nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)) : 0.0f;
+                    } else {
+                        eps[0] = __ldg(p.noise + nrow + q);
+                    }
+                } else {
+                    uint32_t rnd[4];
+                    philox4x32_10((uint32_t)q, (uint32_t)job + p.env_id_offset, p.step_lo, p.step_hi, p.seed_lo, p.seed_hi, rnd);
+                    box_muller(rnd[0], rnd[1], eps[0], eps[1]);
+                    if (rf == 1) box_muller(rnd[2], rnd[3], eps[2], eps[3]);
+                }
+                if (rf == 1) {
+                    const float2 g0 = *reinterpret_cast<const float2 *>(gt_t + r0 * pitch + c0);
+                    const float2 g1 = *reinterpret_cast<const float2 *>(gt_t + (r0 + 1) * pitch + c0);
+                    const float gv[4] = {g0.x, g0.y, g1.x, g1.y};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) z[k] = ok[k] ? __saturatef(fmaf(s2, eps[k], gv[k])) : 0.0f;
+                } else {
+                    int pr = qy, pc = qx;
+                    if (out_c != nqx) {
+                        pr = small ? (int)(((uint32_t)q * magic_c) >> 16) : fdiv(q, out_c, inv_outc);
+                        pc = q - pr * out_c;
+                    }
+                    float d = 0.0f;
+                    if (!generic_taps) {
+                        const float4 tr = tapr[pr], tc = tapc[pc];
+                        const int rs = __float_as_int(tr.x), cs = __float_as_int(tc.x);
+                        const float wr[3] = {tr.y, tr.z, tr.w};
+                        const int cb[3] = {cs, min(cs + 1, nx - 1), min(cs + 2, nx - 1)};
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            const float *rowp = gt_t + min(rs + a, ny - 1) * pitch;
+                            const float rowsum = fmaf(tc.w, rowp[cb[2]], fmaf(tc.z, rowp[cb[1]], tc.y * rowp[cb[0]]));
+                            d = fmaf(wr[a], rowsum, d);
+                        }
+                    } else {
+                        d = downsample_generic(gt_t, pitch, pr, pc, ny, nx, out_r, out_c);
+                    }
+                    z[0] = __saturatef(fmaf(s2, eps[0], d));
+                }
+                if (p.z_out != nullptr) {
+                    if (rf == 1) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (ok[k]) p.z_out[nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)] = z[k];
+                    } else {
+                        p.z_out[nrow + q] = z[0];
+                    }
+                }
+
+                // ---- fusion + reward, results straight to HBM --------------------------------------
+                float mn[4], vn[4];
+                bool msk[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) msk[k] = ok[k] && (!adaptive || (fmaf(p.kappa, v[k], m[k]) >= p.thr));
+                acc += kalman_quad(fc, cok, rok, m, v, z, msk, mn, vn);
+                float2 *o = mv_g + r0 * X + c0;
+                o[0] = make_float2(mn[0], vn[0]);
+                if (cok) o[1] = make_float2(mn[1], vn[1]);
+                if (rok) o[X] = make_float2(mn[2], vn[2]);
+                if (ok[3]) o[X + 1] = make_float2(mn[3], vn[3]);
+            }
+        }
+
+        // per-env information gain: fp32 partials per lane (<= 17 quads), fp64 tree across the warp
+        double accd = (double)acc;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, sft);
+        if (lane == 0) {
+            const double px = __dadd_rn(__dmul_rn(p.res, (double)c0v.z), __dmul_rn(0.5, p.res));
+            const double py = __dadd_rn(__dmul_rn(p.res, (double)c0v.w), __dmul_rn(0.5, p.res));
+            const float cost = job_cost(p, px, py, L.alt, c->prev[0], c->prev[1], c->prev[2]);
+            if (p.reward != nullptr) p.reward[job] = (float)accd * __frcp_rn(cost + 1.0f);
+            if (!keep_prev) {
+                double *ps = p.prev_state + 3 * (size_t)job;
+                ps[0] = px;
+                ps[1] = py;
+                ps[2] = L.alt;
+            }
+        }
+        __syncwarp();  // every lane is done with slot s (tiles, SlotCtl, tap tables)
+
+        // (C) refill slot s with the job resolved at (A); (D) next ticket to resolve
+        fill(s, job_n, id_n);
+        if (need_chunk) {
+            chunk_base = __shfl_sync(0xffffffffu, fresh, 0);
+            chunk_used = 0;
+        }
+        tk = chunk_base + (unsigned)chunk_used;
+        ++chunk_used;
+        cur_job = other_job;
+        other_job = job_n;
+        s ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace ipp

@@ -184,6 +184,22 @@ class BatchedEngine:
     def sync(self) -> None:
         self._ck(self._lib.ipp_sync(self._h))
 
+    # -- kernel path selection ------------------------------------------------------------------
+    PATHS = {"lsu": capi.PATH_LSU, "async": capi.PATH_ASYNC, "tma": capi.PATH_TMA}
+
+    def set_step_path(self, path: str) -> None:
+        """Request the step kernel: "async" (default, cp.async-staged persistent kernel), "lsu" (general
+        gather kernel) or "tma" (TMA box copies).  Unavailable paths fall back (see ``step_path``)."""
+        self._ck(self._lib.ipp_set_option(self._h, capi.OPT_STEP_PATH, self.PATHS[path]))
+
+    @property
+    def step_path(self) -> str:
+        v = self._lib.ipp_get_option(self._h, capi.OPT_STEP_PATH)
+        return {b: a for a, b in self.PATHS.items()}[int(v)]
+
+    def path_launches(self, path: str) -> int:
+        return int(self._lib.ipp_get_option(self._h, capi.OPT_LAUNCHES_LSU + self.PATHS[path]))
+
     # -- reset / world -------------------------------------------------------------------------
     def reset(self, prior_mean: float = 0.5, prior_var: float = 1.82, prior_var_per_env=None, init_pose=None) -> None:
         pv = None if prior_var_per_env is None else _f32(prior_var_per_env, (self.batch,))

@@ -1,0 +1,181 @@
+"""GPU tests of the persistent (cp.async- and TMA-staged) kernels and of the full-size workload.
+
+* the persistent paths must reproduce the general LSU kernel bit for bit (same arithmetic, different staging);
+* it must match the reference-pinned oracle on the 200x200 windowed golden vectors driven by ACTION IDS;
+* size-independent properties at BASELINE.json's full size (65 536 envs x 200x200): untouched cells stay
+  bit-identical, variance never grows, reward * (cost + 1) equals the drop of the per-env trace computed by
+  the independent eval kernel ("checksum of checksums"), determinism, sharding invariance.
+"""
+import numpy as np
+import pytest
+
+from oracle import ipp_oracle as orc
+from tests._util import engine_cfg, golden, make_params, oracle_cfg, params_from_json, smooth_field
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(params, batch, **kw):
+    from ipp_rl_b200 import BatchedEngine
+
+    return BatchedEngine(engine_cfg(params, batch, **kw))
+
+
+@pytest.mark.parametrize("grid", [(40, 40, 1.0, 8, 20, 6), (24, 36, 1.0, 8, 20, 6), (200, 200, 1.0, 8, 20, 6), (64, 64, 2.0, 6, 30, 8)])
+@pytest.mark.parametrize("reward_mode,adaptive", [(0, False), (1, False), (0, True), (1, True)])
+def test_persistent_paths_are_bit_identical_to_lsu_path(grid, reward_mode, adaptive):
+    X, Y, res, a0, a1, da = grid
+    params = make_params(X, Y, res, a0, a1, da, kappa=0.25, thr=0.45)
+    B, T = 96, 4
+    rng = np.random.RandomState(3)
+    gt = np.stack([smooth_field(rng, (Y, X)) for _ in range(8)])[np.arange(B) % 8]
+    mean0 = rng.uniform(0, 1, (B, Y, X)).astype(np.float32)
+    var0 = rng.uniform(0.05, 2.0, (B, Y, X)).astype(np.float32)
+    out = {}
+    for path in ("lsu", "async", "tma"):
+        with _engine(params, B, layout=1, seed=99) as eng:
+            eng.set_step_path(path)
+            assert eng.step_path == path, "persistent paths must be available for MV layout with x_dim % 4 == 0"
+            eng.reset(0.5, 1.82)
+            eng.set_ground_truth(gt)
+            eng.set_state(mean0, var0)
+            r2 = np.random.RandomState(17)
+            rs, zs = [], []
+            for t in range(T):
+                ids = r2.randint(0, eng.num_actions, B).astype(np.int32)
+                if t == 1:  # borders / corners on purpose
+                    ids[:8] = [0, X - 1, X * (Y - 1), X * Y - 1, eng.num_actions - 1, eng.num_actions - X, X * Y, 2 * X * Y - 1][:8]
+                if t == 2:
+                    noise = r2.standard_normal((B, eng.max_measurements)).astype(np.float32)
+                    r, z = eng.step(ids, noise=noise, reward_mode=reward_mode, adaptive=adaptive, return_measurements=True)
+                    zs.append(z)
+                else:
+                    r = eng.step(ids, reward_mode=reward_mode, adaptive=adaptive)
+                rs.append(r.copy())
+            m, v = eng.get_state()
+            out[path] = (np.array(rs), m, v, eng.get_prev_pose(), zs[0])
+            assert eng.path_launches(path) == T
+    for path in ("async", "tma"):
+        for a, b in zip(out[path], out["lsu"]):
+            assert np.array_equal(a, b), path
+
+
+@pytest.mark.parametrize("path", ["async", "tma"])
+def test_persistent_windowed_golden_by_action_id(path):
+    """Reference-pinned T2 vectors (200x200) through the persistent paths: poses at cell centres -> action ids."""
+    g = golden("golden_windowed_T2.npz")
+    params = params_from_json(g["w200_cfg"])
+    n = 200
+    cfg = oracle_cfg(params)
+    poses = g["w200_poses"]
+    tbl = orc.enumerate_actions(cfg)
+    # keep the poses that are exact action-table entries
+    keep, ids = [], []
+    for k, q in enumerate(poses):
+        col, row = (q[0] - 0.5), (q[1] - 0.5)
+        if col == int(col) and row == int(row) and q[2] in (8, 14, 20):
+            i = int({8: 0, 14: 1, 20: 2}[int(q[2])] * n * n + n * int(col) + int(row))
+            assert np.array_equal(tbl[i], q)
+            keep.append(k)
+            ids.append(i)
+    assert len(keep) >= 8
+    K = len(keep)
+    var0 = np.random.RandomState(0).uniform(0.1, 2.0, (n, n))
+    mean0 = np.random.RandomState(1).uniform(0.0, 1.0, (n, n))
+    with _engine(params, K, layout=1) as eng:
+        eng.set_step_path(path)
+        assert eng.step_path == path
+        eng.reset(0.5, 1.0)
+        eng.set_ground_truth(np.broadcast_to(g["w200_gt"], (K, n, n)))
+        eng.set_state(np.broadcast_to(mean0, (K, n, n)), np.broadcast_to(var0, (K, n, n)))
+        eng.set_prev_pose(poses[keep])
+        stride = max(eng.max_measurements, 23 * 23)
+        noise = np.zeros((K, stride), np.float32)
+        noise[:, : 23 * 23] = g["w200_eps"][keep]
+        r, z = eng.step(np.array(ids, np.int32), noise=noise, return_measurements=True)
+        assert eng.path_launches(path) == 1
+        mean, var = eng.get_state()
+    for j, k in enumerate(keep):
+        xl, xr, yu, yd = g["w200_fov"][k]
+        ny, nx = yd - yu + 1, xr - xl + 1
+        m = int(np.prod(g["w200_zshape"][k]))
+        assert np.max(np.abs(z[j, :m] - g["w200_z"][k, :m])) <= 1e-5
+        assert np.max(np.abs(var[j, yu : yd + 1, xl : xr + 1] - g["w200_var_w"][k, :ny, :nx])) <= 1e-5
+        assert np.max(np.abs(mean[j, yu : yd + 1, xl : xr + 1] - g["w200_mean_w"][k, :ny, :nx])) <= 1e-5
+        assert abs(r[j] - g["w200_tr"][k]) <= 1e-5 * max(1.0, abs(g["w200_tr"][k]))
+        chk = var[j].copy()
+        chk[yu : yd + 1, xl : xr + 1] = var0.astype(np.float32)[yu : yd + 1, xl : xr + 1]
+        assert np.array_equal(chk, var0.astype(np.float32))
+
+
+@pytest.mark.parametrize("path", ["async", "lsu", "tma"])
+def test_full_size_properties(path):
+    """BASELINE.json C3 size: 65 536 envs x 200x200 (31.5 GB of maps in HBM)."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    B = 65536 if free > 60e9 else 8192
+    X = Y = 200
+    params = make_params(X, Y, 1.0, 8, 20, 6)
+    rng = np.random.RandomState(123)
+    with _engine(params, B, layout=1, seed=5) as eng:
+        eng.set_step_path(path)
+        eng.reset(0.5, 1.82)
+        eng.synth_ground_truth(77)
+        tr0 = eng.eval()[:, 4].astype(np.float64)
+        assert np.allclose(tr0, 1.82 * X * Y, rtol=1e-6)
+        sample = np.sort(rng.choice(B, 64, replace=False))
+        total_gain = np.zeros(B)
+        prev_state = {int(b): eng.get_state(int(b), 1) for b in sample}
+        for t in range(3):
+            ids = rng.randint(0, eng.num_actions, B).astype(np.int32)
+            prev = eng.get_prev_pose()
+            r = eng.step(ids, reward_mode=0).astype(np.float64)
+            assert np.all(r > 0) and np.all(np.isfinite(r))
+            cur = eng.get_prev_pose()
+            d = np.linalg.norm(cur - prev, axis=1)
+            d_acc = np.minimum(0.5 * d, 1.0)
+            cost = (d - 2 * d_acc) / 2.0 + 2 * np.sqrt(2 * d_acc / 2.0)
+            total_gain += r * (cost + 1)
+            cfg = oracle_cfg(params)
+            tbl_pose = lambda i: cur[i]  # noqa: E731
+            for b in sample:
+                b = int(b)
+                m1, v1 = eng.get_state(b, 1)
+                m0, v0 = prev_state[b]
+                xl, xr, yu, yd = orc.project_field_of_view(cfg, tbl_pose(b))
+                outside = np.ones((Y, X), bool)
+                outside[yu : yd + 1, xl : xr + 1] = False
+                assert np.array_equal(v1[0][outside], v0[0][outside]) and np.array_equal(m1[0][outside], m0[0][outside])
+                assert np.all(v1[0][~outside] < v0[0][~outside])
+                prev_state[b] = (m1, v1)
+        tr1 = eng.eval()[:, 4].astype(np.float64)
+        # checksum of checksums: trace drop measured by the eval kernel == accumulated step rewards
+        assert np.allclose(tr0 - tr1, total_gain, rtol=2e-4, atol=1e-2)
+        assert abs((tr0 - tr1).sum() - total_gain.sum()) <= 1e-5 * total_gain.sum()
+
+
+def test_sharding_invariance_and_determinism():
+    """An env's trajectory depends on (seed, global env id, step) only — not on how the batch is split."""
+    X = Y = 64
+    params = make_params(X, Y, 1.0, 8, 20, 6)
+    B = 256
+    rng = np.random.RandomState(8)
+    gt = np.stack([smooth_field(rng, (Y, X)) for _ in range(16)])[np.arange(B) % 16]
+    ids = rng.randint(0, 3 * X * Y, (3, B)).astype(np.int32)
+
+    def run(first, count, path="async"):
+        with _engine(params, count, layout=1, seed=42, env_id_offset=first) as eng:
+            eng.set_step_path(path)
+            eng.reset(0.5, 1.82)
+            eng.set_ground_truth(gt[first : first + count])
+            rs = [eng.step(ids[t, first : first + count]).copy() for t in range(3)]
+            return np.array(rs), eng.get_state()
+
+    r_all, (m_all, v_all) = run(0, B)
+    r_again, (m_again, _) = run(0, B)
+    assert np.array_equal(r_all, r_again) and np.array_equal(m_all, m_again)
+    for first, count in ((0, 64), (64, 128), (192, 64)):
+        r, (m, v) = run(first, count)
+        assert np.array_equal(r, r_all[:, first : first + count])
+        assert np.array_equal(m, m_all[first : first + count]) and np.array_equal(v, v_all[first : first + count])
