@@ -215,17 +215,13 @@ void *ipp_device_ptr(ipp_engine *e, int32_t which);
  *   IPP_PATH_ASYNC (default) persistent kernel, footprints staged with cp.async, double buffered
  *                            per warp (MV layout; falls back to LSU otherwise)
  *   IPP_PATH_LSU             general warp-per-env gather kernel (every mode / input form)
- *   IPP_PATH_TMA             persistent kernel with TMA box copies (MV layout, x_dim % 4 == 0;
- *                            kept for reference — slower on these narrow footprints)
  * ipp_get_option(IPP_OPT_STEP_PATH) returns the path in effect; IPP_OPT_LAUNCHES_* (read only) count
- * the step launches per path.  The environment variable IPP_STEP_PATH=lsu|async|tma sets the default. */
+ * the step launches per path.  The environment variable IPP_STEP_PATH=lsu|async sets the default. */
 #define IPP_PATH_LSU 0
 #define IPP_PATH_ASYNC 1
-#define IPP_PATH_TMA 2
 #define IPP_OPT_STEP_PATH 1
 #define IPP_OPT_LAUNCHES_LSU 2
 #define IPP_OPT_LAUNCHES_ASYNC 3
-#define IPP_OPT_LAUNCHES_TMA 4
 int ipp_set_option(ipp_engine *e, int32_t option, int64_t value);
 int64_t ipp_get_option(const ipp_engine *e, int32_t option);
 

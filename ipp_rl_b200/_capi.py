@@ -35,9 +35,9 @@ MAX_ALTITUDE_LEVELS = 32
 NUM_METRICS = 8
 
 PTR_MEAN, PTR_VAR, PTR_GT, PTR_REWARD, PTR_STREAM = range(5)
-PATH_LSU, PATH_ASYNC, PATH_TMA = 0, 1, 2
+PATH_LSU, PATH_ASYNC = 0, 1
 OPT_STEP_PATH = 1
-OPT_LAUNCHES_LSU, OPT_LAUNCHES_ASYNC, OPT_LAUNCHES_TMA = 2, 3, 4
+OPT_LAUNCHES_LSU, OPT_LAUNCHES_ASYNC = 2, 3
 
 
 class IppLibraryError(RuntimeError):

@@ -13,7 +13,6 @@
 #include <cstdlib>
 
 #include "step_async.cuh"
-#include "step_tma.cuh"
 
 using namespace ipp;
 
@@ -49,23 +48,16 @@ struct ipp_engine {
     int *h_status = nullptr;  // pinned
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    // TMA-staged persistent path (step_tma.cuh)
-    bool tma_ok = false;       // tensor maps built and usable for this configuration
     // cp.async-staged persistent path (step_async.cuh) and the path switch
     bool async_ok = false;
     int step_path = IPP_PATH_ASYNC;  // requested path (ipp_set_option / IPP_STEP_PATH)
     int async_warps = 0, async_mv_tile = 0, async_gt_tile = 0;
-    float4 *d_level_taps = nullptr;
-    uint32_t level_taps_ok = 0;
+    float2 *d_level_taps = nullptr;
+    int level_tap_mode[kLevelTabs] = {-1, -1, -1, -1};
     size_t async_smem = 0;
-    uint64_t path_launches[3] = {0, 0, 0};
-    CUtensorMap *d_maps = nullptr;
+    uint64_t path_launches[2] = {0, 0};
     unsigned int *d_tickets = nullptr;
-    int tma_parity = 0;
-    int tma_warps = 0;
-    int tma_mv_tile = 0, tma_gt_tile = 0;
-    size_t tma_smem = 0;
-    short tma_bw_mv[IPP_MAX_ALTITUDE_LEVELS]{}, tma_bw_gt[IPP_MAX_ALTITUDE_LEVELS]{}, tma_bh[IPP_MAX_ALTITUDE_LEVELS]{};
+    int ticket_parity = 0;
     uint64_t launches = 0;
     uint64_t steps = 0;
     uint64_t device_bytes = 0;
@@ -352,84 +344,9 @@ static int build_lut(ipp_engine *e) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA path set-up: one pair of 3-D tensor maps per altitude level (box = that level's footprint)
+// persistent-path set-up
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-// Returns IPP_OK and sets e->tma_ok when the persistent TMA kernel can serve this configuration;
-// leaves tma_ok == false (and still IPP_OK) when it cannot — the general LSU kernel is used then.
-static int setup_tma(ipp_engine *e) {
-    const ipp_config &c = e->cfg;
-    e->tma_ok = false;
-    if (c.layout != IPP_LAYOUT_MV) return IPP_OK;  // tiles are {mean,var}-interleaved
-    if (c.x_dim % 4 != 0) return IPP_OK;           // tensor-map strides must be multiples of 16 B
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
-        qres != cudaDriverEntryPointSuccess) {
-        cudaGetLastError();
-        return IPP_OK;
-    }
-    encode_tiled_fn encode = (encode_tiled_fn)fn;
-    const int X = c.x_dim, Y = c.y_dim, B = c.batch;
-    int max_mv = 0, max_gt = 0;
-    CUtensorMap host_maps[2 * IPP_MAX_ALTITUDE_LEVELS];
-    for (int k = 0; k < e->n_levels; ++k) {
-        const int fw = std::min(2 * e->lut[k].rx + 1, X), fh = std::min(2 * e->lut[k].ry + 1, Y);
-        const int bw_mv = round_up(fw + 1, 2), bw_gt = round_up(fw + 3, 4), bh = fh;  // aligned supersets
-        if (bw_gt > 128 || bh > 256) return IPP_OK;  // box limits (256 elements / dim)
-        e->tma_bw_mv[k] = (short)bw_mv;
-        e->tma_bw_gt[k] = (short)bw_gt;
-        e->tma_bh[k] = (short)bh;
-        max_mv = std::max(max_mv, round_up(bw_mv * bh * 8, 128));
-        // +1 row/col of slack: a quad may read one row/col past an odd footprint (masked afterwards)
-        max_gt = std::max(max_gt, round_up(bw_gt * bh * 4, 128));
-        const cuuint32_t estr[3] = {1, 1, 1};
-        {
-            const cuuint64_t gdim[3] = {(cuuint64_t)2 * X, (cuuint64_t)Y, (cuuint64_t)B};
-            const cuuint64_t gstr[2] = {(cuuint64_t)8 * X, (cuuint64_t)8 * X * Y};
-            const cuuint32_t box[3] = {(cuuint32_t)(2 * bw_mv), (cuuint32_t)bh, 1};
-            if (encode(&host_maps[2 * k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, e->d_mean, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                return IPP_OK;
-        }
-        {
-            const cuuint64_t gdim[3] = {(cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B};
-            const cuuint64_t gstr[2] = {(cuuint64_t)4 * X, (cuuint64_t)4 * X * Y};
-            const cuuint32_t box[3] = {(cuuint32_t)bw_gt, (cuuint32_t)bh, 1};
-            if (encode(&host_maps[2 * k + 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, e->d_gt, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                return IPP_OK;
-        }
-    }
-    // one extra row of slack per tile so that the (masked) read of row `ny` of an odd footprint stays
-    // inside the slot
-    max_mv = round_up(max_mv + 8 * 130, 128);
-    max_gt = round_up(max_gt + 4 * 130, 128);
-    const size_t per_warp = (size_t)kTmaSlots * (max_mv + max_gt) + kTmaSlots * sizeof(uint64_t) + 2 * kTmaTapCap * sizeof(float4);
-    int dev_smem = 0;
-    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device) != cudaSuccess) return IPP_OK;
-    int warps = (int)std::min<size_t>(kTmaMaxWarps, ((size_t)dev_smem - 1024) / per_warp);
-    if (warps < 4) return IPP_OK;  // footprints too large to pipeline in shared memory
-    e->tma_warps = warps;
-    e->tma_mv_tile = max_mv;
-    e->tma_gt_tile = max_gt;
-    e->tma_smem = per_warp * warps;
-    if (cudaFuncSetAttribute(ipp_step_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tma_smem) != cudaSuccess) {
-        cudaGetLastError();
-        return IPP_OK;
-    }
-    int rc;
-    if ((rc = dev_alloc(e, &e->d_maps, 2 * (size_t)e->n_levels)) != IPP_OK) return rc;
-    CU(e, cudaMemcpyAsync(e->d_maps, host_maps, 2 * (size_t)e->n_levels * sizeof(CUtensorMap), cudaMemcpyHostToDevice, e->stream));
-    CU(e, cudaStreamSynchronize(e->stream));
-    e->tma_ok = true;
-    return IPP_OK;
-}
 
 // cp.async-staged persistent path: needs the MV layout and footprints that fit two slots per warp.
 static int setup_async(ipp_engine *e) {
@@ -439,49 +356,48 @@ static int setup_async(ipp_engine *e) {
     if ((rc = dev_alloc(e, &e->d_tickets, 2)) != IPP_OK) return rc;
     CU(e, cudaMemsetAsync(e->d_tickets, 0, 2 * sizeof(unsigned int), e->stream));
     if (c.layout != IPP_LAYOUT_MV) return IPP_OK;
-    int max_cells = 0;  // pitch * (rows + 1): one row of slack for the masked read past an odd footprint
+    int max_cells = 0;  // even pitch * rows of the largest footprint
     for (int k = 0; k < e->n_levels; ++k) {
         const int fw = std::min(2 * e->lut[k].rx + 1, c.x_dim), fh = std::min(2 * e->lut[k].ry + 1, c.y_dim);
-        max_cells = std::max(max_cells, ((fw + 1) & ~1) * (fh + 1));
+        max_cells = std::max(max_cells, ((fw + 1) & ~1) * fh);
     }
     const int mv_tile = round_up(max_cells * 8, 16), gt_tile = round_up(max_cells * 4, 16);
-    const size_t per_warp = (size_t)kAsyncSlots * (mv_tile + gt_tile) + kAsyncSlots * sizeof(SlotCtl) + 2 * kAsyncTapCap * sizeof(float4);
+    const size_t per_warp = (size_t)kAsyncSlots * (mv_tile + gt_tile) + kAsyncSlots * sizeof(SlotCtl) + kTapFloats2 * sizeof(float2);
+    const size_t per_cta = (size_t)kLevelTabs * kTapFloats2 * sizeof(float2);
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device) != cudaSuccess) return IPP_OK;
-    const int warps = (int)std::min<size_t>(kAsyncMaxWarps, (size_t)dev_smem / per_warp);
-    if (warps < 4) return IPP_OK;  // footprints too large to pipeline in shared memory
+    if ((size_t)dev_smem < per_cta + 4 * per_warp) return IPP_OK;  // footprints too large to pipeline in shared memory
+    const int warps = (int)std::min<size_t>(kAsyncMaxWarps, ((size_t)dev_smem - per_cta) / per_warp);
     e->async_warps = warps;
     e->async_mv_tile = mv_tile;
     e->async_gt_tile = gt_tile;
-    e->async_smem = per_warp * warps;
+    e->async_smem = per_warp * warps + per_cta;
     if (cudaFuncSetAttribute(ipp_step_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->async_smem) != cudaSuccess) {
         cudaGetLastError();
         return IPP_OK;
     }
-    // tap tables of the unclipped footprint of every level (dsize-quirk orientation)
-    int h_dims[4 * IPP_MAX_ALTITUDE_LEVELS] = {0};
-    for (int k = 0; k < e->n_levels; ++k) {
+    // tap tables of the unclipped footprint of the first kLevelTabs levels (dsize-quirk orientation)
+    int h_dims[4 * kLevelTabs] = {0};
+    for (int k = 0; k < std::min(e->n_levels, kLevelTabs); ++k) {
         const int fw = 2 * e->lut[k].rx + 1, fh = 2 * e->lut[k].ry + 1;
-        if (e->lut[k].rf != 2 || fw > c.x_dim || fh > c.y_dim) continue;  // out dims stay 0 -> table flagged unusable
+        if (e->lut[k].rf != 2 || fw > c.x_dim || fh > c.y_dim) continue;  // dims stay 0 -> no table for this level
         h_dims[4 * k + 0] = fh;
         h_dims[4 * k + 1] = fw;
         h_dims[4 * k + 2] = (fw + 1) / 2;  // out_r = nqx (quirk)
         h_dims[4 * k + 3] = (fh + 1) / 2;  // out_c = nqy
     }
-    int *d_dims = nullptr;
-    uint32_t *d_mask = nullptr;
-    if ((rc = dev_alloc(e, &e->d_level_taps, (size_t)e->n_levels * 2 * kAsyncTapCap)) != IPP_OK) return rc;
+    int *d_dims = nullptr, *d_modes = nullptr;
+    if ((rc = dev_alloc(e, &e->d_level_taps, (size_t)kLevelTabs * kTapFloats2)) != IPP_OK) return rc;
     CU(e, cudaMalloc((void **)&d_dims, sizeof h_dims));
-    CU(e, cudaMalloc((void **)&d_mask, sizeof(uint32_t)));
+    CU(e, cudaMalloc((void **)&d_modes, kLevelTabs * sizeof(int)));
     CU(e, cudaMemcpyAsync(d_dims, h_dims, sizeof h_dims, cudaMemcpyHostToDevice, e->stream));
-    CU(e, cudaMemsetAsync(d_mask, 0, sizeof(uint32_t), e->stream));
-    CU(e, cudaMemsetAsync(e->d_level_taps, 0, (size_t)e->n_levels * 2 * kAsyncTapCap * sizeof(float4), e->stream));
-    build_level_taps_kernel<<<e->n_levels, 32, 0, e->stream>>>(e->d_level_taps, d_dims, d_mask);
+    CU(e, cudaMemsetAsync(e->d_level_taps, 0, (size_t)kLevelTabs * kTapFloats2 * sizeof(float2), e->stream));
+    build_level_taps_kernel<<<kLevelTabs, 32, 0, e->stream>>>(e->d_level_taps, d_dims, d_modes);
     e->launches++;
-    CU(e, cudaMemcpyAsync(&e->level_taps_ok, d_mask, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(e->level_tap_mode, d_modes, kLevelTabs * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
     cudaFree(d_dims);
-    cudaFree(d_mask);
+    cudaFree(d_modes);
     e->async_ok = true;
     return IPP_OK;
 }
@@ -491,15 +407,15 @@ static int launch_async(ipp_engine *e, const StepParams &p) {
     ap.base = p;
     ap.tickets = e->d_tickets;
     ap.level_taps = e->d_level_taps;
-    ap.level_taps_ok = e->level_taps_ok;
-    ap.parity = e->tma_parity;
+    memcpy(ap.level_tap_mode, e->level_tap_mode, sizeof ap.level_tap_mode);
+    ap.parity = e->ticket_parity;
     ap.warps = e->async_warps;
     ap.mv_tile_bytes = e->async_mv_tile;
     ap.gt_tile_bytes = e->async_gt_tile;
     const int needed = (p.n_jobs + e->async_warps - 1) / e->async_warps;
     const int grid = std::max(1, std::min(e->sm_count, needed));
     ipp_step_async_kernel<<<grid, e->async_warps * 32, e->async_smem, e->stream>>>(ap);
-    e->tma_parity ^= 1;
+    e->ticket_parity ^= 1;
     e->launches++;
     e->path_launches[IPP_PATH_ASYNC]++;
     CU(e, cudaGetLastError());
@@ -508,31 +424,8 @@ static int launch_async(ipp_engine *e, const StepParams &p) {
 
 // the path a Kalman step on action ids takes right now
 static int effective_path(const ipp_engine *e) {
-    if (e->step_path == IPP_PATH_TMA && e->tma_ok) return IPP_PATH_TMA;
     if (e->step_path != IPP_PATH_LSU && e->async_ok) return IPP_PATH_ASYNC;
     return IPP_PATH_LSU;
-}
-
-static int launch_tma(ipp_engine *e, const StepParams &p) {
-    TmaParams tp;
-    tp.base = p;
-    tp.maps = e->d_maps;
-    tp.tickets = e->d_tickets;
-    tp.parity = e->tma_parity;
-    tp.warps = e->tma_warps;
-    tp.mv_tile_bytes = e->tma_mv_tile;
-    tp.gt_tile_bytes = e->tma_gt_tile;
-    memcpy(tp.bw_mv, e->tma_bw_mv, sizeof tp.bw_mv);
-    memcpy(tp.bw_gt, e->tma_bw_gt, sizeof tp.bw_gt);
-    memcpy(tp.bh, e->tma_bh, sizeof tp.bh);
-    const int needed = (p.n_jobs + e->tma_warps - 1) / e->tma_warps;
-    const int grid = std::max(1, std::min(e->sm_count, needed));
-    ipp_step_tma_kernel<<<grid, e->tma_warps * 32, e->tma_smem, e->stream>>>(tp);
-    e->tma_parity ^= 1;
-    e->launches++;
-    e->path_launches[IPP_PATH_TMA]++;
-    CU(e, cudaGetLastError());
-    return IPP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -607,11 +500,9 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
     if (s != cudaSuccess) return bail(fail(e, IPP_ERR_CUDA, "status init: %s", cudaGetErrorString(s)));
     *e->h_status = 0;
     if ((rc = setup_async(e)) != IPP_OK) return bail(rc);
-    if ((rc = setup_tma(e)) != IPP_OK) return bail(rc);
     if (const char *sp = getenv("IPP_STEP_PATH")) {
         if (!strcmp(sp, "lsu")) e->step_path = IPP_PATH_LSU;
         if (!strcmp(sp, "async")) e->step_path = IPP_PATH_ASYNC;
-        if (!strcmp(sp, "tma")) e->step_path = IPP_PATH_TMA;
     }
     *out = e;
     return IPP_OK;
@@ -621,7 +512,7 @@ extern "C" void ipp_destroy(ipp_engine *e) {
     if (!e) return;
     if (e->stream) cudaStreamSynchronize(e->stream);
     void *ptrs[] = {e->d_mean, e->d_var, e->d_gt, e->d_prev, e->d_status, e->d_actions, e->d_poses, e->d_prev_in, e->d_env_index,
-                    e->d_reward, e->d_noise, e->d_z, e->d_metrics, e->d_scratch, e->d_maps, e->d_tickets, e->d_level_taps};
+                    e->d_reward, e->d_noise, e->d_z, e->d_metrics, e->d_scratch, e->d_tickets, e->d_level_taps};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->h_status) cudaFreeHost(e->h_status);
@@ -904,9 +795,7 @@ extern "C" int ipp_step_device(ipp_engine *e, const int32_t *action_ids, const d
     p.z_out = measurements;
     p.flags = flags;
     const int path = (action_ids != nullptr && (flags & (IPP_FLAG_LOGODDS | IPP_FLAG_NO_COMMIT)) == 0) ? effective_path(e) : IPP_PATH_LSU;
-    if (path == IPP_PATH_TMA)
-        rc = launch_tma(e, p);
-    else if (path == IPP_PATH_ASYNC)
+    if (path == IPP_PATH_ASYNC)
         rc = launch_async(e, p);
     else {
         rc = launch_step(e, p, (flags & IPP_FLAG_LOGODDS) ? MODE_LOGODDS : MODE_KALMAN);
@@ -1097,7 +986,7 @@ extern "C" int ipp_set_option(ipp_engine *e, int32_t option, int64_t value) {
     if (!e) return IPP_ERR_INVALID;
     switch (option) {
         case IPP_OPT_STEP_PATH:
-            if (value < IPP_PATH_LSU || value > IPP_PATH_TMA) return fail(e, IPP_ERR_INVALID, "ipp_set_option: step path %lld unknown", (long long)value);
+            if (value < IPP_PATH_LSU || value > IPP_PATH_ASYNC) return fail(e, IPP_ERR_INVALID, "ipp_set_option: step path %lld unknown", (long long)value);
             e->step_path = (int)value;
             return IPP_OK;
         default:
@@ -1111,7 +1000,6 @@ extern "C" int64_t ipp_get_option(const ipp_engine *e, int32_t option) {
         case IPP_OPT_STEP_PATH: return effective_path(e);
         case IPP_OPT_LAUNCHES_LSU: return (int64_t)e->path_launches[IPP_PATH_LSU];
         case IPP_OPT_LAUNCHES_ASYNC: return (int64_t)e->path_launches[IPP_PATH_ASYNC];
-        case IPP_OPT_LAUNCHES_TMA: return (int64_t)e->path_launches[IPP_PATH_TMA];
         default: return -1;
     }
 }

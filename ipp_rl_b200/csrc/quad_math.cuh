@@ -222,46 +222,129 @@ __device__ __forceinline__ float job_cost(const StepParams &p, double px, double
 // One axis of cv2 INTER_AREA decimation: output sample o of n_out integrates the input over
 // [o*s, (o+1)*s), s = n_in/n_out.  Exact integer overlaps in units of 1/n_out; weight =
 // overlap / n_in.  (opencv resize.cpp computeResizeAreaTab; reference call site
-// simulations/sensor_manipulations.py:20-22.)  Entry = {first input index, w0, w1, w2}; count > 3
-// (scale > 2, only for clipped non-square footprints) is flagged with a negative start.
-__device__ __forceinline__ float4 make_tap_entry(int o, int n_in, int n_out) {
+// simulations/sensor_manipulations.py:20-22.)
+// A table entry is 6 floats = 3 x float2: {first input index, w0}, {w1, w2}, {w3, w4}.  Square
+// footprints need 3 taps (scale < 2); clipped, non-square ones up to 5 (scale < 4); anything beyond
+// (exotic FoV / grid shapes) takes the generic loop.
+constexpr int TAPS_FAST = 0, TAPS_WIDE = 1, TAPS_GENERIC = 2;
+
+__device__ __forceinline__ int make_tap_entry(float2 *e /* [3] */, int o, int n_in, int n_out) {
     const int a1 = o * n_in, a2 = a1 + n_in;
     const int start = a1 / n_out;
     const int end = (a2 + n_out - 1) / n_out;  // exclusive
     const float inv = 1.0f / (float)n_in;
-    float w[3];
+    float w[5];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 5; ++k) {
         const int i = start + k;
         const int lo = max(a1, i * n_out), hi = min(a2, (i + 1) * n_out);
         w[k] = hi > lo ? (float)(hi - lo) * inv : 0.0f;
     }
-    return make_float4(__int_as_float(end - start > 3 ? -1 - start : start), w[0], w[1], w[2]);
+    e[0] = make_float2(__int_as_float(start), w[0]);
+    e[1] = make_float2(w[1], w[2]);
+    e[2] = make_float2(w[3], w[4]);
+    const int cnt = end - start;
+    return cnt <= 3 ? TAPS_FAST : (cnt <= 5 ? TAPS_WIDE : TAPS_GENERIC);
 }
 
 // generic weight of input i for output o (slow path)
-__device__ __forceinline__ float tap_weight_generic(int o, int i, int n_in, int n_out) {
+__device__ __forceinline__ float tap_weight_generic(int o, int i, int n_in, int n_out, float inv_n_in) {
     const int a1 = o * n_in, a2 = a1 + n_in;
     const int lo = max(a1, i * n_out), hi = min(a2, (i + 1) * n_out);
-    return hi > lo ? (float)(hi - lo) / (float)n_in : 0.0f;
+    return hi > lo ? (float)(hi - lo) * inv_n_in : 0.0f;
 }
 
-// Build the row / column tap tables of a rf=2 footprint in shared memory (one warp).  Returns true
-// when the fast 3-tap tables cannot be used (table overflow or an axis with scale > 2).
+// Build the row / column tap tables of a rf=2 footprint (one warp): tab[3*idx .. 3*idx+2] for rows,
+// tab[3*(CAP+idx) ..] for columns.  Returns TAPS_FAST / TAPS_WIDE / TAPS_GENERIC for the footprint.
 template <int CAP>
-__device__ __forceinline__ bool build_tap_tables(float4 *tab /* [2*CAP] */, int lane, int ny, int nx, int out_r, int out_c) {
-    bool bad = out_r > CAP || out_c > CAP;
-    if (!bad) {
+__device__ __forceinline__ int build_tap_tables(float2 *tab /* [2*CAP*3] */, int lane, int ny, int nx, int out_r, int out_c) {
+    int mode = (out_r > CAP || out_c > CAP) ? TAPS_GENERIC : TAPS_FAST;
+    if (mode != TAPS_GENERIC) {
         for (int idx = lane; idx < out_r + out_c; idx += 32) {
             const bool is_row = idx < out_r;
-            const float4 e = is_row ? make_tap_entry(idx, ny, out_r) : make_tap_entry(idx - out_r, nx, out_c);
-            tab[is_row ? idx : CAP + idx - out_r] = e;
-            bad |= __float_as_int(e.x) < 0;
+            float2 *e = tab + 3 * (is_row ? idx : CAP + idx - out_r);
+            mode = max(mode, is_row ? make_tap_entry(e, idx, ny, out_r) : make_tap_entry(e, idx - out_r, nx, out_c));
         }
     }
-    bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mode = max(mode, __shfl_xor_sync(0xffffffffu, mode, s));
     __syncwarp();
-    return bad;
+    return mode;
+}
+
+// D[pr, pc] of the down-sampled measurement from a ground-truth tile `g` (row pitch `pitch`, origin =
+// footprint corner; global memory or shared memory).  Rows / columns past the footprint carry weight 0
+// and are clamped.
+struct TapView {
+    const float2 *rows, *cols;  // entry k at [3k .. 3k+2]
+};
+
+template <bool GLOBAL>
+__device__ __forceinline__ float gt_at(const float *g, int i) {
+    return GLOBAL ? __ldg(g + i) : g[i];
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ float downsample_fast(const float *g, int pitch, const TapView &t, int pr, int pc, int ny, int nx) {
+    const float2 r0 = t.rows[3 * pr], r1 = t.rows[3 * pr + 1];
+    const float2 c0 = t.cols[3 * pc], c1 = t.cols[3 * pc + 1];
+    const int rs = __float_as_int(r0.x), cs = __float_as_int(c0.x);
+    const float wr[3] = {r0.y, r1.x, r1.y};
+    const int cb[3] = {cs, min(cs + 1, nx - 1), min(cs + 2, nx - 1)};
+    float d = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float *rowp = g + min(rs + a, ny - 1) * pitch;
+        const float rowsum = fmaf(c1.y, gt_at<GLOBAL>(rowp, cb[2]), fmaf(c1.x, gt_at<GLOBAL>(rowp, cb[1]), c0.y * gt_at<GLOBAL>(rowp, cb[0])));
+        d = fmaf(wr[a], rowsum, d);
+    }
+    return d;
+}
+
+// clipped non-square footprints: up to 5 taps per axis (kept out of line: ~15 % of the rf=2 envs)
+template <bool GLOBAL>
+__device__ __noinline__ float downsample_wide(const float *g, int pitch, TapView t, int pr, int pc, int ny, int nx) {
+    const float2 r0 = t.rows[3 * pr], r1 = t.rows[3 * pr + 1], r2 = t.rows[3 * pr + 2];
+    const float2 c0 = t.cols[3 * pc], c1 = t.cols[3 * pc + 1], c2 = t.cols[3 * pc + 2];
+    const int rs = __float_as_int(r0.x), cs = __float_as_int(c0.x);
+    const float wr[5] = {r0.y, r1.x, r1.y, r2.x, r2.y};
+    const float wc[5] = {c0.y, c1.x, c1.y, c2.x, c2.y};
+    float d = 0.0f;
+#pragma unroll 1
+    for (int a = 0; a < 5; ++a) {
+        const float *rowp = g + min(rs + a, ny - 1) * pitch;
+        float rowsum = 0.0f;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) rowsum = fmaf(wc[b], gt_at<GLOBAL>(rowp, min(cs + b, nx - 1)), rowsum);
+        d = fmaf(wr[a], rowsum, d);
+    }
+    return d;
+}
+
+// anything else (decimation scale >= 4 or footprints wider than the tap tables)
+template <bool GLOBAL>
+__device__ __noinline__ float downsample_generic(const float *g, int pitch, int pr, int pc, int ny, int nx, int out_r, int out_c) {
+    const int rs = (pr * ny) / out_r, re = ((pr + 1) * ny + out_r - 1) / out_r;
+    const int cs = (pc * nx) / out_c, ce = ((pc + 1) * nx + out_c - 1) / out_c;
+    const float inv_ny = 1.0f / (float)ny, inv_nx = 1.0f / (float)nx;
+    float d = 0.0f;
+#pragma unroll 1
+    for (int a = rs; a < re; ++a) {
+        const float *rowp = g + min(a, ny - 1) * pitch;
+        float rowsum = 0.0f;
+#pragma unroll 1
+        for (int b = cs; b < ce; ++b) rowsum = fmaf(tap_weight_generic(pc, b, nx, out_c, inv_nx), gt_at<GLOBAL>(rowp, min(b, nx - 1)), rowsum);
+        d = fmaf(tap_weight_generic(pr, a, ny, out_r, inv_ny), rowsum, d);
+    }
+    return d;
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ float downsample(int mode, const float *g, int pitch, const TapView &t, int pr, int pc, int ny, int nx, int out_r,
+                                            int out_c) {
+    if (mode == TAPS_FAST) return downsample_fast<GLOBAL>(g, pitch, t, pr, pc, ny, nx);
+    if (mode == TAPS_WIDE) return downsample_wide<GLOBAL>(g, pitch, t, pr, pc, ny, nx);
+    return downsample_generic<GLOBAL>(g, pitch, pr, pc, ny, nx, out_r, out_c);
 }
 
 // Shannon entropy [nats] of Bernoulli(sigmoid(l)):  log1p(e^-|l|) + |l| e^-|l| / (1 + e^-|l|)

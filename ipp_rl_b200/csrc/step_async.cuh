@@ -7,40 +7,43 @@
 // Here every warp keeps the COMPLETE footprint of its next env in flight — {mean,var} tile with 8-byte
 // and ground-truth tile with 4-byte asynchronous copies, all 32 lanes issuing, no registers held —
 // while it fuses the env whose tiles have already landed.  Two slots per warp, cp.async group
-// accounting, no block-level synchronisation at all.  Work is handed out through a global ticket
-// counter (dynamic load balance: footprints are 81 / 289 / 529 cells), fetched one env ahead so that
-// neither the atomic nor the action-id load is ever waited for.  Up to 2 x 16 footprints (~140 KB)
-// are in flight per SM independent of register pressure.  Results go back with 64-bit stores.
+// accounting, no block-level synchronisation in the loop.  Work is handed out through a global
+// ticket counter (dynamic load balance: footprints are 81 / 289 / 529 cells), fetched one env ahead
+// so that neither the atomic nor the action-id load is ever waited for.  Up to 2 x 16 footprints
+// (~140 KB) are in flight per SM independent of register pressure.  Results go back with 64-bit
+// stores (write-back L2).
 //
 // The loop body is kept small on purpose (ncu: the first version, 63 KB of SASS, spent most of its
 // time in instruction-fetch stalls): per-slot state lives in shared memory so that the body exists
-// once, rarely used paths are out of line, and index divisions use a 16-bit magic multiplier.
+// once, rarely used paths are out of line, index divisions use a 16-bit magic multiplier, and the
+// INTER_AREA tap tables of the unclipped footprints are precomputed per altitude level.
 //
-// (A TMA variant of the same pipeline — 3-D tensor-map box copies, step_tma.cuh — is kept for
-// reference: the TMA unit spends ~40 cycles per 100-200 B box row, which makes it slower than even
-// the plain LSU kernel on these narrow footprints; see profiles/ and DESIGN.md.)
+// (A TMA variant of the same pipeline — 3-D tensor-map box copies — was measured and retired:
+// the TMA unit spends ~40 cycles per 100-200 B box row, slower than even the plain LSU kernel on
+// these narrow footprints; profiles/attic/step_tma.cuh.txt, tools/tma_probe.cu, DESIGN.md.)
 //
 //   grid  = #SMs (persistent, 1 CTA / SM), block = up to 16 warps, dynamic smem ~ 225 KB
-//   smem  = [warp][slot]{mv tile, gt tile} | [warp][slot] SlotCtl | [warp] INTER_AREA tap tables
+//   smem  = [warp][slot]{mv tile, gt tile} | [warp][slot] SlotCtl | [warp] tap tables | level tap tables
 #pragma once
 #include "step_kernel.cuh"
 
 namespace ipp {
 
-constexpr int kAsyncSlots = 2;     // footprints in flight per warp
-constexpr int kAsyncTapCap = 16;   // tap-table entries per axis (footprints up to 32 cells wide)
+constexpr int kAsyncSlots = 2;      // footprints in flight per warp
 constexpr int kAsyncMaxWarps = 16;
-constexpr int kTicketChunk = 4;    // tickets taken per atomic
+constexpr int kTicketChunk = 4;     // tickets taken per atomic
+constexpr int kLevelTabs = 4;       // altitude levels whose interior tap tables are staged in smem
+constexpr int kTapFloats2 = 2 * kTapCap * 3;  // float2 per tap-table pair (rows + cols)
 
 struct AsyncParams {
     StepParams base;
     unsigned int *tickets;     // [2] ping-pong work counters
-    const float4 *level_taps;  // [n_levels][2 * kAsyncTapCap] tap tables of the unclipped footprints (nullable entries flagged)
+    const float2 *level_taps;  // [kLevelTabs][kTapFloats2] tap tables of the unclipped footprints
     int parity;                // counter consumed by this launch; the other one is zeroed for the next
     int warps;                 // warps per CTA
     int mv_tile_bytes;         // per-slot tile capacities (multiples of 16 B)
     int gt_tile_bytes;
-    uint32_t level_taps_ok;    // bit k: level k has a usable 3-tap table
+    int level_tap_mode[kLevelTabs];  // TAPS_FAST / TAPS_WIDE, or -1: no table for this level
 };
 
 // per-(warp, slot) control block, written when the slot is filled, read when it is fused
@@ -65,28 +68,17 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// per-level tap tables of the unclipped (interior) footprints, built once at engine creation
-__global__ void build_level_taps_kernel(float4 *tabs, const int *out_dims /* [levels][4] = ny, nx, out_r, out_c */, uint32_t *ok_mask) {
+// per-level tap tables of the unclipped (interior) footprints, built once at engine creation with the
+// same device code the kernels use per env (bit-identical entries)
+__global__ void build_level_taps_kernel(float2 *tabs, const int *dims /* [levels][4] = ny, nx, out_r, out_c */, int *modes) {
     const int k = blockIdx.x;
-    const int ny = out_dims[4 * k], nx = out_dims[4 * k + 1], out_r = out_dims[4 * k + 2], out_c = out_dims[4 * k + 3];
-    bool bad = true;
-    if (out_r >= 1 && out_c >= 1 && out_r <= ny && out_c <= nx)
-        bad = build_tap_tables<kAsyncTapCap>(tabs + (size_t)k * 2 * kAsyncTapCap, (int)threadIdx.x, ny, nx, out_r, out_c);
-    if (threadIdx.x == 0 && !bad) atomicOr(ok_mask, 1u << k);
-}
-
-// rarely taken: a clipped, non-square rf=2 footprint with a decimation scale above 2 (more than 3 taps)
-__device__ __noinline__ float downsample_generic(const float *gt_t, int pitch, int pr, int pc, int ny, int nx, int out_r, int out_c) {
-    const int rs = (pr * ny) / out_r, re = ((pr + 1) * ny + out_r - 1) / out_r;
-    const int cs = (pc * nx) / out_c, ce = ((pc + 1) * nx + out_c - 1) / out_c;
-    float d = 0.0f;
-    for (int a = rs; a < re; ++a) {
-        const float *rowp = gt_t + min(a, ny - 1) * pitch;
-        float rowsum = 0.0f;
-        for (int b = cs; b < ce; ++b) rowsum = fmaf(tap_weight_generic(pc, b, nx, out_c), rowp[min(b, nx - 1)], rowsum);
-        d = fmaf(tap_weight_generic(pr, a, ny, out_r), rowsum, d);
+    const int ny = dims[4 * k], nx = dims[4 * k + 1], out_r = dims[4 * k + 2], out_c = dims[4 * k + 3];
+    int mode = -1;
+    if (out_r >= 1 && out_c >= 1 && out_r <= ny && out_c <= nx) {
+        mode = build_tap_tables<kTapCap>(tabs + (size_t)k * kTapFloats2, (int)threadIdx.x, ny, nx, out_r, out_c);
+        if (mode == TAPS_GENERIC) mode = -1;
     }
-    return d;
+    if (threadIdx.x == 0) modes[k] = mode;
 }
 
 __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(const __grid_constant__ AsyncParams ap) {
@@ -97,7 +89,13 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
     unsigned char *my_stages = smem_raw + (size_t)w * kAsyncSlots * stage_bytes;
     unsigned char *after = smem_raw + (size_t)ap.warps * kAsyncSlots * stage_bytes;
     SlotCtl *ctl = reinterpret_cast<SlotCtl *>(after) + w * kAsyncSlots;
-    float4 *taps = reinterpret_cast<float4 *>(after + (size_t)ap.warps * kAsyncSlots * sizeof(SlotCtl)) + w * 2 * kAsyncTapCap;
+    float2 *tap_base = reinterpret_cast<float2 *>(after + (size_t)ap.warps * kAsyncSlots * sizeof(SlotCtl));
+    float2 *taps = tap_base + (size_t)w * kTapFloats2;                 // this warp's per-env tables
+    const float2 *lvl_taps = tap_base + (size_t)ap.warps * kTapFloats2;  // shared, read-only after the barrier
+
+    // stage the per-level tap tables (a few hundred bytes each) once per CTA
+    for (int i = threadIdx.x; i < kLevelTabs * kTapFloats2; i += blockDim.x) const_cast<float2 *>(lvl_taps)[i] = __ldg(ap.level_taps + i);
+    __syncthreads();
 
     unsigned int *ticket = ap.tickets + ap.parity;
     if (blockIdx.x == 0 && threadIdx.x == 0) ap.tickets[ap.parity ^ 1] = 0u;  // for the next launch
@@ -132,11 +130,13 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
             const int RP = 32 / W;
             const int lr = lane / W, lc = lane - lr * W;
             const size_t org = (size_t)job * p.plane + (size_t)(yu * X + xl);
+            const uint32_t tile = smem_u32(my_stages + (size_t)s * stage_bytes);
             for (int c0 = lc; c0 < nx; c0 += 32) {  // one pass unless the footprint is wider than 32 cells
                 const float2 *src_mv = mv_base + org + (size_t)(lr * X + c0);
                 const float *src_gt = p.gt + org + (size_t)(lr * X + c0);
-                uint32_t dst_mv = smem_u32(my_stages + (size_t)s * stage_bytes) + 8u * (uint32_t)(lr * pitch + c0);
-                uint32_t dst_gt = smem_u32(my_stages + (size_t)s * stage_bytes) + (uint32_t)ap.mv_tile_bytes + 4u * (uint32_t)(lr * pitch + c0);
+                uint32_t dst_mv = tile + 8u * (uint32_t)(lr * pitch + c0);
+                uint32_t dst_gt = tile + (uint32_t)ap.mv_tile_bytes + 4u * (uint32_t)(lr * pitch + c0);
+#pragma unroll 2
                 for (int r = lr; r < ny; r += RP) {
                     cp_async_8(dst_mv, src_mv);
                     cp_async_4(dst_gt, src_gt);
@@ -155,15 +155,16 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
     if (lane == 0) chunk_base = atomicAdd(ticket, (unsigned)kTicketChunk);
     chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
     int chunk_used = 3;
-    int next_job[kAsyncSlots];  // job resident in each slot (-1: none); mirrors SlotCtl::job
-#pragma unroll
-    for (int s = 0; s < kAsyncSlots; ++s) {
-        const unsigned int t = chunk_base + s;
-        next_job[s] = t < (unsigned)n_jobs ? (int)t : -1;
-        const int id = next_job[s] >= 0 ? __ldg(p.action_ids + next_job[s]) : 0;
-        fill(s, next_job[s], id);
+    int cur_job, other_job;
+    {
+        const unsigned int ta = chunk_base, tb = chunk_base + 1;
+        cur_job = ta < (unsigned)n_jobs ? (int)ta : -1;
+        other_job = tb < (unsigned)n_jobs ? (int)tb : -1;
+        const int ida = cur_job >= 0 ? __ldg(p.action_ids + cur_job) : 0;
+        const int idb = other_job >= 0 ? __ldg(p.action_ids + other_job) : 0;
+        fill(0, cur_job, ida);
+        fill(1, other_job, idb);
     }
-    int cur_job = next_job[0], other_job = next_job[1];
     unsigned int tk = chunk_base + 2;  // ticket whose action id has not been loaded yet
     int s = 0;
 
@@ -198,16 +199,21 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         const float *gt_t = reinterpret_cast<const float *>(st + ap.mv_tile_bytes);
 
         // INTER_AREA tap tables: the per-level table when the footprint is unclipped, else built here
-        const float4 *tapr = taps, *tapc = taps + kAsyncTapCap;
-        bool generic_taps = false, unsupported = false;
+        TapView tapv;
+        tapv.rows = taps;
+        tapv.cols = taps + 3 * kTapCap;
+        int tap_mode = TAPS_FAST;
+        bool unsupported = false;
         if (rf == 2) {
             unsupported = out_r > ny || out_c > nx;
-            const bool interior = nx == 2 * L.rx + 1 && ny == 2 * L.ry + 1 && ((ap.level_taps_ok >> lvl) & 1u) && (quirk || nqx == nqy);
+            const int lmode = lvl < kLevelTabs ? ap.level_tap_mode[lvl] : -1;
+            const bool interior = lmode >= 0 && nx == 2 * L.rx + 1 && ny == 2 * L.ry + 1 && (quirk || nqx == nqy);
             if (interior) {
-                tapr = ap.level_taps + (size_t)lvl * 2 * kAsyncTapCap;
-                tapc = tapr + kAsyncTapCap;
+                tapv.rows = lvl_taps + (size_t)lvl * kTapFloats2;
+                tapv.cols = tapv.rows + 3 * kTapCap;
+                tap_mode = lmode;
             } else if (!unsupported) {
-                generic_taps = build_tap_tables<kAsyncTapCap>(taps, lane, ny, nx, out_r, out_c);
+                tap_mode = build_tap_tables<kTapCap>(taps, lane, ny, nx, out_r, out_c);
             }
         }
 
@@ -216,10 +222,10 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         fc.R = L.R;
         fc.invR = __frcp_rn(L.R);
         fc.entropy = entropy;
-        // q / nqx and q / out_c with a 16-bit magic multiplier (exact for q * d < 65536), else float path
+        // q / nqx and q / out_c with a 16-bit magic multiplier floor(65536/d)+1 (exact for q*d < 65536)
         const bool small = nq * max(nqx, out_c) < 65536;
-        const uint32_t magic_x = 65536u / (uint32_t)nqx + 1u, magic_c = 65536u / (uint32_t)out_c + 1u;
         const float inv_nqx = __frcp_rn((float)nqx), inv_outc = __frcp_rn((float)out_c);
+        const uint32_t magic_x = (uint32_t)(65536.0f * inv_nqx) + 1u, magic_c = (uint32_t)(65536.0f * inv_outc) + 1u;
         float2 *mv_g = mv_base + (size_t)job * p.plane + (size_t)(yu * X + xl);
         const size_t nrow = (size_t)job * (size_t)p.noise_stride;
         float acc = 0.0f;
@@ -227,16 +233,18 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         if (unsupported) {
             if (lane == 0) atomicOr(p.status, 1);
         } else {
+#pragma unroll 1
             for (int q = lane; q < nq; q += 32) {
                 const int qy = small ? (int)(((uint32_t)q * magic_x) >> 16) : fdiv(q, nqx, inv_nqx);
                 const int qx = q - qy * nqx;
                 const int r0 = 2 * qy, c0 = 2 * qx;
                 const bool cok = c0 + 1 < nx, rok = r0 + 1 < ny;
                 const bool ok[4] = {true, cok, rok, cok && rok};
+                const int r1 = min(r0 + 1, ny - 1);  // clamped: the tile has exactly ny rows
 
                 // ---- belief from the staged tile: two 128-bit shared loads (pitch is even) -------
                 const float4 top = *reinterpret_cast<const float4 *>(mv_t + r0 * pitch + c0);
-                const float4 bot = *reinterpret_cast<const float4 *>(mv_t + (r0 + 1) * pitch + c0);
+                const float4 bot = *reinterpret_cast<const float4 *>(mv_t + r1 * pitch + c0);
                 const float m[4] = {top.x, cok ? top.z : 0.0f, rok ? bot.x : 0.0f, ok[3] ? bot.z : 0.0f};
                 const float v[4] = {top.y, cok ? top.w : 0.0f, rok ? bot.y : 0.0f, ok[3] ? bot.w : 0.0f};
 
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 }
                 if (rf == 1) {
                     const float2 g0 = *reinterpret_cast<const float2 *>(gt_t + r0 * pitch + c0);
-                    const float2 g1 = *reinterpret_cast<const float2 *>(gt_t + (r0 + 1) * pitch + c0);
+                    const float2 g1 = *reinterpret_cast<const float2 *>(gt_t + r1 * pitch + c0);
                     const float gv[4] = {g0.x, g0.y, g1.x, g1.y};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) z[k] = ok[k] ? __saturatef(fmaf(s2, eps[k], gv[k])) : 0.0f;
@@ -268,21 +276,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                         pr = small ? (int)(((uint32_t)q * magic_c) >> 16) : fdiv(q, out_c, inv_outc);
                         pc = q - pr * out_c;
                     }
-                    float d = 0.0f;
-                    if (!generic_taps) {
-                        const float4 tr = tapr[pr], tc = tapc[pc];
-                        const int rs = __float_as_int(tr.x), cs = __float_as_int(tc.x);
-                        const float wr[3] = {tr.y, tr.z, tr.w};
-                        const int cb[3] = {cs, min(cs + 1, nx - 1), min(cs + 2, nx - 1)};
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) {
-                            const float *rowp = gt_t + min(rs + a, ny - 1) * pitch;
-                            const float rowsum = fmaf(tc.w, rowp[cb[2]], fmaf(tc.z, rowp[cb[1]], tc.y * rowp[cb[0]]));
-                            d = fmaf(wr[a], rowsum, d);
-                        }
-                    } else {
-                        d = downsample_generic(gt_t, pitch, pr, pc, ny, nx, out_r, out_c);
-                    }
+                    const float d = downsample<false>(tap_mode, gt_t, pitch, tapv, pr, pc, ny, nx, out_r, out_c);
                     z[0] = __saturatef(fmaf(s2, eps[0], d));
                 }
                 if (p.z_out != nullptr) {

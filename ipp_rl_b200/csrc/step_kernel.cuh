@@ -1,8 +1,8 @@
 // step_kernel.cuh — the general fused step kernel (sm_100a): one warp per job, footprint gathered
 // straight from HBM with LSU loads.  Handles every mode and input form of the C ABI (action ids or
 // fp64 poses, env_index jobs, predict-only, measure-only, caller-supplied measurements, log-odds).
-// The throughput path for the headline configuration is the TMA-staged persistent kernel in
-// step_tma.cuh; both share quad_math.cuh.
+// The throughput path for the headline configuration is the cp.async-staged persistent kernel in
+// step_async.cuh; both share quad_math.cuh and produce bit-identical results.
 //
 // The footprint is tiled by 2x2-cell "quads" anchored at its top-left cell; lane l handles quads
 // l, l+32, ...  A quad is exactly one measurement block at resolution factor 2 and four independent
@@ -18,7 +18,7 @@ namespace ipp {
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kTapCap = 64;  // tap-table entries per axis staged in shared memory
+constexpr int kTapCap = 16;  // tap-table entries per axis staged in shared memory (same in both kernels)
 
 // ---------------------------------------------------------------------------------------------
 // belief accessors for the two HBM layouts
@@ -62,7 +62,7 @@ struct Belief<IPP_LAYOUT_MV> {
 
 template <int LAYOUT, int MODE>
 __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constant__ StepParams p) {
-    __shared__ float4 s_taps[kWarpsPerBlock][2 * kTapCap];
+    __shared__ float2 s_taps[kWarpsPerBlock][2 * kTapCap * 3];
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -78,18 +78,21 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
     const bool adaptive = (p.flags & IPP_FLAG_ADAPTIVE) != 0;
     const bool commit = (p.flags & IPP_FLAG_NO_COMMIT) == 0 && !p.measure_only;
     const bool simulate = (MODE != MODE_PREDICT) && (p.z_in == nullptr);
-    const bool downsample = simulate && g.rf == 2;
+    const bool need_taps = simulate && g.rf == 2;
 
     // INTER_AREA geometry at rf = 2 (rows / cols of the down-sampled measurement D)
     const int out_r = quirk ? nqx : nqy;
     const int out_c = quirk ? nqy : nqx;
-    bool generic_taps = false;
-    if (MODE != MODE_PREDICT && downsample) {
+    int tap_mode = TAPS_FAST;
+    TapView tapv;
+    tapv.rows = s_taps[wib];
+    tapv.cols = s_taps[wib] + 3 * kTapCap;
+    if (MODE != MODE_PREDICT && need_taps) {
         if (out_r > g.ny || out_c > g.nx) {
             if (lane == 0) atomicOr(p.status, 1);
             return;
         }
-        generic_taps = build_tap_tables<kTapCap>(s_taps[wib], lane, g.ny, g.nx, out_r, out_c);
+        tap_mode = build_tap_tables<kTapCap>(s_taps[wib], lane, g.ny, g.nx, out_r, out_c);
     }
 
     FuseCtx fc;
@@ -167,28 +170,7 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
                 } else {
                     // D[pr, pc] with the measurement's flat index q: (pr, pc) = (q / out_c, q % out_c)
                     const int pr = fdiv(q, out_c, inv_outc), pc = q - pr * out_c;
-                    float d = 0.0f;
-                    if (!generic_taps) {
-                        const float4 tr = s_taps[wib][pr], tc = s_taps[wib][kTapCap + pc];
-                        const int rs = __float_as_int(tr.x), cs = __float_as_int(tc.x);
-                        const float wr[3] = {tr.y, tr.z, tr.w};
-                        const int cb[3] = {cs, min(cs + 1, g.nx - 1), min(cs + 2, g.nx - 1)};
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) {
-                            const float *row = gt + origin + min(rs + a, g.ny - 1) * X;
-                            const float rowsum = fmaf(tc.w, __ldg(row + cb[2]), fmaf(tc.z, __ldg(row + cb[1]), tc.y * __ldg(row + cb[0])));
-                            d = fmaf(wr[a], rowsum, d);
-                        }
-                    } else {
-                        const int rs = (pr * g.ny) / out_r, re = ((pr + 1) * g.ny + out_r - 1) / out_r;
-                        const int cs = (pc * g.nx) / out_c, ce = ((pc + 1) * g.nx + out_c - 1) / out_c;
-                        for (int a = rs; a < re; ++a) {
-                            const float *row = gt + origin + min(a, g.ny - 1) * X;
-                            float rowsum = 0.0f;
-                            for (int b = cs; b < ce; ++b) rowsum = fmaf(tap_weight_generic(pc, b, g.nx, out_c), __ldg(row + min(b, g.nx - 1)), rowsum);
-                            d = fmaf(tap_weight_generic(pr, a, g.ny, out_r), rowsum, d);
-                        }
-                    }
+                    const float d = downsample<true>(tap_mode, gt + origin, X, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
                     z[0] = __saturatef(fmaf(g.s2, eps[0], d));
                 }
             }

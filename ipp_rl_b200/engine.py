@@ -185,11 +185,11 @@ class BatchedEngine:
         self._ck(self._lib.ipp_sync(self._h))
 
     # -- kernel path selection ------------------------------------------------------------------
-    PATHS = {"lsu": capi.PATH_LSU, "async": capi.PATH_ASYNC, "tma": capi.PATH_TMA}
+    PATHS = {"lsu": capi.PATH_LSU, "async": capi.PATH_ASYNC}
 
     def set_step_path(self, path: str) -> None:
-        """Request the step kernel: "async" (default, cp.async-staged persistent kernel), "lsu" (general
-        gather kernel) or "tma" (TMA box copies).  Unavailable paths fall back (see ``step_path``)."""
+        """Request the step kernel: "async" (default, cp.async-staged persistent kernel), or "lsu" (general
+        gather kernel).  Unavailable paths fall back (see ``step_path``)."""
         self._ck(self._lib.ipp_set_option(self._h, capi.OPT_STEP_PATH, self.PATHS[path]))
 
     @property

@@ -1,4 +1,4 @@
-"""GPU tests of the persistent (cp.async- and TMA-staged) kernels and of the full-size workload.
+"""GPU tests of the persistent cp.async-staged kernel and of the full-size workload.
 
 * the persistent paths must reproduce the general LSU kernel bit for bit (same arithmetic, different staging);
 * it must match the reference-pinned oracle on the 200x200 windowed golden vectors driven by ACTION IDS;
@@ -32,7 +32,7 @@ def test_persistent_paths_are_bit_identical_to_lsu_path(grid, reward_mode, adapt
     mean0 = rng.uniform(0, 1, (B, Y, X)).astype(np.float32)
     var0 = rng.uniform(0.05, 2.0, (B, Y, X)).astype(np.float32)
     out = {}
-    for path in ("lsu", "async", "tma"):
+    for path in ("lsu", "async"):
         with _engine(params, B, layout=1, seed=99) as eng:
             eng.set_step_path(path)
             assert eng.step_path == path, "persistent paths must be available for MV layout with x_dim % 4 == 0"
@@ -55,12 +55,12 @@ def test_persistent_paths_are_bit_identical_to_lsu_path(grid, reward_mode, adapt
             m, v = eng.get_state()
             out[path] = (np.array(rs), m, v, eng.get_prev_pose(), zs[0])
             assert eng.path_launches(path) == T
-    for path in ("async", "tma"):
+    for path in ("async",):
         for a, b in zip(out[path], out["lsu"]):
             assert np.array_equal(a, b), path
 
 
-@pytest.mark.parametrize("path", ["async", "tma"])
+@pytest.mark.parametrize("path", ["async"])
 def test_persistent_windowed_golden_by_action_id(path):
     """Reference-pinned T2 vectors (200x200) through the persistent paths: poses at cell centres -> action ids."""
     g = golden("golden_windowed_T2.npz")
@@ -108,7 +108,7 @@ def test_persistent_windowed_golden_by_action_id(path):
         assert np.array_equal(chk, var0.astype(np.float32))
 
 
-@pytest.mark.parametrize("path", ["async", "lsu", "tma"])
+@pytest.mark.parametrize("path", ["async", "lsu"])
 def test_full_size_properties(path):
     """BASELINE.json C3 size: 65 536 envs x 200x200 (31.5 GB of maps in HBM)."""
     import torch
