@@ -156,10 +156,12 @@ def run_ours(args, rank, world, local_rank):
     # synthetic action streams: uniform-random valid (cell, altitude) per env per step
     rng = np.random.RandomState(777 + rank)
     total = W + K
-    ids_host = rng.randint(0, eng.num_actions, size=(total, B)).astype(np.int32)
-    ids_e2e = rng.randint(0, eng.num_actions, size=(total, B)).astype(np.int32)
-    cells_timed = footprint_cells(ids_host[W:].astype(np.int64), X, Y, radii)  # (K, B)
-    alg_bytes_per_launch = float((20 * cells_timed + 16).sum()) / K
+    POOL = min(total, 64)  # distinct action sets, cycled (each env still sees a different action every step)
+    ids_host = rng.randint(0, eng.num_actions, size=(POOL, B)).astype(np.int32)
+    ids_e2e = rng.randint(0, eng.num_actions, size=(POOL, B)).astype(np.int32)
+    cells_pool = footprint_cells(ids_host.astype(np.int64), X, Y, radii).sum(axis=1)  # (POOL,)
+    cells_timed_total = float(sum(cells_pool[t % POOL] for t in range(W, W + K)))
+    alg_bytes_per_launch = (20.0 * cells_timed_total + 16.0 * B * K) / K
 
     reward_modes = {"entropy": capi.REWARD_GAUSS_ENTROPY, "trace": capi.REWARD_TRACE}
 
@@ -176,7 +178,7 @@ def run_ours(args, rank, world, local_rank):
 
         def device_loop(mode, lo, hi):
             for t in range(lo, hi):
-                eng.step_device(action_ids_ptr=ids_dev[t].data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=mode)
+                eng.step_device(action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=mode)
 
         results = {}
         clocks = None
@@ -210,20 +212,21 @@ def run_ours(args, rank, world, local_rank):
 
         def e2e_step(t):
             if dist is None:
-                eng.step(ids_np[t], reward_mode=capi.REWARD_GAUSS_ENTROPY, out=out_np)
+                eng.step(ids_np[t % POOL], reward_mode=capi.REWARD_GAUSS_ENTROPY, out=out_np)
             else:
-                staged = ids_pinned[t].cuda(non_blocking=True)
+                staged = ids_pinned[t % POOL].cuda(non_blocking=True)
                 eng.step_device(action_ids_ptr=staged.data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=capi.REWARD_GAUSS_ENTROPY)
                 dist.all_gather_into_tensor(gathered, reward_dev)
                 out_pinned.copy_(gathered, non_blocking=True)
                 stream.synchronize()
 
+        KE = min(K, args.e2e_steps)  # the e2e leg is host-latency bound; keep the default run short
         for t in range(W):
             e2e_step(t)
         barrier()
         launches_e2e0 = eng.launches
         t0 = time.perf_counter()
-        for t in range(W, W + K):
+        for t in range(W, W + KE):
             e2e_step(t)
         barrier()
         e2e_s = time.perf_counter() - t0
@@ -240,7 +243,7 @@ def run_ours(args, rank, world, local_rank):
         try:
             from oracle import cpu_baseline
 
-            r = cpu_baseline.run(WORKLOAD, steps=2, warmup=1, envs=args.cpu_envs, reward_mode=1)
+            r = cpu_baseline.run(WORKLOAD, steps=3, warmup=1, envs=args.cpu_envs, reward_mode=1, min_seconds=1.0)
             cpu = {"value": r["steps_per_sec"], "unit": "env-steps/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         except Exception as exc:  # report, never hide
             cpu = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "port", "sample": f"failed: {exc!r}"}
@@ -271,8 +274,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                         "mean_cells_per_env_step": float(cells_timed.mean()), "kernel": "ipp_step_kernel<layout, KALMAN>"},
-            "e2e": {"value": world * B * K / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * B * world,
+                         "mean_cells_per_env_step": cells_timed_total / (B * K), "kernel": "ipp_step_async_kernel" if eng.step_path == "async" else "ipp_step_kernel<MV, KALMAN>", "step_path": eng.step_path},
+            "e2e": {"value": world * B * KE / e2e_s, "steps": KE, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * B * world,
                     "d2h_bytes_per_step": 4 * B * world * (world if dist is not None else 1),
                     "path": "BatchedEngine.step (ipp_step: pinned host ids -> H2D -> fused kernel -> D2H rewards)" if dist is None else
                             "pinned host ids -> H2D -> ipp_step_device -> NCCL all_gather(rewards) -> D2H"},
@@ -291,13 +294,14 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "mv"), choices=["planes", "mv"])
     ap.add_argument("--cpu-envs", type=int, default=4096, help="env sample of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=500, help="steps of the host-buffer (e2e) leg (<= --steps)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -1,0 +1,85 @@
+"""Env-batch sharding across GPUs (one process per GPU, ``torch.distributed``).
+
+Envs are independent (the reference deep-copies one Mapping per repetition / episode,
+experiments/experiments.py:181-185, planning/mcts_zero/episode_generators.py:53), so the hot path
+shards with NO collective: rank r owns the contiguous env slice ``shard_bounds(total, world, r)``
+with its own maps in its own HBM.  An env's RNG stream is keyed by its GLOBAL id
+(``ipp_config.env_id_offset``), so results do not depend on the split.  The only exchange is the
+one a trainer's experience buffer needs: an all-gather of the per-env rewards (4 B per env per step).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .engine import BatchedEngine, EngineConfig
+
+
+def shard_bounds(total: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """(first_env, count) of rank's contiguous slice; the remainder goes to the lowest ranks."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    base, rem = divmod(int(total), int(world_size))
+    count = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, count
+
+
+def all_shard_counts(total: int, world_size: int) -> List[int]:
+    return [shard_bounds(total, world_size, r)[1] for r in range(world_size)]
+
+
+def sharded_config(cfg: EngineConfig, total_envs: int, world_size: int, rank: int, device: Optional[int] = None) -> EngineConfig:
+    """Config of this rank's engine: its slice size, its global env-id offset, its device."""
+    first, count = shard_bounds(total_envs, world_size, rank)
+    if count < 1:
+        raise ValueError(f"rank {rank} of {world_size} gets no env out of {total_envs}")
+    kw = dict(cfg.__dict__)
+    kw.update(batch=count, env_id_offset=cfg.env_id_offset + first)
+    if device is not None:
+        kw["device"] = device
+    return EngineConfig(**kw)
+
+
+def gather_rewards(local, total_envs: int, group=None):
+    """All-gather the per-env rewards of every rank into one (total_envs,) tensor, ordered by global
+    env id.  ``local`` is this rank's 1-D torch tensor (CUDA with the nccl backend, CPU with gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    counts = all_shard_counts(total_envs, world)
+    if local.numel() != counts[dist.get_rank(group)]:
+        raise ValueError(f"local rewards have {local.numel()} entries, this rank owns {counts[dist.get_rank(group)]} envs")
+    if len(set(counts)) == 1:
+        out = torch.empty(total_envs, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    # uneven split: pad every shard to the largest one, gather, drop the padding
+    width = max(counts)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    out = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * width : r * width + c] for r, c in enumerate(counts)])
+
+
+class ShardedEngine:
+    """This rank's slice of a ``total_envs`` batch.  ``step`` takes / returns LOCAL arrays; ``global_slice``
+    tells which rows of a global action array belong here."""
+
+    def __init__(self, cfg: EngineConfig, total_envs: int, world_size: int, rank: int, device: Optional[int] = None):
+        self.total_envs, self.world_size, self.rank = total_envs, world_size, rank
+        self.first, self.count = shard_bounds(total_envs, world_size, rank)
+        self.engine = BatchedEngine(sharded_config(cfg, total_envs, world_size, rank, device))
+
+    @property
+    def global_slice(self) -> slice:
+        return slice(self.first, self.first + self.count)
+
+    def step(self, global_actions: np.ndarray, **kw) -> np.ndarray:
+        return self.engine.step(np.asarray(global_actions)[self.global_slice], **kw)
+
+    def close(self):
+        self.engine.close()

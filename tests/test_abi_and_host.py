@@ -1,0 +1,235 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ipp_b200.h declares (no compute calls
+without a GPU), the ctypes structs match the header's layout, the host-side mirror of the reference
+interface behaves like the reference (names, validation, error behaviour), and the env-batch sharding
+works across 2 processes (gloo)."""
+import ctypes
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ipp_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ipp_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ipp_rl_b200 import _capi
+
+    lib = _capi.load_library()
+    declared = _declared_functions()
+    assert len(declared) >= 24
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ipp_b200.h but not exported"
+    assert sorted(_capi.SIGNATURES) == declared, "ctypes SIGNATURES must list exactly the header's functions"
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    from ipp_rl_b200 import _capi
+
+    probe = tmp_path / "sz.c"
+    probe.write_text(
+        f'#include "{HEADER}"\n#include <stdio.h>\n#include <stddef.h>\n'
+        "int main(){printf(\"%zu %zu %zu %zu %zu\\n\", sizeof(ipp_config), sizeof(ipp_info), offsetof(ipp_config, resolution), "
+        "offsetof(ipp_config, seed), offsetof(ipp_info, altitude)); return 0;}\n"
+    )
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", str(probe), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(_capi.ipp_config), ctypes.sizeof(_capi.ipp_info), _capi.ipp_config.resolution.offset,
+                     _capi.ipp_config.seed.offset, _capi.ipp_info.altitude.offset]
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from ipp_rl_b200 import _capi
+
+    with pytest.raises(_capi.IppLibraryError):
+        _capi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ipp_rl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+                assert "ipp_oracle" not in txt or f.endswith((".cuh", ".cu")) and "Mirrored in oracle" in txt, f
+
+
+# ---- host mirror of the reference interface ---------------------------------------------------------
+def _params():
+    from tests._util import make_params
+
+    return make_params(10, 10, 4, 8, 14, 6)
+
+
+def test_factories_validate_like_the_reference():
+    from ipp_rl_b200.mapping.grid_maps import GridMap
+    from ipp_rl_b200.sensors.models.sensor_model_factories import SensorModelFactory
+    from ipp_rl_b200.sensors.models.sensor_models import AltitudeSensorModel
+    from ipp_rl_b200.sensors.sensor_factories import SensorFactory
+    from ipp_rl_b200.sensors.cameras import RGBCamera
+
+    p = _params()
+    gm = GridMap(p)
+    assert (gm.x_dim, gm.y_dim, gm.resolution, gm.num_grid_cells) == (10, 10, 4, 100)
+    model = SensorModelFactory(p).create_sensor_model()
+    assert isinstance(model, AltitudeSensorModel) and (model.coeff_a, model.coeff_b) == (0.05, 0.2)
+    sensor = SensorFactory(p, model, gm).create_sensor()
+    assert isinstance(sensor, RGBCamera) and sensor.sensor_simulation is None
+    # missing / unknown keys -> ValueError (reference: logger.error + bare raise ValueError)
+    with pytest.raises(ValueError):
+        GridMap({}).x_dim
+    bad = _params()
+    bad["sensor"]["model"]["type"] = "unknown_model"
+    with pytest.raises(ValueError):
+        SensorModelFactory(bad)
+    bad = _params()
+    del bad["sensor"]["model"]["coeff_b"]
+    with pytest.raises(ValueError):
+        SensorModelFactory(bad)
+    bad = _params()
+    bad["sensor"]["type"] = "lidar"
+    with pytest.raises(ValueError):
+        SensorFactory(bad, model, gm)
+    bad = _params()
+    del bad["sensor"]["encoding"]
+    with pytest.raises(ValueError):
+        SensorFactory(bad, model, gm)
+
+
+def test_host_sensor_and_actions_match_reference_vectors():
+    from ipp_rl_b200.mapping.grid_maps import GridMap
+    from ipp_rl_b200.planning.common import actions
+    from ipp_rl_b200.sensors.models.sensor_model_factories import SensorModelFactory
+    from ipp_rl_b200.sensors.sensor_factories import SensorFactory
+    from tests._util import golden, params_from_json
+
+    g = golden("golden_sensor_actions_metrics.npz")
+    for si in range(int(g["fp_count"])):
+        p = params_from_json(g[f"fp{si}_cfg"])
+        p["sensor"].update(type="rgb_camera", encoding="rgb8")
+        p["sensor"]["model"]["type"] = "altitude_dependent"
+        gm = GridMap(p)
+        model = SensorModelFactory(p).create_sensor_model()
+        s = SensorFactory(p, model, gm).create_sensor()
+        for q, f, r, s2 in list(zip(g[f"fp{si}_poses"], g[f"fp{si}_fov"], g[f"fp{si}_rf"], g[f"fp{si}_sigma2"]))[::3]:
+            assert s.project_field_of_view(q) == tuple(int(t) for t in f)
+            assert s.get_resolution_factor(q) == r
+            assert model.get_noise_variance(q) == pytest.approx(s2, abs=1e-16)
+    gm = GridMap(_params())
+    assert np.array_equal(actions.action_table(gm, 8, 14, 6), g["act_ex10_table"])
+    assert np.array_equal(actions.action_dict_to_np_array(actions.enumerate_actions(gm, 8, 14, 6)), g["act_ex10_table"])
+    uav = {"max_v": 2, "max_a": 2}
+    for a, b, ft, ed in zip(g["cost_a"], g["cost_b"], g["cost_flight_time"], g["cost_distance"]):
+        assert actions.action_costs(a, b, uav) == pytest.approx(ft, abs=1e-13)
+        assert actions.action_costs(a, b, None) == pytest.approx(ed, abs=1e-13)
+    acts = actions.get_actions(np.array([2.0, 2.0, 14.0]), 12.0, gm, 8, 14, 6, uav)
+    want = [a for a in g["act_ex10_table"] if 0 < actions.action_costs(a, np.array([2.0, 2.0, 14.0]), uav) <= 12.0]
+    assert sorted(map(tuple, acts)) == sorted(map(tuple, want)) and len(acts) > 0
+
+
+def test_host_metrics_and_rewards_match_reference_vectors():
+    from ipp_rl_b200.mapping.grid_maps import DiagonalCovariance
+    from ipp_rl_b200.planning import evaluation_metrics as em
+    from ipp_rl_b200.planning.common import rewards
+    from tests._util import golden
+
+    g = golden("golden_sensor_actions_metrics.npz")
+    for k, (Y, X) in enumerate(g["met_shapes"]):
+        gt, mean, var, msk = (g[n][k, :Y, :X] for n in ("met_gt", "met_mean", "met_var", "met_mask"))
+        cov, m = DiagonalCovariance(var), msk.astype(bool).ravel()
+        with np.errstate(all="ignore"):
+            got = [em.root_mean_squared_error(gt, mean), em.weighted_root_mean_squared_error(gt, mean), em.mean_log_loss(gt, mean, cov),
+                   em.weighted_mean_log_loss(gt, mean, cov), em.map_uncertainty(cov), em.map_uncertainty_difference(cov, m),
+                   em.root_mean_squared_error(gt, mean, m), em.map_uncertainty(cov, m)]
+        for x, y in zip(g["met_values"][k], got):
+            assert (np.isnan(x) and np.isnan(y)) or y == pytest.approx(x, rel=1e-12)
+        assert np.array_equal(rewards.compute_adaptive_msk(mean, cov, 0.6, 0.3), m)
+        assert np.array_equal(np.diag(np.asarray(cov)), var.ravel()) and np.trace(cov) == pytest.approx(var.sum())
+
+
+def test_ground_truth_generators_are_seed_compatible():
+    from ipp_rl_b200.simulations import ground_truths
+
+    def ref_like(pk, x_dim, y_dim):  # straight transcription of the published algorithm, scalar loops
+        noise = np.fft.fft2(np.random.normal(size=(y_dim, x_dim)))
+        amp = np.zeros((y_dim, x_dim))
+        for i, kx in enumerate(ground_truths.fft_indices(y_dim)):
+            for j, ky in enumerate(ground_truths.fft_indices(x_dim)):
+                amp[i, j] = 0.0 if (kx == 0 and ky == 0) else np.sqrt(pk(np.sqrt(float(kx) ** 2 + float(ky) ** 2)))
+        f = np.fft.ifft2(noise * amp).real
+        return (f - f.min()) / (f.max() - f.min())
+
+    for x, y in [(10, 10), (17, 12), (32, 32)]:
+        np.random.seed(5)
+        a = ground_truths.gaussian_random_field(lambda k: k ** (-5.0), x, y)
+        np.random.seed(5)
+        b = ref_like(lambda k: k ** (-5.0), x, y)
+        assert a.shape == (y, x) and np.max(np.abs(a - b)) < 1e-10 and a.min() == 0 and a.max() == 1
+
+
+def test_facade_objects_pickle_without_cuda_handles():
+    from ipp_rl_b200.mapping.grid_maps import DiagonalCovariance, GridMap
+
+    gm = GridMap(_params())
+    gm.mean, gm.cov_matrix = np.zeros((10, 10)), DiagonalCovariance(np.ones(100))
+    setattr(gm, "_b200_backend", lambda: 0)  # stands for a live device backend: not picklable
+    clone = pickle.loads(pickle.dumps(gm))
+    assert not hasattr(clone, "_b200_backend") and clone.x_dim == 10 and np.trace(clone.cov_matrix) == 100
+
+
+# ---- sharding (N > 1 path) -----------------------------------------------------------------------------
+def test_shard_bounds_cover_the_batch():
+    from ipp_rl_b200.distributed import all_shard_counts, shard_bounds, sharded_config
+    from ipp_rl_b200 import EngineConfig
+
+    for total, world in [(65536, 8), (131072, 8), (10, 3), (7, 7), (100, 1)]:
+        spans = [shard_bounds(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+            assert f0 + c0 == f1
+        assert all_shard_counts(total, world) == [c for _, c in spans]
+    cfg = sharded_config(EngineConfig(batch=1, env_id_offset=5), 10, 3, 2, device=2)
+    assert (cfg.batch, cfg.env_id_offset, cfg.device) == (3, 5 + 7, 2)
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from ipp_rl_b200.distributed import gather_rewards, shard_bounds
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+for total in (10, 7):
+    first, count = shard_bounds(total, 2, rank)
+    local = torch.arange(first, first + count, dtype=torch.float32) * 1.5   # "reward" of global env i = 1.5 i
+    out = gather_rewards(local, total)
+    assert torch.equal(out, torch.arange(total, dtype=torch.float32) * 1.5), (rank, out)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gather_rewards_two_processes_gloo(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-2000:]
+        assert "ok" in so
