@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libipp_b200.so")
+LIB_PATH = os.environ.get("IPP_B200_LIB") or os.path.join(_HERE, "csrc", "libipp_b200.so")  # override: ablation builds
 
 IPP_ABI_VERSION = 1
 IPP_OK = 0

@@ -52,6 +52,7 @@ struct ipp_engine {
     bool async_ok = false;
     int step_path = IPP_PATH_ASYNC;  // requested path (ipp_set_option / IPP_STEP_PATH)
     int async_warps = 0, async_mv_tile = 0, async_gt_tile = 0;
+    bool async_vec16 = false;
     float2 *d_level_taps = nullptr;
     int level_tap_mode[kLevelTabs] = {-1, -1, -1, -1};
     size_t async_smem = 0;
@@ -356,12 +357,20 @@ static int setup_async(ipp_engine *e) {
     if ((rc = dev_alloc(e, &e->d_tickets, 2)) != IPP_OK) return rc;
     CU(e, cudaMemsetAsync(e->d_tickets, 0, 2 * sizeof(unsigned int), e->stream));
     if (c.layout != IPP_LAYOUT_MV) return IPP_OK;
-    int max_cells = 0;  // even pitch * rows of the largest footprint
+    // tile capacities for the largest footprint; with 16-byte staging (x_dim % 4 == 0) the tiles hold the
+    // aligned superset of each row: {mean,var} pitch = roundup(1 + fw, 2) cells, gt pitch = roundup(3 + fw, 4) floats
+    e->async_vec16 = (c.x_dim % 4 == 0);
+    const char *v16 = getenv("IPP_ASYNC_VEC16");
+    if (v16 && v16[0] == '0') e->async_vec16 = false;
+    int mv_cells = 0, gt_cells = 0;
     for (int k = 0; k < e->n_levels; ++k) {
         const int fw = std::min(2 * e->lut[k].rx + 1, c.x_dim), fh = std::min(2 * e->lut[k].ry + 1, c.y_dim);
-        max_cells = std::max(max_cells, ((fw + 1) & ~1) * fh);
+        const int pm = e->async_vec16 ? round_up(fw + 1, 2) : round_up(fw, 2);
+        const int pg = e->async_vec16 ? round_up(fw + 3, 4) : round_up(fw, 2);
+        mv_cells = std::max(mv_cells, pm * fh);
+        gt_cells = std::max(gt_cells, pg * fh);
     }
-    const int mv_tile = round_up(max_cells * 8, 16), gt_tile = round_up(max_cells * 4, 16);
+    const int mv_tile = round_up(mv_cells * 8, 16), gt_tile = round_up(gt_cells * 4, 16);
     const size_t per_warp = (size_t)kAsyncSlots * (mv_tile + gt_tile) + kAsyncSlots * sizeof(SlotCtl) + kTapFloats2 * sizeof(float2);
     const size_t per_cta = (size_t)kLevelTabs * kTapFloats2 * sizeof(float2);
     int dev_smem = 0;
@@ -412,6 +421,7 @@ static int launch_async(ipp_engine *e, const StepParams &p) {
     ap.warps = e->async_warps;
     ap.mv_tile_bytes = e->async_mv_tile;
     ap.gt_tile_bytes = e->async_gt_tile;
+    ap.vec16 = e->async_vec16 ? 1 : 0;
     const int needed = (p.n_jobs + e->async_warps - 1) / e->async_warps;
     const int grid = std::max(1, std::min(e->sm_count, needed));
     ipp_step_async_kernel<<<grid, e->async_warps * 32, e->async_smem, e->stream>>>(ap);

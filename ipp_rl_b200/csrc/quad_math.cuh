@@ -114,6 +114,30 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, fl
     n1 = r * __sinf(th);
 }
 
+// The engine's noise stream (mirrored by oracle device_noise_field):
+//   rf = 1: quad q draws group q;  its four cells use the group's four normals.
+//   rf = 2: measurement i uses normal (i >> 5) & 3 of group (i & 31) + 32 * (i >> 7), i.e. with i = q =
+//           lane + 32 * iteration a lane keeps the four normals of ONE Philox call for four consecutive
+//           iterations — one call per four measurement blocks instead of one each, no cross-lane traffic.
+// `cache` must persist across the iterations of one env.
+__device__ __forceinline__ void draw_normals(const StepParams &p, int rf, int q, uint32_t env_id, float (&cache)[4], float (&eps)[4]) {
+    if (rf == 1) {
+        uint32_t rnd[4];
+        philox4x32_10((uint32_t)q, env_id, p.step_lo, p.step_hi, p.seed_lo, p.seed_hi, rnd);
+        box_muller(rnd[0], rnd[1], eps[0], eps[1]);
+        box_muller(rnd[2], rnd[3], eps[2], eps[3]);
+    } else {
+        const int t = (q >> 5) & 3;
+        if (t == 0) {  // warp-uniform: every lane is in the same iteration
+            uint32_t rnd[4];
+            philox4x32_10((uint32_t)((q & 31) + 32 * (q >> 7)), env_id, p.step_lo, p.step_hi, p.seed_lo, p.seed_hi, rnd);
+            box_muller(rnd[0], rnd[1], cache[0], cache[1]);
+            box_muller(rnd[2], rnd[3], cache[2], cache[3]);
+        }
+        eps[0] = t == 0 ? cache[0] : (t == 1 ? cache[1] : (t == 2 ? cache[2] : cache[3]));
+    }
+}
+
 // floor(n / d) for 0 <= n < 2^31, d >= 1 and n/d < 2^20: float estimate (error < 1) + one correction.
 __device__ __forceinline__ int fdiv(int n, int d, float inv_d) {
     int q = (int)(__int2float_rz(n) * inv_d);

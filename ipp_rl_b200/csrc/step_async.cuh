@@ -29,9 +29,15 @@
 
 namespace ipp {
 
-constexpr int kAsyncSlots = 2;      // footprints in flight per warp
-constexpr int kAsyncMaxWarps = 16;
-constexpr int kTicketChunk = 4;     // tickets taken per atomic
+#ifndef IPP_ASYNC_SLOTS
+#define IPP_ASYNC_SLOTS 2
+#endif
+#ifndef IPP_ASYNC_MAX_WARPS
+#define IPP_ASYNC_MAX_WARPS 16
+#endif
+constexpr int kAsyncSlots = IPP_ASYNC_SLOTS;         // footprints in flight per warp
+constexpr int kAsyncMaxWarps = IPP_ASYNC_MAX_WARPS;  // warps per CTA (1 CTA / SM), further limited by shared memory
+constexpr int kTicketChunk = 8;                      // tickets taken per atomic
 constexpr int kLevelTabs = 4;       // altitude levels whose interior tap tables are staged in smem
 constexpr int kTapFloats2 = 2 * kTapCap * 3;  // float2 per tap-table pair (rows + cols)
 
@@ -43,6 +49,7 @@ struct AsyncParams {
     int warps;                 // warps per CTA
     int mv_tile_bytes;         // per-slot tile capacities (multiples of 16 B)
     int gt_tile_bytes;
+    int vec16;                 // 1: 16-byte L1-bypassing staging copies (x_dim % 4 == 0)
     int level_tap_mode[kLevelTabs];  // TAPS_FAST / TAPS_WIDE, or -1: no table for this level
 };
 
@@ -61,6 +68,9 @@ __device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -124,52 +134,88 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 *reinterpret_cast<int4 *>(&c->xl) = make_int4(xl, yu, nx, ny);
             }
             if (lane < 3) cp_async_8(smem_u32(&c->prev[lane]), p.prev_state + 3 * (size_t)job + lane);
-            // lanes are laid out as RP row-segments of W columns: a warp instruction covers RP rows of the
-            // footprint, each a coalesced run of 32 B sectors; addresses advance by constant strides
-            const int W = nx <= 8 ? 8 : (nx <= 16 ? 16 : 32);
-            const int RP = 32 / W;
-            const int lr = lane / W, lc = lane - lr * W;
-            const size_t org = (size_t)job * p.plane + (size_t)(yu * X + xl);
             const uint32_t tile = smem_u32(my_stages + (size_t)s * stage_bytes);
-            for (int c0 = lc; c0 < nx; c0 += 32) {  // one pass unless the footprint is wider than 32 cells
-                const float2 *src_mv = mv_base + org + (size_t)(lr * X + c0);
-                const float *src_gt = p.gt + org + (size_t)(lr * X + c0);
-                uint32_t dst_mv = tile + 8u * (uint32_t)(lr * pitch + c0);
-                uint32_t dst_gt = tile + (uint32_t)ap.mv_tile_bytes + 4u * (uint32_t)(lr * pitch + c0);
+            if (ap.vec16) {
+                // 16-byte copies that bypass L1 (cp.async.cg): every row is fetched as the 16-byte aligned
+                // superset of its footprint segment — the same 32 B sectors, a quarter of the copy instructions,
+                // and no L1 line allocation limiting the copies in flight.  Needs x_dim % 4 == 0.
+                const int ox = xl & 1, oxg = xl & 3;
+                const int cm = (ox + nx + 1) >> 1, cg = (oxg + nx + 3) >> 2;  // 16 B chunks per row
+                const size_t row0 = (size_t)job * p.plane + (size_t)(yu * X);
+                {
+                    const int W = cm <= 8 ? 8 : (cm <= 16 ? 16 : 32), RP = 32 / W;
+                    const int lr = lane / W, lc = lane - lr * W;
+                    for (int c0 = lc; c0 < cm; c0 += 32) {
+                        const float4 *src = reinterpret_cast<const float4 *>(mv_base + row0 + (xl - ox)) + (size_t)(lr * (X >> 1) + c0);
+                        uint32_t dst = tile + 16u * (uint32_t)(lr * cm + c0);
 #pragma unroll 2
-                for (int r = lr; r < ny; r += RP) {
-                    cp_async_8(dst_mv, src_mv);
-                    cp_async_4(dst_gt, src_gt);
-                    src_mv += RP * X;
-                    src_gt += RP * X;
-                    dst_mv += 8u * (uint32_t)(RP * pitch);
-                    dst_gt += 4u * (uint32_t)(RP * pitch);
+                        for (int r = lr; r < ny; r += RP) {
+                            cp_async_16(dst, src);
+                            src += RP * (X >> 1);
+                            dst += 16u * (uint32_t)(RP * cm);
+                        }
+                    }
+                }
+                {
+                    const int W = cg <= 8 ? 8 : (cg <= 16 ? 16 : 32), RP = 32 / W;
+                    const int lr = lane / W, lc = lane - lr * W;
+                    for (int c0 = lc; c0 < cg; c0 += 32) {
+                        const float4 *src = reinterpret_cast<const float4 *>(p.gt + row0 + (xl - oxg)) + (size_t)(lr * (X >> 2) + c0);
+                        uint32_t dst = tile + (uint32_t)ap.mv_tile_bytes + 16u * (uint32_t)(lr * cg + c0);
+#pragma unroll 2
+                        for (int r = lr; r < ny; r += RP) {
+                            cp_async_16(dst, src);
+                            src += RP * (X >> 2);
+                            dst += 16u * (uint32_t)(RP * cg);
+                        }
+                    }
+                }
+            } else {
+                // lanes are laid out as RP row-segments of W columns: a warp instruction covers RP rows of the
+                // footprint, each a coalesced run of 32 B sectors; addresses advance by constant strides
+                const int W = nx <= 8 ? 8 : (nx <= 16 ? 16 : 32);
+                const int RP = 32 / W;
+                const int lr = lane / W, lc = lane - lr * W;
+                const size_t org = (size_t)job * p.plane + (size_t)(yu * X + xl);
+                for (int c0 = lc; c0 < nx; c0 += 32) {  // one pass unless the footprint is wider than 32 cells
+                    const float2 *src_mv = mv_base + org + (size_t)(lr * X + c0);
+                    const float *src_gt = p.gt + org + (size_t)(lr * X + c0);
+                    uint32_t dst_mv = tile + 8u * (uint32_t)(lr * pitch + c0);
+                    uint32_t dst_gt = tile + (uint32_t)ap.mv_tile_bytes + 4u * (uint32_t)(lr * pitch + c0);
+#pragma unroll 2
+                    for (int r = lr; r < ny; r += RP) {
+                        cp_async_8(dst_mv, src_mv);
+                        cp_async_4(dst_gt, src_gt);
+                        src_mv += RP * X;
+                        src_gt += RP * X;
+                        dst_mv += 8u * (uint32_t)(RP * pitch);
+                        dst_gt += 4u * (uint32_t)(RP * pitch);
+                    }
                 }
             }
+        } else if (lane == 0) {
+            ctl[s].job = -1;  // out of work: the loop ends when it reaches this slot
         }
         cp_async_commit();  // always: keeps the group count in step with the slot rotation
     };
 
-    // ---- prologue: one ticket chunk; fill both slots ---------------------------------------------
+    // ---- prologue: one ticket chunk; fill every slot -----------------------------------------------
+    static_assert(kTicketChunk > kAsyncSlots, "the first chunk must cover the prologue fills plus one ticket");
     unsigned int chunk_base = 0;
     if (lane == 0) chunk_base = atomicAdd(ticket, (unsigned)kTicketChunk);
     chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
-    int chunk_used = 3;
-    int cur_job, other_job;
-    {
-        const unsigned int ta = chunk_base, tb = chunk_base + 1;
-        cur_job = ta < (unsigned)n_jobs ? (int)ta : -1;
-        other_job = tb < (unsigned)n_jobs ? (int)tb : -1;
-        const int ida = cur_job >= 0 ? __ldg(p.action_ids + cur_job) : 0;
-        const int idb = other_job >= 0 ? __ldg(p.action_ids + other_job) : 0;
-        fill(0, cur_job, ida);
-        fill(1, other_job, idb);
+    int chunk_used = kAsyncSlots + 1;
+#pragma unroll
+    for (int k = 0; k < kAsyncSlots; ++k) {
+        const unsigned int t = chunk_base + k;
+        const int jb = t < (unsigned)n_jobs ? (int)t : -1;
+        fill(k, jb, jb >= 0 ? __ldg(p.action_ids + jb) : 0);
     }
-    unsigned int tk = chunk_base + 2;  // ticket whose action id has not been loaded yet
+    unsigned int tk = chunk_base + kAsyncSlots;  // ticket whose action id has not been loaded yet
     int s = 0;
 
 #pragma unroll 1
-    while (cur_job >= 0) {
+    while (true) {
         // (A) start the next fetches early: action id of ticket tk and, when the chunk is used up, a fresh
         //     chunk of tickets — both are consumed only after this env has been fused
         const int job_n = tk < (unsigned)n_jobs ? (int)tk : -1;
@@ -186,17 +232,21 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         const int4 c0v = *reinterpret_cast<const int4 *>(&c->job);
         const int4 c1v = *reinterpret_cast<const int4 *>(&c->xl);
         const int job = c0v.x, lvl = c0v.y;
+        if (job < 0) break;  // warp-uniform: tickets are monotonic, every later slot is empty too
         const int xl = c1v.x, yu = c1v.y, nx = c1v.z, ny = c1v.w;
         const AltLevel &L = p.lut[lvl];
         const int rf = L.rf;
         const float s2 = L.s2;
-        const int pitch = (nx + 1) & ~1;
+        // tile geometry: with 16-byte staging the tiles start at the aligned cell left of the footprint
+        const int ox = ap.vec16 ? (xl & 1) : 0, oxg = ap.vec16 ? (xl & 3) : 0;
+        const int pm = ap.vec16 ? ((ox + nx + 1) & ~1) : ((nx + 1) & ~1);  // {mean,var} tile pitch [cells]
+        const int pg = ap.vec16 ? ((oxg + nx + 3) & ~3) : pm;              // ground-truth tile pitch [floats]
         const int nqx = (nx + 1) >> 1, nqy = (ny + 1) >> 1;
         const int nq = nqx * nqy;
         const int out_r = quirk ? nqx : nqy, out_c = quirk ? nqy : nqx;
         const unsigned char *st = my_stages + (size_t)s * stage_bytes;
-        const float2 *mv_t = reinterpret_cast<const float2 *>(st);
-        const float *gt_t = reinterpret_cast<const float *>(st + ap.mv_tile_bytes);
+        const float2 *mv_t = reinterpret_cast<const float2 *>(st) + ox;
+        const float *gt_t = reinterpret_cast<const float *>(st + ap.mv_tile_bytes) + oxg;
 
         // INTER_AREA tap tables: the per-level table when the footprint is unclipped, else built here
         TapView tapv;
@@ -229,6 +279,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         float2 *mv_g = mv_base + (size_t)job * p.plane + (size_t)(yu * X + xl);
         const size_t nrow = (size_t)job * (size_t)p.noise_stride;
         float acc = 0.0f;
+        float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four iterations
 
         if (unsupported) {
             if (lane == 0) atomicOr(p.status, 1);
@@ -243,8 +294,15 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 const int r1 = min(r0 + 1, ny - 1);  // clamped: the tile has exactly ny rows
 
                 // ---- belief from the staged tile: two 128-bit shared loads (pitch is even) -------
-                const float4 top = *reinterpret_cast<const float4 *>(mv_t + r0 * pitch + c0);
-                const float4 bot = *reinterpret_cast<const float4 *>(mv_t + r1 * pitch + c0);
+                float4 top, bot;
+                if (ox == 0) {  // warp-uniform: 16-byte aligned quad rows
+                    top = *reinterpret_cast<const float4 *>(mv_t + r0 * pm + c0);
+                    bot = *reinterpret_cast<const float4 *>(mv_t + r1 * pm + c0);
+                } else {
+                    const float2 a = mv_t[r0 * pm + c0], b = mv_t[r0 * pm + c0 + 1], c2 = mv_t[r1 * pm + c0], d2 = mv_t[r1 * pm + c0 + 1];
+                    top = make_float4(a.x, a.y, b.x, b.y);
+                    bot = make_float4(c2.x, c2.y, d2.x, d2.y);
+                }
                 const float m[4] = {top.x, cok ? top.z : 0.0f, rok ? bot.x : 0.0f, ok[3] ? bot.z : 0.0f};
                 const float v[4] = {top.y, cok ? top.w : 0.0f, rok ? bot.y : 0.0f, ok[3] ? bot.w : 0.0f};
 
@@ -259,15 +317,10 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                         eps[0] = __ldg(p.noise + nrow + q);
                     }
                 } else {
-                    uint32_t rnd[4];
-                    philox4x32_10((uint32_t)q, (uint32_t)job + p.env_id_offset, p.step_lo, p.step_hi, p.seed_lo, p.seed_hi, rnd);
-                    box_muller(rnd[0], rnd[1], eps[0], eps[1]);
-                    if (rf == 1) box_muller(rnd[2], rnd[3], eps[2], eps[3]);
+                    draw_normals(p, rf, q, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
                 }
                 if (rf == 1) {
-                    const float2 g0 = *reinterpret_cast<const float2 *>(gt_t + r0 * pitch + c0);
-                    const float2 g1 = *reinterpret_cast<const float2 *>(gt_t + r1 * pitch + c0);
-                    const float gv[4] = {g0.x, g0.y, g1.x, g1.y};
+                    const float gv[4] = {gt_t[r0 * pg + c0], gt_t[r0 * pg + c0 + 1], gt_t[r1 * pg + c0], gt_t[r1 * pg + c0 + 1]};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) z[k] = ok[k] ? __saturatef(fmaf(s2, eps[k], gv[k])) : 0.0f;
                 } else {
@@ -276,7 +329,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                         pr = small ? (int)(((uint32_t)q * magic_c) >> 16) : fdiv(q, out_c, inv_outc);
                         pc = q - pr * out_c;
                     }
-                    const float d = downsample<false>(tap_mode, gt_t, pitch, tapv, pr, pc, ny, nx, out_r, out_c);
+                    const float d = downsample<false>(tap_mode, gt_t, pg, tapv, pr, pc, ny, nx, out_r, out_c);
                     z[0] = __saturatef(fmaf(s2, eps[0], d));
                 }
                 if (p.z_out != nullptr) {
@@ -329,9 +382,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         }
         tk = chunk_base + (unsigned)chunk_used;
         ++chunk_used;
-        cur_job = other_job;
-        other_job = job_n;
-        s ^= 1;
+        s = (s + 1 == kAsyncSlots) ? 0 : s + 1;
     }
     cp_async_wait<0>();
 }

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
     const size_t nrow = (size_t)job * (size_t)p.noise_stride;
 
     float acc = 0.0f;  // per-lane partial (<= a few dozen quads); fp64 tree across the warp
+    float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int q = lane; q < nq; q += 32) {
         const int qy = fdiv(q, nqx, inv_nqx), qx = q - qy * nqx;
@@ -158,10 +159,7 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
                         eps[0] = __ldg(p.noise + nrow + q);
                     }
                 } else {
-                    uint32_t rnd[4];
-                    philox4x32_10((uint32_t)q, (uint32_t)env + p.env_id_offset, p.step_lo, p.step_hi, p.seed_lo, p.seed_hi, rnd);
-                    box_muller(rnd[0], rnd[1], eps[0], eps[1]);
-                    if (g.rf == 1) box_muller(rnd[2], rnd[3], eps[2], eps[3]);
+                    draw_normals(p, g.rf, q, (uint32_t)env + p.env_id_offset, nrm_cache, eps);
                 }
                 if (g.rf == 1) {
 #pragma unroll

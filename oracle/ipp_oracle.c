@@ -206,8 +206,8 @@ int orc_step(const orc_cfg *c, int B, const double *gt, double *mean, double *va
                 } else {
                     for (int i = 0; i < nz; ++i) {
                         double n4[4];
-                        device_normals(seed, (uint32_t)(env_offset + b), step, (uint32_t)i, n4);
-                        z[i] += s2 * n4[0];
+                        device_normals(seed, (uint32_t)(env_offset + b), step, (uint32_t)((i & 31) + 32 * (i >> 7)), n4);
+                        z[i] += s2 * n4[(i >> 5) & 3];
                     }
                 }
             }

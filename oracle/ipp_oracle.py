@@ -575,7 +575,8 @@ def device_noise_field(cfg: OracleConfig, position, seed: int, env: int, step: i
     """The eps array (measurement shape, C order) the engine's Philox mode applies for this
     (env, step).  The footprint is tiled by 2x2 cell quads anchored at (yu, xl), quad index
     ``g = qy * ceil(nx/2) + qx``.  rf=1: cell (2qy+dy, 2qx+dx) uses normal ``[g, 2*dy+dx]``.
-    rf=2: measurement i (flat index into z) uses normal ``[i, 0]``."""
+    rf=2: measurement i (flat index into z) uses normal ``[(i & 31) + 32 * (i >> 7), (i >> 5) & 3]`` — four
+    consecutive 32-blocks of measurements share one Philox call per lane position (quad_math.cuh draw_normals)."""
     xl, xr, yu, yd = project_field_of_view(cfg, position)
     nx, ny = xr - xl + 1, yd - yu + 1
     rf = resolution_factor(cfg, position)
@@ -588,7 +589,11 @@ def device_noise_field(cfg: OracleConfig, position, seed: int, env: int, step: i
                 eps[r, c] = nrm[(r // 2) * nqx + (c // 2), 2 * (r % 2) + (c % 2)]
         return eps
     shape = measurement_shape(cfg, position)
-    return nrm[: shape[0] * shape[1], 0].reshape(shape)
+    m = shape[0] * shape[1]
+    i = np.arange(m)
+    groups = (i & 31) + 32 * (i >> 7)
+    nrm = device_normals(seed, env, step, int(groups.max()) + 1)
+    return nrm[groups, (i >> 5) & 3].reshape(shape)
 
 
 # --------------------------------------------------------------------------------------
