@@ -349,6 +349,21 @@ static int build_lut(ipp_engine *e) {
 // ------------------------------------------------------------------------------------------------
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+typedef void (*async_kernel_t)(const AsyncParams);
+// bit 0: entropy reward, bit 1: adaptive mask, bit 2: extras (host noise / measurement read-back)
+static async_kernel_t async_variant(int v) {
+    switch (v & 7) {
+        case 0: return ipp_step_async_kernel<false, false, false>;
+        case 1: return ipp_step_async_kernel<true, false, false>;
+        case 2: return ipp_step_async_kernel<false, true, false>;
+        case 3: return ipp_step_async_kernel<true, true, false>;
+        case 4: return ipp_step_async_kernel<false, false, true>;
+        case 5: return ipp_step_async_kernel<true, false, true>;
+        case 6: return ipp_step_async_kernel<false, true, true>;
+        default: return ipp_step_async_kernel<true, true, true>;
+    }
+}
+
 // cp.async-staged persistent path: needs the MV layout and footprints that fit two slots per warp.
 static int setup_async(ipp_engine *e) {
     const ipp_config &c = e->cfg;
@@ -381,10 +396,11 @@ static int setup_async(ipp_engine *e) {
     e->async_mv_tile = mv_tile;
     e->async_gt_tile = gt_tile;
     e->async_smem = per_warp * warps + per_cta;
-    if (cudaFuncSetAttribute(ipp_step_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->async_smem) != cudaSuccess) {
-        cudaGetLastError();
-        return IPP_OK;
-    }
+    for (int v = 0; v < 8; ++v)
+        if (cudaFuncSetAttribute(async_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->async_smem) != cudaSuccess) {
+            cudaGetLastError();
+            return IPP_OK;
+        }
     // tap tables of the unclipped footprint of the first kLevelTabs levels (dsize-quirk orientation)
     int h_dims[4 * kLevelTabs] = {0};
     for (int k = 0; k < std::min(e->n_levels, kLevelTabs); ++k) {
@@ -424,7 +440,9 @@ static int launch_async(ipp_engine *e, const StepParams &p) {
     ap.vec16 = e->async_vec16 ? 1 : 0;
     const int needed = (p.n_jobs + e->async_warps - 1) / e->async_warps;
     const int grid = std::max(1, std::min(e->sm_count, needed));
-    ipp_step_async_kernel<<<grid, e->async_warps * 32, e->async_smem, e->stream>>>(ap);
+    const int variant = (((p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY) ? 1 : 0) | ((p.flags & IPP_FLAG_ADAPTIVE) ? 2 : 0) |
+                        ((p.noise != nullptr || p.z_out != nullptr) ? 4 : 0);
+    async_variant(variant)<<<grid, e->async_warps * 32, e->async_smem, e->stream>>>(ap);
     e->ticket_parity ^= 1;
     e->launches++;
     e->path_launches[IPP_PATH_ASYNC]++;

@@ -388,35 +388,50 @@ __device__ __forceinline__ float bernoulli_entropy(float l) {
 struct FuseCtx {
     int rf;
     float R, invR;
-    bool entropy;
 };
 
+// SFU reciprocal / log2 (1 instruction each, ~1 ulp): two orders below the 1e-5 parity tolerance
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ENTROPY and ADAPTIVE are compile-time: with run-time flags both reward variants are issued predicated-off
+// (ncu: ~50 wasted warp-instructions per env).
+template <bool ENTROPY, bool ADAPTIVE>
 __device__ __forceinline__ float kalman_quad(const FuseCtx &c, bool cok, bool rok, const float (&m)[4], const float (&v)[4],
                                              const float (&z)[4], const bool (&msk)[4], float (&mn)[4], float (&vn)[4]) {
+    constexpr float kHalfLn2 = 0.34657359f;  // 0.5 * ln 2
     float gain_q = 0.0f;
     if (c.rf == 1) {
         float prod = 1.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float S = v[k] + c.R;
-            const float gain = v[k] * __frcp_rn(S);
+            const float gain = v[k] * fast_rcp(S);
             vn[k] = gain * c.R;  // v R / (v + R)  ==  v - v^2/S, cancellation-free
             mn[k] = fmaf(gain, z[k] - m[k], m[k]);
-            if (c.entropy)
-                prod *= msk[k] ? S * c.invR : 1.0f;  // v/v' = S/R
+            const bool in = ADAPTIVE ? msk[k] : true;  // cells outside the footprint have v = 0: S/R = 1, v*gain = 0
+            if (ENTROPY)
+                prod *= in ? S * c.invR : 1.0f;  // v/v' = S/R
             else
-                gain_q += msk[k] ? v[k] * gain : 0.0f;
+                gain_q += in ? __fmul_rn(v[k], gain) : 0.0f;  // __fmul_rn: no context-dependent fma contraction
         }
-        if (c.entropy) gain_q = 0.5f * __logf(prod);
+        if (ENTROPY) gain_q = __fmul_rn(kHalfLn2, fast_lg2(prod));  // __fmul_rn: the caller's "acc +=" must not fuse
     } else {
-        const int cnt = 1 + (int)cok + (int)rok + (int)(cok && rok);
-        const float w = cnt == 4 ? 0.25f : 0.5f;  // sensor_models.py:76-79
+        const float w = (cok && rok) ? 0.25f : 0.5f;  // sensor_models.py:76-79: partial blocks weigh 1/rf
         const float w2 = w * w;
         const float sv = (v[0] + v[1]) + (v[2] + v[3]);
         const float sm = (m[0] + m[1]) + (m[2] + m[3]);
         const float S = fmaf(w2, sv, c.R);
-        const float invS = __frcp_rn(S);
-        const float innov = z[0] - w * sm;
+        const float invS = fast_rcp(S);
+        const float innov = fmaf(-w, sm, z[0]);
         float rest[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -424,17 +439,27 @@ __device__ __forceinline__ float kalman_quad(const FuseCtx &c, bool cok, bool ro
             const float vk_invS = v[k] * invS;
             vn[k] = vk_invS * rest[k];
             mn[k] = fmaf(w * vk_invS, innov, m[k]);
-            if (!c.entropy) gain_q += msk[k] ? w2 * v[k] * vk_invS : 0.0f;
+            if (!ENTROPY) gain_q += (ADAPTIVE ? msk[k] : true) ? __fmul_rn(w2 * v[k], vk_invS) : 0.0f;
         }
-        if (c.entropy) {
-            // prod_k v_k / v'_k = prod_k S / rest_k over the masked cells
-            const float a = (msk[0] ? rest[0] : S) * (msk[1] ? rest[1] : S);
-            const float b = (msk[2] ? rest[2] : S) * (msk[3] ? rest[3] : S);
-            const float S2 = S * S;
-            gain_q = 0.5f * __logf((S2 * __frcp_rn(a)) * (S2 * __frcp_rn(b)));
+        if (ENTROPY) {
+            // 0.5 ln prod_k v_k / v'_k = 0.5 ln( S^4 / prod_k f_k ),  f_k = rest_k for the masked cells, else S
+            // (cells outside the footprint have v = 0, i.e. rest = S): two independent SFU logs, no division
+            const float a = ((ADAPTIVE && !msk[0]) ? S : rest[0]) * ((ADAPTIVE && !msk[1]) ? S : rest[1]);
+            const float b = ((ADAPTIVE && !msk[2]) ? S : rest[2]) * ((ADAPTIVE && !msk[3]) ? S : rest[3]);
+            gain_q = __fmul_rn(kHalfLn2, fmaf(4.0f, fast_lg2(S), -fast_lg2(a * b)));
         }
     }
     return gain_q;
+}
+
+// run-time dispatch for callers that are not specialised themselves (the general kernel)
+__device__ __forceinline__ float kalman_quad_rt(bool entropy, bool adaptive, const FuseCtx &c, bool cok, bool rok, const float (&m)[4],
+                                                const float (&v)[4], const float (&z)[4], const bool (&msk)[4], float (&mn)[4],
+                                                float (&vn)[4]) {
+    if (entropy) {
+        return adaptive ? kalman_quad<true, true>(c, cok, rok, m, v, z, msk, mn, vn) : kalman_quad<true, false>(c, cok, rok, m, v, z, msk, mn, vn);
+    }
+    return adaptive ? kalman_quad<false, true>(c, cok, rok, m, v, z, msk, mn, vn) : kalman_quad<false, false>(c, cok, rok, m, v, z, msk, mn, vn);
 }
 
 }  // namespace ipp

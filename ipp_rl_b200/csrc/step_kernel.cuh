@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
     fc.rf = g.rf;
     fc.R = g.R;
     fc.invR = __frcp_rn(g.R);
-    fc.entropy = (p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY;
+    const bool entropy = (p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY;
 
     const float inv_nqx = __frcp_rn((float)nqx);
     const float inv_outc = __frcp_rn((float)out_c);
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
         bool msk[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) msk[k] = ok[k] && (!adaptive || (fmaf(p.kappa, v[k], m[k]) >= p.thr));
-        acc += kalman_quad(fc, cok, rok, m, v, z, msk, mn, vn);
+        acc += kalman_quad_rt(entropy, adaptive, fc, cok, rok, m, v, z, msk, mn, vn);
         if (commit) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -220,14 +220,14 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
     if (p.reward == nullptr && p.measure_only) return;
 
     // ---- warp-shuffle reduction of the per-env information gain ---------------------------------
-    double accd = (double)acc;
+    float accd = acc;  // fp32 tree: <= 32 partials of similar size, relative error ~3e-7
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, s);
 
     if (lane == 0) {
         const double *pv = p.prev_in != nullptr ? p.prev_in + 3 * (size_t)job : p.prev_state + 3 * (size_t)env;
         const float cost = job_cost(p, g.px, g.py, g.ph, pv[0], pv[1], pv[2]);
-        if (p.reward != nullptr) p.reward[job] = (float)accd * __frcp_rn(cost + 1.0f);
+        if (p.reward != nullptr) p.reward[job] = accd * fast_rcp(cost + 1.0f);
         if (commit && (p.flags & IPP_FLAG_KEEP_PREV) == 0) {
             double *ps = p.prev_state + 3 * (size_t)env;
             ps[0] = g.px;
