@@ -115,8 +115,11 @@ def run_reference(args, rank, world):
         "metric": "env_steps_per_sec", "value": res["steps_per_sec"], "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "C3: 200x200 grid, 3-altitude action set, Kalman fusion, entropy-reduction reward",
-                   "batch_per_step_sample": res["envs"], "grid": [200, 200]},
+        "config": {"workload": "C3: batch 65536 envs/GPU, 200x200 grid, 3-altitude action set {8,14,20} m, Kalman fusion, "
+                               "entropy-reduction reward (Gaussian-entropy extension; trace-reduction timed alongside)",
+                   "batch_per_step_sample": res["envs"], "grid": [200, 200], "noise": "Philox4x32-10 (same stream definition)",
+                   "note": "CPU port of the reference algorithm (oracle/ipp_oracle.c, fp64, OpenMP over envs); each step = one pass over a "
+                           "bounded env sample of the same workload"},
         "cpu_baseline": {"value": res["steps_per_sec"], "unit": "env-steps/s", "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": res["steps_per_sec"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

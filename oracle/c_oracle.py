@@ -30,6 +30,7 @@ def lib():
         _lib.orc_step.argtypes = [C.POINTER(orc_cfg), C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_uint64, C.c_int64, C.c_uint64, C.c_int,
                                                                                    C.c_void_p, C.c_void_p]
         _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_set_threads.argtypes = [C.c_int]
     return _lib
 
 
@@ -72,6 +73,16 @@ def step(cfg: orc_cfg, gt, mean, var, prev, actions, eps=None, seed=0, env_offse
     if rc != 0:
         raise RuntimeError(f"orc_step returned {rc}")
     return reward
+
+
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core it may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    lib().orc_set_threads(n)
+    return n
 
 
 def num_threads() -> int:

@@ -28,6 +28,7 @@ def run(workload: dict, steps: int = 3, warmup: int = 1, envs: int = 4096, rewar
     X, Y, res = workload["x_dim"], workload["y_dim"], workload["resolution"]
     cfg = c_oracle.make_cfg(X, Y, res, workload.get("angle_x", 60.0), workload.get("angle_y", 60.0), workload.get("coeff_a", 0.05),
                             workload.get("coeff_b", 0.2), 10.0, workload.get("max_v", 2.0), workload.get("max_a", 2.0))
+    c_oracle.use_all_cores()
     rng = np.random.RandomState(4242)
     base = _synthetic_gt(rng, 32, Y, X)
     gt = np.ascontiguousarray(base[np.arange(envs) % 32])

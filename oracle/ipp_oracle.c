@@ -41,6 +41,14 @@ typedef struct orc_cfg {
 #define ORC_FLAG_NO_DSIZE_QUIRK 8
 #define ORC_FLAG_PREDICT_ONLY 256
 
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
