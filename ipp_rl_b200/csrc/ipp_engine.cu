@@ -384,6 +384,9 @@ static int setup_async(ipp_engine *e) {
         const int pg = e->async_vec16 ? round_up(fw + 3, 4) : round_up(fw, 2);
         mv_cells = std::max(mv_cells, pm * fh);
         gt_cells = std::max(gt_cells, pg * fh);
+        // the kernel divides quad indices with a 16-bit magic multiplier: exact while quads * quads-per-row < 2^15
+        const int nqx = (fw + 1) / 2, nqy = (fh + 1) / 2;
+        if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;
     }
     const int mv_tile = round_up(mv_cells * 8, 16), gt_tile = round_up(gt_cells * 4, 16);
     const size_t per_warp = (size_t)kAsyncSlots * (mv_tile + gt_tile) + kAsyncSlots * sizeof(SlotCtl) + kTapFloats2 * sizeof(float2);

@@ -271,11 +271,11 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         FuseCtx fc;
         fc.rf = rf;
         fc.R = L.R;
-        fc.invR = __frcp_rn(L.R);
-        // q / nqx and q / out_c with a 16-bit magic multiplier floor(65536/d)+1 (exact for q*d < 65536)
-        const bool small = nq * max(nqx, out_c) < 65536;
-        const float inv_nqx = __frcp_rn((float)nqx), inv_outc = __frcp_rn((float)out_c);
-        const uint32_t magic_x = (uint32_t)(65536.0f * inv_nqx) + 1u, magic_c = (uint32_t)(65536.0f * inv_outc) + 1u;
+        fc.invR = fast_rcp(L.R);
+        // q / nqx and q / out_c with a 16-bit magic multiplier floor(65536/d)+1: exact for q*d < 65536, which
+        // the host guarantees for every footprint that fits the shared-memory tiles (setup_async)
+        const uint32_t magic_x = (uint32_t)(65536.0f * fast_rcp((float)nqx) * 1.00000012f) + 1u;
+        const uint32_t magic_c = (uint32_t)(65536.0f * fast_rcp((float)out_c) * 1.00000012f) + 1u;
         float2 *mv_g = mv_base + (size_t)job * p.plane + (size_t)(yu * X + xl);
         const size_t nrow = (size_t)job * (size_t)p.noise_stride;
         float acc = 0.0f;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         } else {
 #pragma unroll 1
             for (int q = lane; q < nq; q += 32) {
-                const int qy = small ? (int)(((uint32_t)q * magic_x) >> 16) : fdiv(q, nqx, inv_nqx);
+                const int qy = (int)(((uint32_t)q * magic_x) >> 16);
                 const int qx = q - qy * nqx;
                 const int r0 = 2 * qy, c0 = 2 * qx;
                 const bool cok = c0 + 1 < nx, rok = r0 + 1 < ny;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 } else {
                     int pr = qy, pc = qx;
                     if (out_c != nqx) {
-                        pr = small ? (int)(((uint32_t)q * magic_c) >> 16) : fdiv(q, out_c, inv_outc);
+                        pr = (int)(((uint32_t)q * magic_c) >> 16);
                         pc = q - pr * out_c;
                     }
                     const float d = downsample<false>(tap_mode, gt_t, pg, tapv, pr, pc, ny, nx, out_r, out_c);

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
     FuseCtx fc;
     fc.rf = g.rf;
     fc.R = g.R;
-    fc.invR = __frcp_rn(g.R);
+    fc.invR = fast_rcp(g.R);
     const bool entropy = (p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY;
 
     const float inv_nqx = __frcp_rn((float)nqx);
