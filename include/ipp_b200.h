@@ -50,6 +50,11 @@ extern "C" {
 /* ---- memory layouts of the belief in HBM --------------------------------------------------- */
 #define IPP_LAYOUT_PLANES 0 /* mean[B][Y][X], var[B][Y][X], gt[B][Y][X] */
 #define IPP_LAYOUT_MV 1     /* {mean,var}[B][Y][X] interleaved float2, gt[B][Y][X] */
+#define IPP_LAYOUT_TILED 2  /* every 128-byte line of HBM holds a 2-D tile: {mean,var} float2 in 4x4-cell tiles, gt float
+                               in 8(x) x 4(y)-cell tiles; tiles row-major over the map (padded to whole tiles), cells
+                               row-major inside a tile.  L2 fetches whole 128 B lines from DRAM, so a footprint pulls in
+                               ~1.4x its own bytes instead of ~2.1x with row-major maps.  Internal to the engine: the
+                               state / ground-truth entry points still exchange dense [n][y_dim][x_dim] arrays. */
 
 /* ---- cost model (planning/common/actions.py:8-41) ---------------------------------------- */
 #define IPP_COST_DISTANCE 0    /* uav_specifications is None -> Euclidean distance */
@@ -203,8 +208,8 @@ int ipp_eval(ipp_engine *e, float *metrics);
 int ipp_eval_device(ipp_engine *e, float *metrics);
 
 /* ---- interop ----------------------------------------------------------------------------------- */
-#define IPP_PTR_MEAN 0   /* PLANES: float[B][Y][X];  MV: float2[B][Y][X] base (mean at .x) */
-#define IPP_PTR_VAR 1    /* PLANES: float[B][Y][X];  MV: same base + 1 float (stride 2) */
+#define IPP_PTR_MEAN 0   /* PLANES: float[B][Y][X];  MV: float2[B][Y][X] base (mean at .x);  TILED: float2 tiles */
+#define IPP_PTR_VAR 1    /* PLANES: float[B][Y][X];  MV / TILED: same base + 1 float (stride 2) */
 #define IPP_PTR_GT 2
 #define IPP_PTR_REWARD 3 /* engine-owned float[batch] staging of the last host-API step */
 #define IPP_PTR_STREAM 4 /* the cudaStream_t the engine launches on */
@@ -213,7 +218,7 @@ void *ipp_device_ptr(ipp_engine *e, int32_t which);
 /* Runtime options.
  * IPP_OPT_STEP_PATH selects the kernel ipp_step uses for Kalman steps on action ids:
  *   IPP_PATH_ASYNC (default) persistent kernel, footprints staged with cp.async, double buffered
- *                            per warp (MV layout; falls back to LSU otherwise)
+ *                            per warp (MV and TILED layouts; falls back to LSU otherwise)
  *   IPP_PATH_LSU             general warp-per-env gather kernel (every mode / input form)
  * ipp_get_option(IPP_OPT_STEP_PATH) returns the path in effect; IPP_OPT_LAUNCHES_* (read only) count
  * the step launches per path.  The environment variable IPP_STEP_PATH=lsu|async sets the default. */

@@ -29,6 +29,7 @@ FLAG_KEEP_PREV = 64
 
 LAYOUT_PLANES = 0
 LAYOUT_MV = 1
+LAYOUT_TILED = 2
 COST_DISTANCE = 0
 COST_FLIGHT_TIME = 1
 MAX_ALTITUDE_LEVELS = 32

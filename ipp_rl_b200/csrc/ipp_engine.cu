@@ -25,9 +25,12 @@ struct ipp_engine {
     AltLevel lut[IPP_MAX_ALTITUDE_LEVELS]{};
     int max_meas = 0;
     int sm_count = 0;
-    size_t plane = 0;
+    size_t plane = 0;     // y_dim * x_dim (dense maps of the ABI)
+    size_t plane_mv = 0;  // cells per env in the belief arrays (TILED: whole 4x4 tiles)
+    size_t plane_gt = 0;  // cells per env in the ground-truth array (TILED: whole 8x4 tiles)
+    int txm = 0, txg = 0, tiles_y = 0;
     // HBM
-    float *d_mean = nullptr;  // PLANES: float[B*plane]; MV: float2[B*plane]
+    float *d_mean = nullptr;  // PLANES: float[B*plane]; MV / TILED: float2[B*plane_mv]
     float *d_var = nullptr;   // PLANES only
     float *d_gt = nullptr;
     double *d_prev = nullptr;  // [B][3]
@@ -119,7 +122,7 @@ __global__ void reset_kernel(float *mean, float *var, int layout, size_t plane, 
     const size_t total = plane * (size_t)batch;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const float pv = prior_var_env ? prior_var_env[i / plane] : prior_var;
-        if (layout == IPP_LAYOUT_MV) {
+        if (layout != IPP_LAYOUT_PLANES) {
             reinterpret_cast<float2 *>(mean)[i] = make_float2(prior_mean, pv);
         } else {
             mean[i] = prior_mean;
@@ -154,6 +157,44 @@ __global__ void mv_pack_kernel(float2 *mv, const float *mean, const float *var, 
     }
 }
 
+// dense [n][Y][X] <-> IPP_LAYOUT_TILED (quad_math.cuh): one thread per dense cell
+struct TiledDims {
+    int X, Y, txm, txg;
+    size_t plane, plane_mv, plane_gt;
+};
+__global__ void tiled_unpack_kernel(const float2 *mv, float *mean, float *var, TiledDims d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t env = i / d.plane;
+        const int c = (int)(i - env * d.plane), R = c / d.X, C = c - R * d.X;
+        const float2 t = mv[env * d.plane_mv + tiled_mv_index(d.txm, R, C)];
+        if (mean) mean[i] = t.x;
+        if (var) var[i] = t.y;
+    }
+}
+__global__ void tiled_pack_kernel(float2 *mv, const float *mean, const float *var, TiledDims d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t env = i / d.plane;
+        const int c = (int)(i - env * d.plane), R = c / d.X, C = c - R * d.X;
+        float2 *o = mv + env * d.plane_mv + tiled_mv_index(d.txm, R, C);
+        float2 t = *o;
+        if (mean) t.x = mean[i];
+        if (var) t.y = var[i];
+        *o = t;
+    }
+}
+// to_tiled != 0: dense -> tiled, else tiled -> dense
+__global__ void tiled_gt_kernel(float *tiled, float *dense, TiledDims d, size_t n, int to_tiled) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t env = i / d.plane;
+        const int c = (int)(i - env * d.plane), R = c / d.X, C = c - R * d.X;
+        float *t = tiled + env * d.plane_gt + tiled_gt_index(d.txg, R, C);
+        if (to_tiled)
+            *t = dense[i];
+        else
+            dense[i] = *t;
+    }
+}
+
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16;
     x *= 0x7feb352du;
@@ -164,7 +205,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 }
 
 // Smooth synthetic field in [0,1]: normalised sum of 6 random plane waves per env.
-__global__ void synth_gt_kernel(float *gt, size_t plane, int X, int batch, uint32_t seed, uint32_t env_off) {
+__global__ void synth_gt_kernel(float *gt, size_t plane, size_t plane_gt, int X, int txg /* > 0: TILED */, int batch, uint32_t seed,
+                                uint32_t env_off) {
     const int env = blockIdx.y;
     __shared__ float fx[6], fy[6], ph[6], am[6];
     if (threadIdx.x < 6) {
@@ -180,13 +222,14 @@ __global__ void synth_gt_kernel(float *gt, size_t plane, int X, int batch, uint3
     __syncthreads();
     float norm = 0.f;
     for (int k = 0; k < 6; ++k) norm += am[k];
-    float *g = gt + (size_t)env * plane;
+    float *g = gt + (size_t)env * plane_gt;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
-        const float x = (float)(i % X), y = (float)(i / X);
+        const int C = (int)(i % X), R = (int)(i / X);
+        const float x = (float)C, y = (float)R;
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 6; ++k) s += am[k] * __sinf(fx[k] * x + fy[k] * y + ph[k]);
-        g[i] = fminf(fmaxf(0.5f + 0.5f * s / norm, 0.0f), 1.0f);
+        g[txg > 0 ? (size_t)tiled_gt_index(txg, R, C) : i] = fminf(fmaxf(0.5f + 0.5f * s / norm, 0.0f), 1.0f);
     }
 }
 
@@ -238,19 +281,24 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double *smem, bool 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, const float *var, const float *gt, int layout, size_t plane,
+__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, const float *var, const float *gt, int layout, TiledDims d,
                                                             float thr, float *metrics) {
     __shared__ double smem[(kEvalThreads / 32) * 10];
     const int env = blockIdx.x;
-    const float *g = gt + (size_t)env * plane;
-    const float *m = mean + (size_t)env * plane * (layout == IPP_LAYOUT_MV ? 2 : 1);
-    const float *v = layout == IPP_LAYOUT_MV ? m + 1 : var + (size_t)env * plane;
-    const int es = layout == IPP_LAYOUT_MV ? 2 : 1;
+    const size_t plane = d.plane;
+    const bool tiled = layout == IPP_LAYOUT_TILED;
+    const float *g = gt + (size_t)env * d.plane_gt;
+    const float *m = mean + (size_t)env * d.plane_mv * (layout != IPP_LAYOUT_PLANES ? 2 : 1);
+    const float *v = layout != IPP_LAYOUT_PLANES ? m + 1 : var + (size_t)env * plane;
+    const int es = layout != IPP_LAYOUT_PLANES ? 2 : 1;
+    // cell i of the dense map -> offsets inside the env's belief / ground-truth arrays
+    auto bi = [&](size_t i) -> size_t { return tiled ? (size_t)tiled_mv_index(d.txm, (int)(i / d.X), (int)(i % d.X)) : i; };
+    auto gi_of = [&](size_t i) -> size_t { return tiled ? (size_t)tiled_gt_index(d.txg, (int)(i / d.X), (int)(i % d.X)) : i; };
 
     // pass 1: min(gt), min(mean), max(gt), sum(gt)
     double a[4] = {1e300, 1e300, -1e300, 0.0};
     for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
-        const double gi = g[i], mi = m[i * es];
+        const double gi = g[gi_of(i)], mi = m[bi(i) * es];
         a[0] = fmin(a[0], gi);
         a[1] = fmin(a[1], mi);
         a[2] = fmax(a[2], gi);
@@ -265,11 +313,12 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, c
     // pass 2
     double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
-        const double gi = g[i], mi = m[i * es], vi = v[i * es];
+        const size_t b = bi(i);
+        const double gi = g[gi_of(i)], mi = m[b * es], vi = v[b * es];
         const double sq = (gi - mi) * (gi - mi);
         const double w = ((gi - mmin) / range) / wsum;
         const double ll = 0.5 * log(2.0 * 3.141592653589793 * vi) + sq / 2.0 * vi;  // (:44) multiplies by P_ii
-        const bool in = g[i] >= thr;
+        const bool in = (float)gi >= thr;
         s[0] += sq;
         s[1] += w * sq;
         s[2] += ll;
@@ -350,18 +399,17 @@ static int build_lut(ipp_engine *e) {
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 typedef void (*async_kernel_t)(const AsyncParams);
-// bit 0: entropy reward, bit 1: adaptive mask, bit 2: extras (host noise / measurement read-back)
+// bit 0: entropy reward, bit 1: adaptive mask, bit 2: extras (host noise / measurement read-back), bit 3: TILED layout
+template <int V>
+static async_kernel_t async_variant_t() {
+    return ipp_step_async_kernel<(V & 1) != 0, (V & 2) != 0, (V & 4) != 0, (V & 8) != 0>;
+}
 static async_kernel_t async_variant(int v) {
-    switch (v & 7) {
-        case 0: return ipp_step_async_kernel<false, false, false>;
-        case 1: return ipp_step_async_kernel<true, false, false>;
-        case 2: return ipp_step_async_kernel<false, true, false>;
-        case 3: return ipp_step_async_kernel<true, true, false>;
-        case 4: return ipp_step_async_kernel<false, false, true>;
-        case 5: return ipp_step_async_kernel<true, false, true>;
-        case 6: return ipp_step_async_kernel<false, true, true>;
-        default: return ipp_step_async_kernel<true, true, true>;
-    }
+    static const async_kernel_t table[16] = {async_variant_t<0>(),  async_variant_t<1>(),  async_variant_t<2>(),  async_variant_t<3>(),
+                                             async_variant_t<4>(),  async_variant_t<5>(),  async_variant_t<6>(),  async_variant_t<7>(),
+                                             async_variant_t<8>(),  async_variant_t<9>(),  async_variant_t<10>(), async_variant_t<11>(),
+                                             async_variant_t<12>(), async_variant_t<13>(), async_variant_t<14>(), async_variant_t<15>()};
+    return table[v & 15];
 }
 
 // cp.async-staged persistent path: needs the MV layout and footprints that fit two slots per warp.
@@ -371,12 +419,13 @@ static int setup_async(ipp_engine *e) {
     int rc;
     if ((rc = dev_alloc(e, &e->d_tickets, 2)) != IPP_OK) return rc;
     CU(e, cudaMemsetAsync(e->d_tickets, 0, 2 * sizeof(unsigned int), e->stream));
-    if (c.layout != IPP_LAYOUT_MV) return IPP_OK;
+    if (c.layout != IPP_LAYOUT_MV && c.layout != IPP_LAYOUT_TILED) return IPP_OK;
     // tile capacities for the largest footprint; with 16-byte staging (x_dim % 4 == 0) the tiles hold the
     // aligned superset of each row: {mean,var} pitch = roundup(1 + fw, 2) cells, gt pitch = roundup(3 + fw, 4) floats
     e->async_vec16 = (c.x_dim % 4 == 0);
     const char *v16 = getenv("IPP_ASYNC_VEC16");
     if (v16 && v16[0] == '0') e->async_vec16 = false;
+    if (c.layout == IPP_LAYOUT_TILED) e->async_vec16 = true;  // tiles are always staged as 16-byte aligned supersets
     int mv_cells = 0, gt_cells = 0;
     for (int k = 0; k < e->n_levels; ++k) {
         const int fw = std::min(2 * e->lut[k].rx + 1, c.x_dim), fh = std::min(2 * e->lut[k].ry + 1, c.y_dim);
@@ -399,7 +448,7 @@ static int setup_async(ipp_engine *e) {
     e->async_mv_tile = mv_tile;
     e->async_gt_tile = gt_tile;
     e->async_smem = per_warp * warps + per_cta;
-    for (int v = 0; v < 8; ++v)
+    for (int v = 0; v < 16; ++v)
         if (cudaFuncSetAttribute(async_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->async_smem) != cudaSuccess) {
             cudaGetLastError();
             return IPP_OK;
@@ -444,7 +493,7 @@ static int launch_async(ipp_engine *e, const StepParams &p) {
     const int needed = (p.n_jobs + e->async_warps - 1) / e->async_warps;
     const int grid = std::max(1, std::min(e->sm_count, needed));
     const int variant = (((p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY) ? 1 : 0) | ((p.flags & IPP_FLAG_ADAPTIVE) ? 2 : 0) |
-                        ((p.noise != nullptr || p.z_out != nullptr) ? 4 : 0);
+                        ((p.noise != nullptr || p.z_out != nullptr) ? 4 : 0) | (e->cfg.layout == IPP_LAYOUT_TILED ? 8 : 0);
     async_variant(variant)<<<grid, e->async_warps * 32, e->async_smem, e->stream>>>(ap);
     e->ticket_parity ^= 1;
     e->launches++;
@@ -473,7 +522,8 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
     if (!(cfg->resolution > 0)) return fail(nullptr, IPP_ERR_INVALID, "ipp_create: environment.resolution must be > 0");
     if (!(cfg->angle_x_deg > 0 && cfg->angle_x_deg < 180 && cfg->angle_y_deg > 0 && cfg->angle_y_deg < 180))
         return fail(nullptr, IPP_ERR_INVALID, "ipp_create: field_of_view angles must be in (0, 180)");
-    if (cfg->layout != IPP_LAYOUT_PLANES && cfg->layout != IPP_LAYOUT_MV) return fail(nullptr, IPP_ERR_INVALID, "ipp_create: unknown layout %d", cfg->layout);
+    if (cfg->layout != IPP_LAYOUT_PLANES && cfg->layout != IPP_LAYOUT_MV && cfg->layout != IPP_LAYOUT_TILED)
+        return fail(nullptr, IPP_ERR_INVALID, "ipp_create: unknown layout %d", cfg->layout);
     if (cfg->cost_mode != IPP_COST_DISTANCE && cfg->cost_mode != IPP_COST_FLIGHT_TIME)
         return fail(nullptr, IPP_ERR_INVALID, "ipp_create: unknown cost_mode %d", cfg->cost_mode);
     if (cfg->cost_mode == IPP_COST_FLIGHT_TIME && !(cfg->max_v > 0 && cfg->max_a > 0))
@@ -488,6 +538,14 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
     if (e->cfg.tan_half_x == 0) e->cfg.tan_half_x = std::tan(0.5 * (e->cfg.angle_x_deg * (kPi / 180.0)));
     if (e->cfg.tan_half_y == 0) e->cfg.tan_half_y = std::tan(0.5 * (e->cfg.angle_y_deg * (kPi / 180.0)));
     e->plane = (size_t)cfg->x_dim * cfg->y_dim;
+    e->plane_mv = e->plane_gt = e->plane;
+    if (cfg->layout == IPP_LAYOUT_TILED) {
+        e->txm = (cfg->x_dim + 3) / 4;
+        e->txg = (cfg->x_dim + 7) / 8;
+        e->tiles_y = (cfg->y_dim + 3) / 4;
+        e->plane_mv = (size_t)e->tiles_y * e->txm * 16;
+        e->plane_gt = (size_t)e->tiles_y * e->txg * 32;
+    }
 
     auto bail = [&](int rc) {
         g_create_err = e->err;
@@ -515,14 +573,18 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         if (s != cudaSuccess) return bail(fail(e, IPP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(s)));
         e->own_stream = true;
     }
-    const size_t cells = e->plane * (size_t)cfg->batch;
-    if (cfg->layout == IPP_LAYOUT_MV) {
+    const size_t cells = e->plane_mv * (size_t)cfg->batch, cells_gt = e->plane_gt * (size_t)cfg->batch;
+    if (cfg->layout != IPP_LAYOUT_PLANES) {
         if ((rc = dev_alloc(e, &e->d_mean, 2 * cells)) != IPP_OK) return bail(rc);
     } else {
         if ((rc = dev_alloc(e, &e->d_mean, cells)) != IPP_OK) return bail(rc);
         if ((rc = dev_alloc(e, &e->d_var, cells)) != IPP_OK) return bail(rc);
     }
-    if ((rc = dev_alloc(e, &e->d_gt, cells)) != IPP_OK) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_gt, cells_gt)) != IPP_OK) return bail(rc);
+    if (cfg->layout == IPP_LAYOUT_TILED) {  // padding cells of partial tiles are staged (never used): keep them finite
+        cudaMemsetAsync(e->d_gt, 0, cells_gt * sizeof(float), e->stream);
+        cudaMemsetAsync(e->d_mean, 0, 2 * cells * sizeof(float), e->stream);
+    }
     if ((rc = dev_alloc(e, &e->d_prev, 3 * (size_t)cfg->batch)) != IPP_OK) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_status, 1)) != IPP_OK) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_metrics, (size_t)cfg->batch * IPP_NUM_METRICS)) != IPP_OK) return bail(rc);
@@ -575,6 +637,18 @@ extern "C" int ipp_get_info(const ipp_engine *e, ipp_info *out) {
     return IPP_OK;
 }
 
+static TiledDims tiled_dims(const ipp_engine *e) {
+    TiledDims d;
+    d.X = e->cfg.x_dim;
+    d.Y = e->cfg.y_dim;
+    d.txm = e->txm;
+    d.txg = e->txg;
+    d.plane = e->plane;
+    d.plane_mv = e->plane_mv;
+    d.plane_gt = e->plane_gt;
+    return d;
+}
+
 static int check_status(ipp_engine *e) {
     // device status word -> host (after a synchronising copy)
     CU(e, cudaMemcpyAsync(e->h_status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -612,8 +686,8 @@ extern "C" int ipp_reset(ipp_engine *e, float prior_mean, float prior_var, const
         CU(e, cudaMemcpyAsync(e->d_reward, prior_var_per_env, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         d_pv = e->d_reward;
     }
-    reset_kernel<<<grid_for(e->plane * (size_t)B, 256, e->sm_count), 256, 0, e->stream>>>(e->d_mean, e->d_var, e->cfg.layout, e->plane, B,
-                                                                                          prior_mean, prior_var, d_pv);
+    reset_kernel<<<grid_for(e->plane_mv * (size_t)B, 256, e->sm_count), 256, 0, e->stream>>>(e->d_mean, e->d_var, e->cfg.layout, e->plane_mv, B,
+                                                                                             prior_mean, prior_var, d_pv);
     const double dflt[3] = {2.0, 2.0, 14.0};  // planning/missions.py:69
     const double *ip = init_pose ? init_pose : dflt;
     fill_prev_kernel<<<(B + 255) / 256, 256, 0, e->stream>>>(e->d_prev, B, ip[0], ip[1], ip[2]);
@@ -629,10 +703,31 @@ static int check_range(ipp_engine *e, int32_t first, int32_t n, const char *who)
     return IPP_OK;
 }
 
+// dense <-> tiled ground truth through the dense scratch buffer (TILED layout)
+static int gt_transfer_tiled(ipp_engine *e, float *user, int32_t first_env, int32_t n_env, int32_t user_is_device, bool upload) {
+    const size_t n = (size_t)n_env * e->plane;
+    float *dense = user;
+    int rc;
+    if (!user_is_device) {
+        if ((rc = ensure(e, &e->d_scratch, &e->cap_scratch, n)) != IPP_OK) return rc;
+        dense = e->d_scratch;
+        if (upload) CU(e, cudaMemcpyAsync(dense, user, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    }
+    tiled_gt_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(e->d_gt + (size_t)first_env * e->plane_gt, dense, tiled_dims(e), n,
+                                                                         upload ? 1 : 0);
+    e->launches++;
+    CU(e, cudaGetLastError());
+    if (!user_is_device && !upload) CU(e, cudaMemcpyAsync(user, dense, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
 extern "C" int ipp_set_ground_truth(ipp_engine *e, const float *gt, int32_t first_env, int32_t n_env, int32_t src_is_device) {
     if (!e || !gt) return IPP_ERR_INVALID;
     int rc = check_range(e, first_env, n_env, "ipp_set_ground_truth");
     if (rc != IPP_OK) return rc;
+    if (n_env == 0) return IPP_OK;
+    if (e->cfg.layout == IPP_LAYOUT_TILED) return gt_transfer_tiled(e, const_cast<float *>(gt), first_env, n_env, src_is_device, true);
     CU(e, cudaMemcpyAsync(e->d_gt + (size_t)first_env * e->plane, gt, (size_t)n_env * e->plane * sizeof(float),
                           src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
@@ -643,6 +738,8 @@ extern "C" int ipp_get_ground_truth(ipp_engine *e, float *gt, int32_t first_env,
     if (!e || !gt) return IPP_ERR_INVALID;
     int rc = check_range(e, first_env, n_env, "ipp_get_ground_truth");
     if (rc != IPP_OK) return rc;
+    if (n_env == 0) return IPP_OK;
+    if (e->cfg.layout == IPP_LAYOUT_TILED) return gt_transfer_tiled(e, gt, first_env, n_env, dst_is_device, false);
     CU(e, cudaMemcpyAsync(gt, e->d_gt + (size_t)first_env * e->plane, (size_t)n_env * e->plane * sizeof(float),
                           dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
@@ -657,12 +754,13 @@ extern "C" int ipp_synth_ground_truth(ipp_engine *e, uint64_t seed) {
         for (int first = 0; first < e->cfg.batch; first += 65535) {
             const int n = std::min(65535, e->cfg.batch - first);
             dim3 g2(grid.x, (unsigned)n);
-            synth_gt_kernel<<<g2, 256, 0, e->stream>>>(e->d_gt + (size_t)first * e->plane, e->plane, e->cfg.x_dim, n, (uint32_t)seed,
-                                                       (uint32_t)(e->cfg.env_id_offset + first));
+            synth_gt_kernel<<<g2, 256, 0, e->stream>>>(e->d_gt + (size_t)first * e->plane_gt, e->plane, e->plane_gt, e->cfg.x_dim, e->txg, n,
+                                                       (uint32_t)seed, (uint32_t)(e->cfg.env_id_offset + first));
             e->launches++;
         }
     } else {
-        synth_gt_kernel<<<grid, 256, 0, e->stream>>>(e->d_gt, e->plane, e->cfg.x_dim, e->cfg.batch, (uint32_t)seed, (uint32_t)e->cfg.env_id_offset);
+        synth_gt_kernel<<<grid, 256, 0, e->stream>>>(e->d_gt, e->plane, e->plane_gt, e->cfg.x_dim, e->txg, e->cfg.batch, (uint32_t)seed,
+                                                     (uint32_t)e->cfg.env_id_offset);
         e->launches++;
     }
     CU(e, cudaGetLastError());
@@ -686,7 +784,11 @@ extern "C" int ipp_get_state(ipp_engine *e, float *mean, float *var, int32_t fir
             dm = mean ? e->d_scratch : nullptr;
             dv = var ? e->d_scratch + n : nullptr;
         }
-        mv_unpack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(reinterpret_cast<const float2 *>(e->d_mean) + off, dm, dv, n);
+        if (e->cfg.layout == IPP_LAYOUT_TILED)
+            tiled_unpack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(
+                reinterpret_cast<const float2 *>(e->d_mean) + (size_t)first_env * e->plane_mv, dm, dv, tiled_dims(e), n);
+        else
+            mv_unpack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(reinterpret_cast<const float2 *>(e->d_mean) + off, dm, dv, n);
         e->launches++;
         if (!dst_is_device) {
             if (mean) CU(e, cudaMemcpyAsync(mean, dm, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
@@ -720,7 +822,11 @@ extern "C" int ipp_set_state(ipp_engine *e, const float *mean, const float *var,
                 dv = e->d_scratch + n;
             }
         }
-        mv_pack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(reinterpret_cast<float2 *>(e->d_mean) + off, dm, dv, n);
+        if (e->cfg.layout == IPP_LAYOUT_TILED)
+            tiled_pack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(
+                reinterpret_cast<float2 *>(e->d_mean) + (size_t)first_env * e->plane_mv, dm, dv, tiled_dims(e), n);
+        else
+            mv_pack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(reinterpret_cast<float2 *>(e->d_mean) + off, dm, dv, n);
         e->launches++;
     }
     CU(e, cudaGetLastError());
@@ -750,7 +856,10 @@ static void fill_params(const ipp_engine *e, StepParams &p) {
     p.mean = e->d_mean;
     p.var = e->d_var;
     p.gt = e->d_gt;
-    p.plane = e->plane;
+    p.plane = e->plane_mv;
+    p.plane_gt = e->plane_gt;
+    p.txm = e->txm;
+    p.txg = e->txg;
     p.X = c.x_dim;
     p.Y = c.y_dim;
     p.batch = c.batch;
@@ -784,7 +893,9 @@ static void fill_params(const ipp_engine *e, StepParams &p) {
 template <int MODE>
 static void launch_mode(ipp_engine *e, const StepParams &p) {
     const int blocks = (p.n_jobs + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (e->cfg.layout == IPP_LAYOUT_MV)
+    if (e->cfg.layout == IPP_LAYOUT_TILED)
+        ipp_step_kernel<IPP_LAYOUT_TILED, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
+    else if (e->cfg.layout == IPP_LAYOUT_MV)
         ipp_step_kernel<IPP_LAYOUT_MV, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
     else
         ipp_step_kernel<IPP_LAYOUT_PLANES, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
@@ -983,8 +1094,8 @@ extern "C" int ipp_predict(ipp_engine *e, int32_t n_jobs, const int32_t *env_ind
 
 extern "C" int ipp_eval_device(ipp_engine *e, float *metrics) {
     if (!e || !metrics) return IPP_ERR_INVALID;
-    eval_kernel<<<e->cfg.batch, kEvalThreads, 0, e->stream>>>(e->d_mean, e->d_var, e->d_gt, e->cfg.layout, e->plane, (float)e->cfg.value_threshold,
-                                                              metrics);
+    eval_kernel<<<e->cfg.batch, kEvalThreads, 0, e->stream>>>(e->d_mean, e->d_var, e->d_gt, e->cfg.layout, tiled_dims(e),
+                                                              (float)e->cfg.value_threshold, metrics);
     e->launches++;
     CU(e, cudaGetLastError());
     return IPP_OK;
@@ -1003,7 +1114,7 @@ extern "C" void *ipp_device_ptr(ipp_engine *e, int32_t which) {
     if (!e) return nullptr;
     switch (which) {
         case IPP_PTR_MEAN: return e->d_mean;
-        case IPP_PTR_VAR: return e->cfg.layout == IPP_LAYOUT_MV ? (void *)(e->d_mean + 1) : (void *)e->d_var;
+        case IPP_PTR_VAR: return e->cfg.layout != IPP_LAYOUT_PLANES ? (void *)(e->d_mean + 1) : (void *)e->d_var;
         case IPP_PTR_GT: return e->d_gt;
         case IPP_PTR_REWARD:
             if (ensure_job_buffers(e, (size_t)e->cfg.batch) != IPP_OK) return nullptr;

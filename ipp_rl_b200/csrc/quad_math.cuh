@@ -39,7 +39,9 @@ struct StepParams {
     float *mean;
     float *var;
     const float *gt;
-    size_t plane;  // y_dim * x_dim
+    size_t plane;     // cells per env in the belief arrays (y_dim * x_dim; TILED: padded to whole 4x4 tiles)
+    size_t plane_gt;  // cells per env in the ground-truth array (TILED: padded to whole 8x4 tiles)
+    int txm, txg;     // TILED: tiles per tile-row of the belief (ceil(X/4)) and of the ground truth (ceil(X/8))
     int X, Y;
     int n_jobs;
     int batch;
@@ -148,6 +150,13 @@ __device__ __forceinline__ int fdiv(int n, int d, float inv_d) {
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// IPP_LAYOUT_TILED: every 128-byte line of HBM holds a compact 2-D tile, so that the lines a footprint pulls in
+// (L2 fetches whole 128 B lines from DRAM on this part) are mostly cells the step needs:
+//   belief  float2 {mean,var}: 4 x 4 cells per line;   ground truth float: 8 (x) x 4 (y) cells per line;
+//   tiles row-major over the map, cells row-major inside a tile.
+__device__ __forceinline__ int tiled_mv_index(int txm, int R, int C) { return (((R >> 2) * txm + (C >> 2)) << 4) + ((R & 3) << 2) + (C & 3); }
+__device__ __forceinline__ int tiled_gt_index(int txg, int R, int C) { return (((R >> 2) * txg + (C >> 3)) << 5) + ((R & 3) << 3) + (C & 7); }
 
 // ---------------------------------------------------------------------------------------------
 // per-job geometry (footprint, sensor model) — computed redundantly by every lane (SIMT: one
@@ -303,13 +312,25 @@ struct TapView {
     const float2 *rows, *cols;  // entry k at [3k .. 3k+2]
 };
 
-template <bool GLOBAL>
-__device__ __forceinline__ float gt_at(const float *g, int i) {
-    return GLOBAL ? __ldg(g + i) : g[i];
-}
+// Ground-truth views: at(r, c) = value at row r, column c of the footprint (origin = its top-left cell).
+struct GtShared {  // staged tile in shared memory, row pitch `pitch` floats
+    const float *g;
+    int pitch;
+    __device__ __forceinline__ float at(int r, int c) const { return g[r * pitch + c]; }
+};
+struct GtRowMajor {  // global memory, row-major map; g points at the footprint origin
+    const float *g;
+    int pitch;
+    __device__ __forceinline__ float at(int r, int c) const { return __ldg(g + r * pitch + c); }
+};
+struct GtTiled {  // global memory, IPP_LAYOUT_TILED; g points at the env's plane
+    const float *g;
+    int txg, yu, xl;
+    __device__ __forceinline__ float at(int r, int c) const { return __ldg(g + tiled_gt_index(txg, yu + r, xl + c)); }
+};
 
-template <bool GLOBAL>
-__device__ __forceinline__ float downsample_fast(const float *g, int pitch, const TapView &t, int pr, int pc, int ny, int nx) {
+template <class G>
+__device__ __forceinline__ float downsample_fast(const G &g, const TapView &t, int pr, int pc, int ny, int nx) {
     const float2 r0 = t.rows[3 * pr], r1 = t.rows[3 * pr + 1];
     const float2 c0 = t.cols[3 * pc], c1 = t.cols[3 * pc + 1];
     const int rs = __float_as_int(r0.x), cs = __float_as_int(c0.x);
@@ -318,16 +339,16 @@ __device__ __forceinline__ float downsample_fast(const float *g, int pitch, cons
     float d = 0.0f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const float *rowp = g + min(rs + a, ny - 1) * pitch;
-        const float rowsum = fmaf(c1.y, gt_at<GLOBAL>(rowp, cb[2]), fmaf(c1.x, gt_at<GLOBAL>(rowp, cb[1]), c0.y * gt_at<GLOBAL>(rowp, cb[0])));
+        const int rr = min(rs + a, ny - 1);
+        const float rowsum = fmaf(c1.y, g.at(rr, cb[2]), fmaf(c1.x, g.at(rr, cb[1]), c0.y * g.at(rr, cb[0])));
         d = fmaf(wr[a], rowsum, d);
     }
     return d;
 }
 
 // clipped non-square footprints: up to 5 taps per axis (kept out of line: ~15 % of the rf=2 envs)
-template <bool GLOBAL>
-__device__ __noinline__ float downsample_wide(const float *g, int pitch, TapView t, int pr, int pc, int ny, int nx) {
+template <class G>
+__device__ __noinline__ float downsample_wide(G g, TapView t, int pr, int pc, int ny, int nx) {
     const float2 r0 = t.rows[3 * pr], r1 = t.rows[3 * pr + 1], r2 = t.rows[3 * pr + 2];
     const float2 c0 = t.cols[3 * pc], c1 = t.cols[3 * pc + 1], c2 = t.cols[3 * pc + 2];
     const int rs = __float_as_int(r0.x), cs = __float_as_int(c0.x);
@@ -336,39 +357,38 @@ __device__ __noinline__ float downsample_wide(const float *g, int pitch, TapView
     float d = 0.0f;
 #pragma unroll 1
     for (int a = 0; a < 5; ++a) {
-        const float *rowp = g + min(rs + a, ny - 1) * pitch;
+        const int rr = min(rs + a, ny - 1);
         float rowsum = 0.0f;
 #pragma unroll
-        for (int b = 0; b < 5; ++b) rowsum = fmaf(wc[b], gt_at<GLOBAL>(rowp, min(cs + b, nx - 1)), rowsum);
+        for (int b = 0; b < 5; ++b) rowsum = fmaf(wc[b], g.at(rr, min(cs + b, nx - 1)), rowsum);
         d = fmaf(wr[a], rowsum, d);
     }
     return d;
 }
 
 // anything else (decimation scale >= 4 or footprints wider than the tap tables)
-template <bool GLOBAL>
-__device__ __noinline__ float downsample_generic(const float *g, int pitch, int pr, int pc, int ny, int nx, int out_r, int out_c) {
+template <class G>
+__device__ __noinline__ float downsample_generic(G g, int pr, int pc, int ny, int nx, int out_r, int out_c) {
     const int rs = (pr * ny) / out_r, re = ((pr + 1) * ny + out_r - 1) / out_r;
     const int cs = (pc * nx) / out_c, ce = ((pc + 1) * nx + out_c - 1) / out_c;
     const float inv_ny = 1.0f / (float)ny, inv_nx = 1.0f / (float)nx;
     float d = 0.0f;
 #pragma unroll 1
     for (int a = rs; a < re; ++a) {
-        const float *rowp = g + min(a, ny - 1) * pitch;
+        const int rr = min(a, ny - 1);
         float rowsum = 0.0f;
 #pragma unroll 1
-        for (int b = cs; b < ce; ++b) rowsum = fmaf(tap_weight_generic(pc, b, nx, out_c, inv_nx), gt_at<GLOBAL>(rowp, min(b, nx - 1)), rowsum);
+        for (int b = cs; b < ce; ++b) rowsum = fmaf(tap_weight_generic(pc, b, nx, out_c, inv_nx), g.at(rr, min(b, nx - 1)), rowsum);
         d = fmaf(tap_weight_generic(pr, a, ny, out_r, inv_ny), rowsum, d);
     }
     return d;
 }
 
-template <bool GLOBAL>
-__device__ __forceinline__ float downsample(int mode, const float *g, int pitch, const TapView &t, int pr, int pc, int ny, int nx, int out_r,
-                                            int out_c) {
-    if (mode == TAPS_FAST) return downsample_fast<GLOBAL>(g, pitch, t, pr, pc, ny, nx);
-    if (mode == TAPS_WIDE) return downsample_wide<GLOBAL>(g, pitch, t, pr, pc, ny, nx);
-    return downsample_generic<GLOBAL>(g, pitch, pr, pc, ny, nx, out_r, out_c);
+template <class G>
+__device__ __forceinline__ float downsample(int mode, const G &g, const TapView &t, int pr, int pc, int ny, int nx, int out_r, int out_c) {
+    if (mode == TAPS_FAST) return downsample_fast(g, t, pr, pc, ny, nx);
+    if (mode == TAPS_WIDE) return downsample_wide(g, t, pr, pc, ny, nx);
+    return downsample_generic(g, pr, pc, ny, nx, out_r, out_c);
 }
 
 // Shannon entropy [nats] of Bernoulli(sigmoid(l)):  log1p(e^-|l|) + |l| e^-|l| / (1 + e^-|l|)

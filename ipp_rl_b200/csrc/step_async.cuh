@@ -70,7 +70,11 @@ __device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+#ifdef IPP_ASYNC_CA16
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -93,7 +97,7 @@ __global__ void build_level_taps_kernel(float2 *tabs, const int *dims /* [levels
 
 // ENTROPY / ADAPTIVE: reward variant and adaptive mask as compile-time switches; EXTRAS: host-supplied noise
 // and measurement read-back (parity / test features, not on the throughput path).
-template <bool ENTROPY, bool ADAPTIVE, bool EXTRAS>
+template <bool ENTROPY, bool ADAPTIVE, bool EXTRAS, bool TILED>
 __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(const __grid_constant__ AsyncParams ap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const StepParams &p = ap.base;
@@ -136,7 +140,66 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
             }
             if (lane < 3) cp_async_8(smem_u32(&c->prev[lane]), p.prev_state + 3 * (size_t)job + lane);
             const uint32_t tile = smem_u32(my_stages + (size_t)s * stage_bytes);
-            if (ap.vec16) {
+            if (TILED) {
+                // IPP_LAYOUT_TILED: the footprint covers a rectangle of 128-byte tiles.  Eight lanes take the eight
+                // 16-byte chunks of one tile, a warp instruction covers four tiles of a tile-row: whole 128 B lines,
+                // constant strides.  Chunks outside the (16-byte aligned) footprint rows are skipped, so the staged
+                // image is the same row-major aligned superset as with row-major 16-byte staging.
+                const int u = lane & 7, t4 = lane >> 3;
+                const int yd = yu + ny - 1, xr = xl + nx - 1;
+                const int ty0 = yu >> 2, nty = (yd >> 2) - ty0 + 1;
+                const int rin = u >> 1;  // row inside the tile
+                {   // belief: 4 x 4 cells of float2 per tile, chunk = 2 cells
+                    const int ox = xl & 1, pm = (ox + nx + 1) & ~1;
+                    const int tx0 = xl >> 2, ntx = (xr >> 2) - tx0 + 1;
+                    const float4 *src_row = reinterpret_cast<const float4 *>(mv_base + (size_t)job * p.plane) + ((size_t)(ty0 * p.txm + tx0 + t4) * 8 + u);
+                    int R = 4 * ty0 + rin;
+                    const int cc0 = 4 * (tx0 + t4) + 2 * (u & 1);  // first cell of this lane's chunk (absolute column)
+                    uint32_t dst_row = tile + 8u * (uint32_t)((R - yu) * pm + (cc0 - xl + ox));
+#pragma unroll 1
+                    for (int ty = 0; ty < nty; ++ty) {
+                        if (R >= yu && R <= yd) {
+                            const float4 *src = src_row;
+                            uint32_t dst = dst_row;
+                            int cc = cc0;
+                            for (int tx = t4; tx < ntx; tx += 4) {
+                                if (cc + 1 >= xl && cc <= xr) cp_async_16(dst, src);
+                                src += 32;   // four tiles
+                                dst += 128u;  // 16 cells
+                                cc += 16;
+                            }
+                        }
+                        src_row += (size_t)p.txm * 8;
+                        dst_row += 32u * (uint32_t)pm;  // four rows
+                        R += 4;
+                    }
+                }
+                {   // ground truth: 8 (x) x 4 (y) floats per tile, chunk = 4 cells
+                    const int oxg = xl & 3, pg = (oxg + nx + 3) & ~3;
+                    const int tx0 = xl >> 3, ntx = (xr >> 3) - tx0 + 1;
+                    const float4 *src_row = reinterpret_cast<const float4 *>(p.gt + (size_t)job * p.plane_gt) + ((size_t)(ty0 * p.txg + tx0 + t4) * 8 + u);
+                    int R = 4 * ty0 + rin;
+                    const int cc0 = 8 * (tx0 + t4) + 4 * (u & 1);
+                    uint32_t dst_row = tile + (uint32_t)ap.mv_tile_bytes + 4u * (uint32_t)((R - yu) * pg + (cc0 - xl + oxg));
+#pragma unroll 1
+                    for (int ty = 0; ty < nty; ++ty) {
+                        if (R >= yu && R <= yd) {
+                            const float4 *src = src_row;
+                            uint32_t dst = dst_row;
+                            int cc = cc0;
+                            for (int tx = t4; tx < ntx; tx += 4) {
+                                if (cc + 3 >= xl && cc <= xr) cp_async_16(dst, src);
+                                src += 32;
+                                dst += 128u;  // 32 cells
+                                cc += 32;
+                            }
+                        }
+                        src_row += (size_t)p.txg * 8;
+                        dst_row += 16u * (uint32_t)pg;
+                        R += 4;
+                    }
+                }
+            } else if (ap.vec16) {
                 // 16-byte copies that bypass L1 (cp.async.cg): every row is fetched as the 16-byte aligned
                 // superset of its footprint segment — the same 32 B sectors, a quarter of the copy instructions,
                 // and no L1 line allocation limiting the copies in flight.  Needs x_dim % 4 == 0.
@@ -239,9 +302,10 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         const int rf = L.rf;
         const float s2 = L.s2;
         // tile geometry: with 16-byte staging the tiles start at the aligned cell left of the footprint
-        const int ox = ap.vec16 ? (xl & 1) : 0, oxg = ap.vec16 ? (xl & 3) : 0;
-        const int pm = ap.vec16 ? ((ox + nx + 1) & ~1) : ((nx + 1) & ~1);  // {mean,var} tile pitch [cells]
-        const int pg = ap.vec16 ? ((oxg + nx + 3) & ~3) : pm;              // ground-truth tile pitch [floats]
+        const bool aligned16 = TILED || ap.vec16;
+        const int ox = aligned16 ? (xl & 1) : 0, oxg = aligned16 ? (xl & 3) : 0;
+        const int pm = aligned16 ? ((ox + nx + 1) & ~1) : ((nx + 1) & ~1);  // {mean,var} tile pitch [cells]
+        const int pg = aligned16 ? ((oxg + nx + 3) & ~3) : pm;              // ground-truth tile pitch [floats]
         const int nqx = (nx + 1) >> 1, nqy = (ny + 1) >> 1;
         const int nq = nqx * nqy;
         const int out_r = quirk ? nqx : nqy, out_c = quirk ? nqy : nqx;
@@ -276,7 +340,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         // the host guarantees for every footprint that fits the shared-memory tiles (setup_async)
         const uint32_t magic_x = (uint32_t)(65536.0f * fast_rcp((float)nqx) * 1.00000012f) + 1u;
         const uint32_t magic_c = (uint32_t)(65536.0f * fast_rcp((float)out_c) * 1.00000012f) + 1u;
-        float2 *mv_g = mv_base + (size_t)job * p.plane + (size_t)(yu * X + xl);
+        float2 *mv_g = mv_base + (size_t)job * p.plane + (TILED ? (size_t)0 : (size_t)(yu * X + xl));
         const size_t nrow = (size_t)job * (size_t)p.noise_stride;
         float acc = 0.0f;
         float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four iterations
@@ -329,7 +393,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                         pr = (int)(((uint32_t)q * magic_c) >> 16);
                         pc = q - pr * out_c;
                     }
-                    const float d = downsample<false>(tap_mode, gt_t, pg, tapv, pr, pc, ny, nx, out_r, out_c);
+                    const float d = downsample(tap_mode, GtShared{gt_t, pg}, tapv, pr, pc, ny, nx, out_r, out_c);
                     z[0] = __saturatef(fmaf(s2, eps[0], d));
                 }
                 if (EXTRAS && p.z_out != nullptr) {
@@ -348,11 +412,32 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
 #pragma unroll
                 for (int k = 0; k < 4; ++k) msk[k] = ok[k] && (!ADAPTIVE || (fmaf(p.kappa, v[k], m[k]) >= p.thr));
                 acc += kalman_quad<ENTROPY, ADAPTIVE>(fc, cok, rok, m, v, z, msk, mn, vn);
-                float2 *o = mv_g + r0 * X + c0;
-                o[0] = make_float2(mn[0], vn[0]);
-                if (cok) o[1] = make_float2(mn[1], vn[1]);
-                if (rok) o[X] = make_float2(mn[2], vn[2]);
-                if (ok[3]) o[X + 1] = make_float2(mn[3], vn[3]);
+                if (TILED) {
+                    const int R0 = yu + r0, C0 = xl + c0;
+                    float2 *o = mv_g + tiled_mv_index(p.txm, R0, C0);
+                    const int dR = (R0 & 3) == 3 ? 16 * p.txm - 12 : 4;  // next row: inside the tile, or the tile below
+                    if (ox == 0) {  // warp-uniform: (C0, C0+1) share a 16-byte chunk
+                        if (cok) {
+                            *reinterpret_cast<float4 *>(o) = make_float4(mn[0], vn[0], mn[1], vn[1]);
+                            if (rok) *reinterpret_cast<float4 *>(o + dR) = make_float4(mn[2], vn[2], mn[3], vn[3]);
+                        } else {
+                            o[0] = make_float2(mn[0], vn[0]);
+                            if (rok) o[dR] = make_float2(mn[2], vn[2]);
+                        }
+                    } else {
+                        const int dC = (C0 & 3) == 3 ? 13 : 1;  // next column: inside the tile, or the tile to the right
+                        o[0] = make_float2(mn[0], vn[0]);
+                        if (cok) o[dC] = make_float2(mn[1], vn[1]);
+                        if (rok) o[dR] = make_float2(mn[2], vn[2]);
+                        if (ok[3]) o[dR + dC] = make_float2(mn[3], vn[3]);
+                    }
+                } else {
+                    float2 *o = mv_g + r0 * X + c0;
+                    o[0] = make_float2(mn[0], vn[0]);
+                    if (cok) o[1] = make_float2(mn[1], vn[1]);
+                    if (rok) o[X] = make_float2(mn[2], vn[2]);
+                    if (ok[3]) o[X + 1] = make_float2(mn[3], vn[3]);
+                }
             }
         }
 

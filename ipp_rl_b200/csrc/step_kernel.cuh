@@ -23,13 +23,36 @@ constexpr int kTapCap = 16;  // tap-table entries per axis staged in shared memo
 // ---------------------------------------------------------------------------------------------
 // belief accessors for the two HBM layouts
 // ---------------------------------------------------------------------------------------------
+// interleaved {mean,var}; IPP_LAYOUT_MV: row-major map, IPP_LAYOUT_TILED: 4x4-cell tiles (quad_math.cuh)
 template <int LAYOUT>
-struct Belief;
+struct Belief {
+    static_assert(LAYOUT == IPP_LAYOUT_MV || LAYOUT == IPP_LAYOUT_TILED, "unknown layout");
+    float2 *mv;
+    __device__ __forceinline__ Belief(const StepParams &p, size_t env) : mv(reinterpret_cast<float2 *>(p.mean) + env * p.plane) {}
+    static __device__ __forceinline__ int idx(const StepParams &p, int R, int C) {
+        return LAYOUT == IPP_LAYOUT_TILED ? tiled_mv_index(p.txm, R, C) : R * p.X + C;
+    }
+    static __device__ __forceinline__ int gidx(const StepParams &p, int R, int C) {
+        return LAYOUT == IPP_LAYOUT_TILED ? tiled_gt_index(p.txg, R, C) : R * p.X + C;
+    }
+    __device__ __forceinline__ void load(int i, float &mean, float &var) const {
+        const float2 t = __ldcg(mv + i);
+        mean = t.x;
+        var = t.y;
+    }
+    __device__ __forceinline__ float load_mean(int i) const { return __ldcg(&mv[i].x); }
+    __device__ __forceinline__ float load_var(int i) const { return __ldcg(&mv[i].y); }
+    __device__ __forceinline__ void store(int i, float mean, float var) const { mv[i] = make_float2(mean, var); }
+    __device__ __forceinline__ void store_mean(int i, float mean) const { mv[i].x = mean; }
+    __device__ __forceinline__ void store_var(int i, float var) const { mv[i].y = var; }
+};
 
 template <>
 struct Belief<IPP_LAYOUT_PLANES> {
     float *m, *v;
     __device__ __forceinline__ Belief(const StepParams &p, size_t env) : m(p.mean + env * p.plane), v(p.var + env * p.plane) {}
+    static __device__ __forceinline__ int idx(const StepParams &p, int R, int C) { return R * p.X + C; }
+    static __device__ __forceinline__ int gidx(const StepParams &p, int R, int C) { return R * p.X + C; }
     __device__ __forceinline__ void load(int i, float &mean, float &var) const {
         mean = __ldcg(m + i);
         var = __ldcg(v + i);
@@ -44,21 +67,6 @@ struct Belief<IPP_LAYOUT_PLANES> {
     __device__ __forceinline__ void store_var(int i, float var) const { v[i] = var; }
 };
 
-template <>
-struct Belief<IPP_LAYOUT_MV> {
-    float2 *mv;
-    __device__ __forceinline__ Belief(const StepParams &p, size_t env) : mv(reinterpret_cast<float2 *>(p.mean) + env * p.plane) {}
-    __device__ __forceinline__ void load(int i, float &mean, float &var) const {
-        const float2 t = __ldcg(mv + i);
-        mean = t.x;
-        var = t.y;
-    }
-    __device__ __forceinline__ float load_mean(int i) const { return __ldcg(&mv[i].x); }
-    __device__ __forceinline__ float load_var(int i) const { return __ldcg(&mv[i].y); }
-    __device__ __forceinline__ void store(int i, float mean, float var) const { mv[i] = make_float2(mean, var); }
-    __device__ __forceinline__ void store_mean(int i, float mean) const { mv[i].x = mean; }
-    __device__ __forceinline__ void store_var(int i, float var) const { mv[i].y = var; }
-};
 
 template <int LAYOUT, int MODE>
 __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constant__ StepParams p) {
@@ -104,9 +112,7 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
     const float inv_nqx = __frcp_rn((float)nqx);
     const float inv_outc = __frcp_rn((float)out_c);
     const Belief<LAYOUT> bel(p, (size_t)env);
-    const float *gt = p.gt + (size_t)env * p.plane;
-    const int X = p.X;
-    const int origin = g.yu * X + g.xl;
+    const float *gt = p.gt + (size_t)env * p.plane_gt;
     const size_t nrow = (size_t)job * (size_t)p.noise_stride;
 
     float acc = 0.0f;  // per-lane partial (<= a few dozen quads); fp64 tree across the warp
@@ -117,8 +123,10 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
         const int r0 = 2 * qy, c0 = 2 * qx;
         const bool cok = c0 + 1 < g.nx, rok = r0 + 1 < g.ny;
         const bool ok[4] = {true, cok, rok, cok && rok};
-        const int i00 = origin + r0 * X + c0;
-        const int off[4] = {i00, i00 + 1, i00 + X, i00 + X + 1};
+        // cell offsets inside the env's belief / ground-truth arrays (clamped: cells past the footprint are never touched)
+        const int R0 = g.yu + r0, C0 = g.xl + c0, R1 = R0 + (rok ? 1 : 0), C1 = C0 + (cok ? 1 : 0);
+        const int off[4] = {Belief<LAYOUT>::idx(p, R0, C0), Belief<LAYOUT>::idx(p, R0, C1), Belief<LAYOUT>::idx(p, R1, C0),
+                            Belief<LAYOUT>::idx(p, R1, C1)};
 
         // ---- gather belief ------------------------------------------------------------------
         float m[4], v[4];
@@ -164,11 +172,15 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
                 if (g.rf == 1) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (ok[k]) z[k] = __saturatef(fmaf(g.s2, eps[k], __ldg(gt + off[k])));
+                        if (ok[k]) z[k] = __saturatef(fmaf(g.s2, eps[k], __ldg(gt + Belief<LAYOUT>::gidx(p, R0 + (k >> 1), C0 + (k & 1)))));
                 } else {
                     // D[pr, pc] with the measurement's flat index q: (pr, pc) = (q / out_c, q % out_c)
                     const int pr = fdiv(q, out_c, inv_outc), pc = q - pr * out_c;
-                    const float d = downsample<true>(tap_mode, gt + origin, X, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
+                    float d;
+                    if (LAYOUT == IPP_LAYOUT_TILED)
+                        d = downsample(tap_mode, GtTiled{gt, p.txg, g.yu, g.xl}, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
+                    else
+                        d = downsample(tap_mode, GtRowMajor{gt + g.yu * p.X + g.xl, p.X}, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
                     z[0] = __saturatef(fmaf(g.s2, eps[0], d));
                 }
             }

@@ -89,7 +89,7 @@ class EngineConfig:
             kw["max_v"], kw["max_a"] = float(uav["max_v"]), float(uav["max_a"])
         backend = params.get("mapping", {}).get("b200", {})
         if "layout" in backend:
-            kw["layout"] = {"planes": capi.LAYOUT_PLANES, "mv": capi.LAYOUT_MV}[backend["layout"]]
+            kw["layout"] = {"planes": capi.LAYOUT_PLANES, "mv": capi.LAYOUT_MV, "tiled": capi.LAYOUT_TILED}[backend["layout"]]
         kw.update(overrides)
         return cls(**kw)
 

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 ATOL = 1e-5
 RTOL = 1e-5
-LAYOUTS = [0, 1]
+LAYOUTS = [0, 1, 2]  # planes, {mean,var} row-major, 128-byte tiles
 
 
 def _engine(params, batch, **kw):

@@ -21,7 +21,8 @@ def _engine(params, batch, **kw):
     return BatchedEngine(engine_cfg(params, batch, **kw))
 
 
-@pytest.mark.parametrize("grid", [(40, 40, 1.0, 8, 20, 6), (24, 36, 1.0, 8, 20, 6), (200, 200, 1.0, 8, 20, 6), (64, 64, 2.0, 6, 30, 8)])
+@pytest.mark.parametrize("grid", [(40, 40, 1.0, 8, 20, 6), (24, 36, 1.0, 8, 20, 6), (200, 200, 1.0, 8, 20, 6), (64, 64, 2.0, 6, 30, 8),
+                                  (37, 43, 1.0, 8, 20, 6)])
 @pytest.mark.parametrize("reward_mode,adaptive", [(0, False), (1, False), (0, True), (1, True)])
 def test_persistent_paths_are_bit_identical_to_lsu_path(grid, reward_mode, adaptive):
     X, Y, res, a0, a1, da = grid
@@ -32,10 +33,12 @@ def test_persistent_paths_are_bit_identical_to_lsu_path(grid, reward_mode, adapt
     mean0 = rng.uniform(0, 1, (B, Y, X)).astype(np.float32)
     var0 = rng.uniform(0.05, 2.0, (B, Y, X)).astype(np.float32)
     out = {}
-    for path in ("lsu", "async"):
-        with _engine(params, B, layout=1, seed=99) as eng:
+    # (layout, path): the tiled layout (any grid shape, incl. partial tiles) must agree with the row-major ones bit for bit
+    combos = [(1, "lsu"), (2, "lsu"), (2, "async")] + ([(1, "async")] if X % 4 == 0 else [])
+    for layout, path in combos:
+        with _engine(params, B, layout=layout, seed=99) as eng:
             eng.set_step_path(path)
-            assert eng.step_path == path, "persistent paths must be available for MV layout with x_dim % 4 == 0"
+            assert eng.step_path == path, "persistent path must be available (MV with x_dim % 4 == 0, TILED always)"
             eng.reset(0.5, 1.82)
             eng.set_ground_truth(gt)
             eng.set_state(mean0, var0)
@@ -53,15 +56,16 @@ def test_persistent_paths_are_bit_identical_to_lsu_path(grid, reward_mode, adapt
                     r = eng.step(ids, reward_mode=reward_mode, adaptive=adaptive)
                 rs.append(r.copy())
             m, v = eng.get_state()
-            out[path] = (np.array(rs), m, v, eng.get_prev_pose(), zs[0])
+            out[(layout, path)] = (np.array(rs), m, v, eng.get_prev_pose(), zs[0], eng.get_ground_truth())
             assert eng.path_launches(path) == T
-    for path in ("async",):
-        for a, b in zip(out[path], out["lsu"]):
-            assert np.array_equal(a, b), path
+    for key in combos[1:]:
+        for a, b in zip(out[key], out[(1, "lsu")]):
+            assert np.array_equal(a, b), key
+    assert np.array_equal(out[(2, "async")][5], gt.astype(np.float32))
 
 
-@pytest.mark.parametrize("path", ["async"])
-def test_persistent_windowed_golden_by_action_id(path):
+@pytest.mark.parametrize("path,layout", [("async", 1), ("async", 2)])
+def test_persistent_windowed_golden_by_action_id(path, layout):
     """Reference-pinned T2 vectors (200x200) through the persistent paths: poses at cell centres -> action ids."""
     g = golden("golden_windowed_T2.npz")
     params = params_from_json(g["w200_cfg"])
@@ -82,7 +86,7 @@ def test_persistent_windowed_golden_by_action_id(path):
     K = len(keep)
     var0 = np.random.RandomState(0).uniform(0.1, 2.0, (n, n))
     mean0 = np.random.RandomState(1).uniform(0.0, 1.0, (n, n))
-    with _engine(params, K, layout=1) as eng:
+    with _engine(params, K, layout=layout) as eng:
         eng.set_step_path(path)
         assert eng.step_path == path
         eng.reset(0.5, 1.0)
@@ -108,8 +112,8 @@ def test_persistent_windowed_golden_by_action_id(path):
         assert np.array_equal(chk, var0.astype(np.float32))
 
 
-@pytest.mark.parametrize("path", ["async", "lsu"])
-def test_full_size_properties(path):
+@pytest.mark.parametrize("path,layout", [("async", 2), ("async", 1), ("lsu", 1)])
+def test_full_size_properties(path, layout):
     """BASELINE.json C3 size: 65 536 envs x 200x200 (31.5 GB of maps in HBM)."""
     import torch
 
@@ -118,7 +122,7 @@ def test_full_size_properties(path):
     X = Y = 200
     params = make_params(X, Y, 1.0, 8, 20, 6)
     rng = np.random.RandomState(123)
-    with _engine(params, B, layout=1, seed=5) as eng:
+    with _engine(params, B, layout=layout, seed=5) as eng:
         eng.set_step_path(path)
         eng.reset(0.5, 1.82)
         eng.synth_ground_truth(77)
@@ -165,7 +169,7 @@ def test_sharding_invariance_and_determinism():
     ids = rng.randint(0, 3 * X * Y, (3, B)).astype(np.int32)
 
     def run(first, count, path="async"):
-        with _engine(params, count, layout=1, seed=42, env_id_offset=first) as eng:
+        with _engine(params, count, layout=2, seed=42, env_id_offset=first) as eng:
             eng.set_step_path(path)
             eng.reset(0.5, 1.82)
             eng.set_ground_truth(gt[first : first + count])
