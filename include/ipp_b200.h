@@ -200,6 +200,21 @@ int ipp_predict_device(ipp_engine *e, int32_t n_jobs, const int32_t *env_index,
                        const int32_t *action_ids, const double *poses, const double *prev_poses,
                        float *reward, uint32_t flags);
 
+/* Path rollout — `horizon` (<= 8) chained prediction steps per job, starting from the env's CURRENT
+ * belief, without writing any state: what MCTS.simulate does along one tree path, one
+ * simulate_prediction_step per level (planning/mcts_zero/mcts.py:239-246 ->
+ * planning/common/optimization.py:14-30), where the reference copies the full covariance per level.
+ * path_action_ids[n_jobs][horizon]: action ids, a negative id ends the path;
+ * prev_poses[n_jobs][3]: pose before the first step (NULL -> the env's stored previous action);
+ * rewards[n_jobs][horizon]: per-step reward (0 past the end of a path).  Later steps of a path see the
+ * variance the earlier ones produced (kept in shared memory).  flags: IPP_REWARD_*, IPP_FLAG_ADAPTIVE. */
+int ipp_rollout(ipp_engine *e, int32_t n_jobs, int32_t horizon, const int32_t *env_index,
+                const int32_t *path_action_ids, const double *prev_poses, float *rewards,
+                uint32_t flags);
+int ipp_rollout_device(ipp_engine *e, int32_t n_jobs, int32_t horizon, const int32_t *env_index,
+                       const int32_t *path_action_ids, const double *prev_poses, float *rewards,
+                       uint32_t flags);
+
 /* Evaluation metrics per env — replaces Mission.eval (planning/missions.py:176-203) over
  * planning/evaluation_metrics.py:4-58.  metrics[batch][IPP_NUM_METRICS] =
  * {rmse, wrmse, mll, wmll, trace, uncertainty_difference, rmse_masked, trace_masked}; the mask is

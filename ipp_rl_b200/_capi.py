@@ -101,6 +101,43 @@ class ipp_info(C.Structure):
     ]
 
 
+class ipp_mcts_config(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_uint32),
+        ("n_trees", C.c_int32),
+        ("first_env", C.c_int32),
+        ("num_simulations", C.c_int32),
+        ("episode_horizon", C.c_int32),
+        ("step_flags", C.c_uint32),
+        ("puct_init", C.c_double),
+        ("puct_base", C.c_double),
+        ("gamma", C.c_double),
+        ("forced_playout_factor", C.c_double),
+        ("max_valid_action_distance", C.c_double),
+        ("dirichlet_eps", C.c_double),
+    ]
+
+
+class ipp_mcts_info(C.Structure):
+    _fields_ = [
+        ("n_trees", C.c_int32),
+        ("max_nodes", C.c_int32),
+        ("levels", C.c_int32),
+        ("window_dim", C.c_int32),
+        ("window_radius", C.c_int32),
+        ("window_slots", C.c_int32),
+        ("max_path", C.c_int32),
+        ("simulations", C.c_int32),
+        ("device_bytes", C.c_uint64),
+        ("launches", C.c_uint64),
+    ]
+
+
+MCTS_MAX_PATH = 8
+MCTS_LEAF_TERMINAL, MCTS_LEAF_EVAL = 0, 1
+MCTS_LEAF_WORDS = 8
+MCTS_PTR_LEAF_INFO, MCTS_PTR_PATH_ACTIONS, MCTS_PTR_PATH_REWARDS = range(3)
+
 _P = C.c_void_p
 _I32, _U32, _F32 = C.c_int32, C.c_uint32, C.c_float
 
@@ -125,6 +162,8 @@ SIGNATURES = {
     "ipp_update": (C.c_int, [_P, _P, _P, _P, _I32, _P, _U32]),
     "ipp_predict": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _U32]),
     "ipp_predict_device": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _U32]),
+    "ipp_rollout": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _U32]),
+    "ipp_rollout_device": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _U32]),
     "ipp_eval": (C.c_int, [_P, _P]),
     "ipp_eval_device": (C.c_int, [_P, _P]),
     "ipp_device_ptr": (_P, [_P, _I32]),
@@ -132,6 +171,16 @@ SIGNATURES = {
     "ipp_get_option": (C.c_int64, [_P, _I32]),
     "ipp_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "ipp_host_free": (C.c_int, [_P]),
+    # include/ipp_mcts.h
+    "ipp_mcts_create": (C.c_int, [_P, C.POINTER(ipp_mcts_config), C.POINTER(_P)]),
+    "ipp_mcts_destroy": (None, [_P]),
+    "ipp_mcts_last_error": (C.c_char_p, [_P]),
+    "ipp_mcts_get_info": (C.c_int, [_P, C.POINTER(ipp_mcts_info)]),
+    "ipp_mcts_begin": (C.c_int, [_P, _P, _P]),
+    "ipp_mcts_simulate_begin": (C.c_int, [_P, _P]),
+    "ipp_mcts_simulate_end": (C.c_int, [_P, _P, _P, _P, _P, _I32]),
+    "ipp_mcts_root_stats": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "ipp_mcts_device_ptr": (_P, [_P, _I32]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -1,0 +1,10 @@
+// engine_internal.h — engine internals shared with the tree-search translation unit (mcts.cu).  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "quad_math.cuh"
+
+int ipp_internal_step_params(const ipp_engine *e, ipp::StepParams *out);
+cudaStream_t ipp_internal_stream(const ipp_engine *e);
+void ipp_internal_count_launches(ipp_engine *e, int n);
+int ipp_internal_fail(ipp_engine *e, int code, const char *msg);

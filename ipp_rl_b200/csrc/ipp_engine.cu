@@ -12,7 +12,9 @@
 
 #include <cstdlib>
 
+#include "rollout_kernel.cuh"
 #include "step_async.cuh"
+#include "engine_internal.h"
 
 using namespace ipp;
 
@@ -1091,6 +1093,75 @@ extern "C" int ipp_predict(ipp_engine *e, int32_t n_jobs, const int32_t *env_ind
     if (reward) CU(e, cudaMemcpyAsync(reward, e->d_reward, J * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     return check_status(e);
 }
+
+// Path rollouts (rollout_kernel.cuh): `horizon` chained prediction steps per job from the env's current belief,
+// nothing written back.
+extern "C" int ipp_rollout_device(ipp_engine *e, int32_t n_jobs, int32_t horizon, const int32_t *env_index, const int32_t *path_action_ids,
+                                  const double *prev_poses, float *rewards, uint32_t flags) {
+    if (!e || !path_action_ids || !rewards) return IPP_ERR_INVALID;
+    if (n_jobs < 0) return fail(e, IPP_ERR_INVALID, "ipp_rollout: n_jobs < 0");
+    if (horizon < 1 || horizon > kMaxHorizon) return fail(e, IPP_ERR_INVALID, "ipp_rollout: horizon %d outside [1, %d]", horizon, kMaxHorizon);
+    if (!env_index && n_jobs != e->cfg.batch) return fail(e, IPP_ERR_INVALID, "ipp_rollout: env_index == NULL requires n_jobs == batch");
+    if (flags & IPP_FLAG_LOGODDS) return fail(e, IPP_ERR_UNSUPPORTED, "ipp_rollout: log-odds rollouts are not implemented");
+    if (n_jobs == 0) return IPP_OK;
+    RolloutParams rp;
+    fill_params(e, rp.base);
+    rp.base.n_jobs = n_jobs;
+    rp.base.env_index = env_index;
+    rp.base.prev_in = prev_poses;
+    rp.base.flags = flags;
+    rp.path_actions = path_action_ids;
+    rp.rewards = rewards;
+    rp.horizon = horizon;
+    int cells = 1;
+    for (int k = 0; k < e->n_levels; ++k)
+        cells = std::max(cells, std::min(2 * e->lut[k].rx + 1, e->cfg.x_dim) * std::min(2 * e->lut[k].ry + 1, e->cfg.y_dim));
+    rp.tile_floats = cells;
+    const size_t smem = (size_t)kRolloutWarps * (horizon - 1) * cells * sizeof(float);
+    void (*kern)(const RolloutParams) = e->cfg.layout == IPP_LAYOUT_TILED ? ipp_rollout_kernel<IPP_LAYOUT_TILED>
+                                        : e->cfg.layout == IPP_LAYOUT_MV  ? ipp_rollout_kernel<IPP_LAYOUT_MV>
+                                                                          : ipp_rollout_kernel<IPP_LAYOUT_PLANES>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(e, IPP_ERR_UNSUPPORTED, "ipp_rollout: %zu B of shared memory per CTA needed (horizon %d x %d-cell footprints)", smem, horizon, cells);
+        }
+    }
+    kern<<<(n_jobs + kRolloutWarps - 1) / kRolloutWarps, kRolloutWarps * 32, smem, e->stream>>>(rp);
+    e->launches++;
+    CU(e, cudaGetLastError());
+    return IPP_OK;
+}
+
+extern "C" int ipp_rollout(ipp_engine *e, int32_t n_jobs, int32_t horizon, const int32_t *env_index, const int32_t *path_action_ids,
+                           const double *prev_poses, float *rewards, uint32_t flags) {
+    if (!e || !path_action_ids || !rewards) return IPP_ERR_INVALID;
+    if (n_jobs <= 0 || horizon < 1) return n_jobs == 0 ? IPP_OK : fail(e, IPP_ERR_INVALID, "ipp_rollout: bad n_jobs / horizon");
+    const size_t J = (size_t)n_jobs, JH = J * (size_t)horizon;
+    if (env_index)
+        for (size_t j = 0; j < J; ++j)
+            if (env_index[j] < 0 || env_index[j] >= e->cfg.batch) return fail(e, IPP_ERR_INVALID, "ipp_rollout: env_index[%zu] = %d outside batch", j, env_index[j]);
+    int rc;
+    if ((rc = ensure_job_buffers(e, std::max(JH, (size_t)e->cfg.batch))) != IPP_OK) return rc;
+    if (env_index) CU(e, cudaMemcpyAsync(e->d_env_index, env_index, J * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaMemcpyAsync(e->d_actions, path_action_ids, JH * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    if (prev_poses) CU(e, cudaMemcpyAsync(e->d_prev_in, prev_poses, 3 * J * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    rc = ipp_rollout_device(e, n_jobs, horizon, env_index ? e->d_env_index : nullptr, e->d_actions, prev_poses ? e->d_prev_in : nullptr,
+                            e->d_reward, flags);
+    if (rc != IPP_OK) return rc;
+    CU(e, cudaMemcpyAsync(rewards, e->d_reward, JH * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    return check_status(e);
+}
+
+// engine_internal.h: what the tree-search translation unit needs from the engine
+int ipp_internal_step_params(const ipp_engine *e, ipp::StepParams *out) {
+    if (!e || !out) return IPP_ERR_INVALID;
+    fill_params(e, *out);
+    return IPP_OK;
+}
+cudaStream_t ipp_internal_stream(const ipp_engine *e) { return e->stream; }
+void ipp_internal_count_launches(ipp_engine *e, int n) { e->launches += (uint64_t)n; }
+int ipp_internal_fail(ipp_engine *e, int code, const char *msg) { return fail(e, code, "%s", msg); }
 
 extern "C" int ipp_eval_device(ipp_engine *e, float *metrics) {
     if (!e || !metrics) return IPP_ERR_INVALID;

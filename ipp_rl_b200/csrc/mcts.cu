@@ -1,0 +1,603 @@
+// mcts.cu — C-ABI implementation of include/ipp_mcts.h for sm_100a: the batched MCTS-zero rollout
+// loop.  One warp per tree; every tree of the batch advances by one simulation per
+// (simulate_begin, simulate_end) pair:
+//
+//   mcts_select_kernel   PUCT descent root -> leaf (compute_uct incl. forced playouts at the root,
+//                        planning/mcts_zero/mcts.py:280-296), creation of the child of a new edge
+//   ipp_rollout_device   rewards of the path's prediction steps (rollout_kernel.cuh)
+//   -- evaluator call-out (policy/value network; not part of this library) --
+//   mcts_expand_kernel   mask + normalise the leaf's priors (mcts.py:196-237), back the value up
+//                        (mcts.py:248-265)
+//
+// Tree storage per tree: `max_nodes` nodes x W window slots (candidate actions = lattice cells
+// within max_valid_action_distance of the node, all altitude levels): prior P (float, -1 = invalid
+// action), Q (float), {child index, visit count} (2 x uint16) = 12 B per slot, plus a 16 B node header.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ipp_mcts.h"
+#include "engine_internal.h"
+
+using namespace ipp;
+
+namespace {
+
+constexpr uint32_t kNoChild = 0xFFFFu;
+constexpr int kTreeWarps = 4;  // trees per CTA
+
+struct TreeDims {
+    int T, M, W, D, r, L, H;  // trees, nodes per tree, window slots, window width, radius, levels, episode horizon
+    int max_path;             // H + 1
+    int first_env;
+    float c_init, c_base, gamma, forced_k, max_dist, dir_eps;
+};
+
+struct TreeArrays {
+    int4 *hdr;       // [T][M]  {packed position, budget bits, Ns, depth | expanded << 8}
+    float *P;        // [T][M][W]
+    float *Q;        // [T][M][W]
+    uint32_t *NC;    // [T][M][W]  child << 16 | visits
+    int *n_nodes;    // [T]
+    double *root_pose;  // [T][3]
+    // per-simulation scratch
+    int *path_node;    // [T][max_path]
+    int *path_slot;    // [T][max_path]
+    int *path_action;  // [T][max_path]  (-1 padded)
+    float *path_reward;  // [T][max_path]
+    int *leaf;           // [T][IPP_MCTS_LEAF_WORDS]
+};
+
+__device__ __forceinline__ int pack_pos(int col, int row, int lvl) { return col | (row << 12) | ((lvl + 1) << 24); }
+__device__ __forceinline__ void unpack_pos(int w, int &col, int &row, int &lvl) {
+    col = w & 0xFFF;
+    row = (w >> 12) & 0xFFF;
+    lvl = (w >> 24) - 1;
+}
+
+// pose of a node: the root keeps the caller's previous action (any pose), every other node sits on the action lattice
+__device__ __forceinline__ void node_pose(const StepParams &p, const TreeArrays &a, int t, int node, int col, int row, int lvl, double &x, double &y,
+                                          double &h) {
+    if (node == 0) {
+        x = a.root_pose[3 * t];
+        y = a.root_pose[3 * t + 1];
+        h = a.root_pose[3 * t + 2];
+    } else {
+        x = __dadd_rn(__dmul_rn(p.res, (double)col), __dmul_rn(0.5, p.res));
+        y = __dadd_rn(__dmul_rn(p.res, (double)row), __dmul_rn(0.5, p.res));
+        h = p.lut[lvl].alt;
+    }
+}
+
+struct Slot {
+    int lvl, col, row;
+    bool in_grid;
+};
+__device__ __forceinline__ Slot slot_cell(const TreeDims &d, const StepParams &p, int s, int ccol, int crow) {
+    const int DD = d.D * d.D;
+    Slot o;
+    o.lvl = s / DD;
+    const int rem = s - o.lvl * DD;
+    const int a = rem / d.D;
+    o.col = ccol + a - d.r;
+    o.row = crow + (rem - a * d.D) - d.r;
+    o.in_grid = o.col >= 0 && o.col < p.X && o.row >= 0 && o.row < p.Y;
+    return o;
+}
+__device__ __forceinline__ void slot_pose(const StepParams &p, const Slot &c, double &x, double &y, double &h) {
+    x = __dadd_rn(__dmul_rn(p.res, (double)c.col), __dmul_rn(0.5, p.res));
+    y = __dadd_rn(__dmul_rn(p.res, (double)c.row), __dmul_rn(0.5, p.res));
+    h = p.lut[c.lvl].alt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// selection: one warp walks one tree from the root to a leaf
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kTreeWarps + (threadIdx.x >> 5);
+    if (t >= d.T) return;
+    int4 *hdr = a.hdr + (size_t)t * d.M;
+    int node = 0, depth = 0, len = 0, kind = IPP_MCTS_LEAF_TERMINAL;
+    int ccol = 0, crow = 0, lvl = -1;
+    float budget = 0.0f;
+    while (true) {
+        const int4 h = hdr[node];
+        unpack_pos(h.x, ccol, crow, lvl);
+        budget = __int_as_float(h.y);
+        const int Ns = h.z;
+        const bool expanded = ((h.w >> 8) & 1) != 0;
+        depth = h.w & 0xFF;
+        if (depth > d.H || !(budget > 0.0f)) {  // mcts.py:175-176
+            kind = IPP_MCTS_LEAF_TERMINAL;
+            break;
+        }
+        if (!expanded) {  // mcts.py:185: leaf -> evaluator
+            kind = IPP_MCTS_LEAF_EVAL;
+            break;
+        }
+        const size_t base = ((size_t)t * d.M + node) * d.W;
+        const float *P = a.P + base, *Q = a.Q + base;
+        uint32_t *NC = a.NC + base;
+        // normalize_q_values (mcts.py:267-278) over the dense action vector: unvisited and out-of-window actions are 0
+        float qmin = 0.0f, qmax = 0.0f;
+        for (int s = lane; s < d.W; s += 32) {
+            const float q = Q[s];
+            qmin = fminf(qmin, q);
+            qmax = fmaxf(qmax, q);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            qmin = fminf(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+            qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+        }
+        const float qscale = qmax > qmin ? 1.0f / (qmax - qmin) : 0.0f;  // all zero -> values unchanged (= 0)
+        // compute_uct (mcts.py:280-296)
+        const float prior_c = d.c_init + logf(((float)Ns + d.c_base + 1.0f) / d.c_base);
+        const float sq = sqrtf((float)Ns + 1.0f);
+        const bool force = depth == 0;
+        float best = -INFINITY;
+        int best_s = 0x7fffffff;
+        for (int s = lane; s < d.W; s += 32) {
+            const float pr = P[s];
+            if (pr < 0.0f) continue;  // ~Vs -> -inf
+            const float n = (float)(NC[s] & 0xFFFFu);
+            float u = (Q[s] - qmin) * qscale + prior_c * pr * (sq / (1.0f + n));
+            if (force && n > 0.0f && n < ceilf(sqrtf(d.forced_k * pr * (float)Ns))) u = INFINITY;
+            if (u > best) {
+                best = u;
+                best_s = s;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int os = __shfl_xor_sync(0xffffffffu, best_s, o);
+            if (ob > best || (ob == best && os < best_s)) {
+                best = ob;
+                best_s = os;
+            }
+        }
+        // the chosen edge
+        const Slot c = slot_cell(d, p, best_s, ccol, crow);
+        double nx, ny, nh, ax, ay, ah;
+        node_pose(p, a, t, node, ccol, crow, lvl, nx, ny, nh);
+        slot_pose(p, c, ax, ay, ah);
+        const float cost = job_cost(p, ax, ay, ah, nx, ny, nh);
+        const float child_budget = budget - cost;  // mcts.py:247
+        if (lane == 0) {
+            a.path_node[(size_t)t * d.max_path + len] = node;
+            a.path_slot[(size_t)t * d.max_path + len] = best_s;
+            a.path_action[(size_t)t * d.max_path + len] = c.lvl * (p.X * p.Y) + p.X * c.col + c.row;
+        }
+        ++len;
+        const uint32_t child = NC[best_s] >> 16;
+        if (child == kNoChild) {
+            const int n_nodes = a.n_nodes[t];
+            if (depth + 1 > d.H || !(child_budget > 0.0f) || n_nodes >= d.M) {
+                kind = IPP_MCTS_LEAF_TERMINAL;  // simulate() returns 0 before any node exists (mcts.py:175-176)
+                depth += 1;
+                budget = child_budget;
+                ccol = c.col, crow = c.row, lvl = c.lvl;
+                node = -1;
+                break;
+            }
+            if (lane == 0) {
+                hdr[n_nodes] = make_int4(pack_pos(c.col, c.row, c.lvl), __float_as_int(child_budget), 0, depth + 1);
+                NC[best_s] = ((uint32_t)n_nodes << 16) | (NC[best_s] & 0xFFFFu);
+                a.n_nodes[t] = n_nodes + 1;
+            }
+            __syncwarp();
+            node = n_nodes;
+            depth += 1;
+            budget = child_budget;
+            ccol = c.col, crow = c.row, lvl = c.lvl;
+            kind = IPP_MCTS_LEAF_EVAL;
+            break;
+        }
+        node = (int)child;
+    }
+    if (lane == 0) {
+        for (int k = len; k < d.max_path; ++k) a.path_action[(size_t)t * d.max_path + k] = -1;
+        int *lf = a.leaf + (size_t)t * IPP_MCTS_LEAF_WORDS;
+        lf[0] = kind;
+        lf[1] = node;
+        lf[2] = ccol;
+        lf[3] = crow;
+        lf[4] = lvl;
+        lf[5] = depth;
+        lf[6] = __float_as_int(budget);
+        lf[7] = len;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// expansion + backup
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a,
+                                                                      const float *priors_window, const float *priors_dense,
+                                                                      const float *values, const float *root_noise, int num_actions) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kTreeWarps + (threadIdx.x >> 5);
+    if (t >= d.T) return;
+    const int *lf = a.leaf + (size_t)t * IPP_MCTS_LEAF_WORDS;
+    const int kind = lf[0], node = lf[1], len = lf[7];
+    int4 *hdr = a.hdr + (size_t)t * d.M;
+    float value = 0.0f;
+    if (kind == IPP_MCTS_LEAF_EVAL) {
+        int ccol, crow, lvl;
+        const int4 h = hdr[node];
+        unpack_pos(h.x, ccol, crow, lvl);
+        const float budget = __int_as_float(h.y);
+        double nx, ny, nh;
+        node_pose(p, a, t, node, ccol, crow, lvl, nx, ny, nh);
+        const size_t base = ((size_t)t * d.M + node) * d.W;
+        float *P = a.P + base, *Q = a.Q + base;
+        uint32_t *NC = a.NC + base;
+        const bool noisy = node == 0 && root_noise != nullptr && d.dir_eps > 0.0f;
+        // get_next_actions_mask (mcts.py:148-158) and policy * mask (mcts.py:220)
+        float sum = 0.0f;
+        int n_valid = 0;
+        for (int s = lane; s < d.W; s += 32) {
+            const Slot c = slot_cell(d, p, s, ccol, crow);
+            float pr = -1.0f;
+            if (c.in_grid) {
+                double ax, ay, ah;
+                slot_pose(p, c, ax, ay, ah);
+                // every reference call site leaves uav_specificaion = None: the mask compares the Euclidean distance with
+                // the budget even when costs are flight times (quirk, reproduced; the budget is decremented by the cost)
+                const float dist = job_dist(ax, ay, ah, nx, ny, nh);
+                if (dist > 0.0f && dist <= budget && dist < d.max_dist) {
+                    pr = priors_window ? priors_window[(size_t)t * d.W + s]
+                                       : (priors_dense ? priors_dense[(size_t)t * num_actions + c.lvl * (p.X * p.Y) + p.X * c.col + c.row] : 1.0f);
+                    pr = fmaxf(pr, 0.0f);
+                    if (noisy) pr = (1.0f - d.dir_eps) * pr;
+                    sum += pr;
+                    if (noisy) pr += d.dir_eps * root_noise[(size_t)t * d.W + s];
+                    ++n_valid;
+                }
+            }
+            P[s] = pr;
+            Q[s] = 0.0f;
+            NC[s] = kNoChild << 16;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+        }
+        __syncwarp();
+        if (n_valid > 0) {  // else: simulate() returns 0 and the node stays a leaf (mcts.py:197-199)
+            // Ps /= sum(Ps) (mcts.py:228-234).  With exploration noise the sum runs over ALL actions, invalid ones
+            // included (noise is added after masking, mcts.py:160-164,225-226): (1-eps) * sum_valid(p) + eps * 1.
+            const float total = noisy ? sum + d.dir_eps : sum;
+            const float scale = total > 0.0f ? 1.0f / total : 0.0f;
+            const float uniform = 1.0f / (float)n_valid;
+            for (int s = lane; s < d.W; s += 32) {
+                const float pr = P[s];
+                if (pr >= 0.0f) P[s] = total > 0.0f ? pr * scale : uniform;
+            }
+            if (lane == 0) hdr[node] = make_int4(h.x, h.y, 0, (h.w & 0xFF) | (1 << 8));
+            value = values ? values[t] : 0.0f;
+        }
+    }
+    // backup (mcts.py:248-265), deepest edge first
+    if (lane == 0) {
+        for (int k = len - 1; k >= 0; --k) {
+            value = a.path_reward[(size_t)t * d.max_path + k] + d.gamma * value;
+            const int n = a.path_node[(size_t)t * d.max_path + k], s = a.path_slot[(size_t)t * d.max_path + k];
+            const size_t i = ((size_t)t * d.M + n) * d.W + s;
+            const uint32_t nc = a.NC[i];
+            const uint32_t visits = nc & 0xFFFFu;
+            a.Q[i] = visits > 0 ? ((float)visits * a.Q[i] + value) / (float)(visits + 1) : value;
+            a.NC[i] = (nc & 0xFFFF0000u) | min(visits + 1u, 0xFFFFu);
+            hdr[n].z += 1;
+        }
+    }
+}
+
+__global__ void mcts_begin_kernel(TreeDims d, TreeArrays a, const StepParams p, const float *budgets) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.T) return;
+    const double x = a.root_pose[3 * t], y = a.root_pose[3 * t + 1];
+    const int col = clampi((int)floor(__ddiv_rn(x, p.res)), 0, p.X - 1), row = clampi((int)floor(__ddiv_rn(y, p.res)), 0, p.Y - 1);
+    a.hdr[(size_t)t * d.M] = make_int4(pack_pos(col, row, -1), __float_as_int(budgets[t]), 0, 0);
+    a.n_nodes[t] = 1;
+}
+
+__global__ void mcts_root_export_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a, float *ps, float *qsa, int *nsa, int *ids,
+                                        int *ns) {
+    const int t = blockIdx.y;
+    const int4 h = a.hdr[(size_t)t * d.M];
+    int ccol, crow, lvl;
+    unpack_pos(h.x, ccol, crow, lvl);
+    const bool expanded = ((h.w >> 8) & 1) != 0;
+    const size_t base = (size_t)t * d.M * d.W;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.W; s += gridDim.x * blockDim.x) {
+        const Slot c = slot_cell(d, p, s, ccol, crow);
+        const size_t o = (size_t)t * d.W + s;
+        if (ps) ps[o] = expanded ? a.P[base + s] : -1.0f;
+        if (qsa) qsa[o] = expanded ? a.Q[base + s] : 0.0f;
+        if (nsa) nsa[o] = expanded ? (int)(a.NC[base + s] & 0xFFFFu) : 0;
+        if (ids) ids[o] = c.in_grid ? c.lvl * (p.X * p.Y) + p.X * c.col + c.row : -1;
+    }
+    if (ns && blockIdx.x == 0 && threadIdx.x == 0) ns[t] = h.z;
+}
+
+__global__ void iota_kernel(int *out, int n, int first) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = first + i;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct ipp_mcts {
+    ipp_engine *env = nullptr;
+    ipp_mcts_config cfg{};
+    TreeDims d{};
+    TreeArrays a{};
+    StepParams sp{};
+    int num_actions = 0;
+    int *d_env_index = nullptr;
+    float *d_budgets = nullptr;
+    // staging for host-side evaluator outputs / exports
+    float *d_in_priors = nullptr, *d_in_values = nullptr, *d_in_noise = nullptr;
+    size_t cap_in_priors = 0;
+    float *d_out_f[2] = {nullptr, nullptr};
+    int *d_out_i[3] = {nullptr, nullptr, nullptr};
+    std::vector<void *> owned;
+    cudaStream_t stream = nullptr;
+    uint64_t device_bytes = 0, launches = 0;
+    int simulations = 0;
+    bool begun = false, pending = false;
+    std::string err;
+};
+
+static thread_local std::string g_mcts_create_err;
+
+static int mfail(ipp_mcts *m, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (m)
+        m->err = buf;
+    else
+        g_mcts_create_err = buf;
+    return code;
+}
+
+#define MCU(m, call)                                                                                              \
+    do {                                                                                                          \
+        cudaError_t _s = (call);                                                                                  \
+        if (_s != cudaSuccess)                                                                                    \
+            return mfail((m), _s == cudaErrorMemoryAllocation ? IPP_ERR_NOMEM : IPP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                         cudaGetErrorString(_s), __FILE__, __LINE__);                                             \
+    } while (0)
+
+template <typename T>
+static int malloc_dev(ipp_mcts *m, T **p, size_t n) {
+    MCU(m, cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    m->owned.push_back((void *)*p);
+    m->device_bytes += n * sizeof(T);
+    return IPP_OK;
+}
+
+extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_mcts **out) {
+    if (!env || !cfg || !out) return mfail(nullptr, IPP_ERR_INVALID, "ipp_mcts_create: NULL argument");
+    *out = nullptr;
+    if (cfg->struct_bytes != sizeof(ipp_mcts_config)) return mfail(nullptr, IPP_ERR_INVALID, "ipp_mcts_create: ABI mismatch");
+    ipp_info info;
+    if (ipp_get_info(env, &info) != IPP_OK) return mfail(nullptr, IPP_ERR_INVALID, "ipp_mcts_create: bad engine");
+    if (cfg->n_trees < 1 || cfg->first_env < 0 || cfg->first_env + cfg->n_trees > info.batch)
+        return mfail(nullptr, IPP_ERR_INVALID, "ipp_mcts_create: trees [%d, %d) outside the engine batch %d", cfg->first_env,
+                     cfg->first_env + cfg->n_trees, info.batch);
+    if (cfg->num_simulations < 1 || cfg->num_simulations > 65000) return mfail(nullptr, IPP_ERR_INVALID, "ipp_mcts_create: num_simulations outside [1, 65000]");
+    if (cfg->episode_horizon < 0 || cfg->episode_horizon + 1 > IPP_MCTS_MAX_PATH)
+        return mfail(nullptr, IPP_ERR_INVALID, "ipp_mcts_create: episode_horizon outside [0, %d]", IPP_MCTS_MAX_PATH - 1);
+    if (!(cfg->max_valid_action_distance > 0) || !(cfg->puct_base > 0))
+        return mfail(nullptr, IPP_ERR_INVALID, "ipp_mcts_create: max_valid_action_distance and puct_base must be > 0");
+    if (info.x_dim > 4095 || info.y_dim > 4095) return mfail(nullptr, IPP_ERR_UNSUPPORTED, "ipp_mcts_create: grids beyond 4095 cells per side");
+
+    ipp_mcts *m = new (std::nothrow) ipp_mcts();
+    if (!m) return mfail(nullptr, IPP_ERR_NOMEM, "ipp_mcts_create: out of host memory");
+    m->env = env;
+    m->cfg = *cfg;
+    ipp_internal_step_params(env, &m->sp);
+    m->stream = ipp_internal_stream(env);
+    m->num_actions = info.num_actions;
+    TreeDims &d = m->d;
+    d.T = cfg->n_trees;
+    d.M = cfg->num_simulations + 1;
+    d.L = info.num_altitude_levels;
+    d.r = (int)std::floor(cfg->max_valid_action_distance / m->sp.res) + 1;
+    d.D = 2 * d.r + 1;
+    d.W = d.L * d.D * d.D;
+    d.H = cfg->episode_horizon;
+    d.max_path = d.H + 1;
+    d.first_env = cfg->first_env;
+    d.c_init = (float)cfg->puct_init;
+    d.c_base = (float)cfg->puct_base;
+    d.gamma = (float)cfg->gamma;
+    d.forced_k = (float)cfg->forced_playout_factor;
+    d.max_dist = (float)cfg->max_valid_action_distance;
+    d.dir_eps = (float)cfg->dirichlet_eps;
+
+    auto bail = [&](int rc) {
+        g_mcts_create_err = m->err;
+        ipp_mcts_destroy(m);
+        return rc;
+    };
+    const size_t TM = (size_t)d.T * d.M, TMW = TM * d.W, TP = (size_t)d.T * d.max_path;
+    int rc;
+    TreeArrays &a = m->a;
+    if ((rc = malloc_dev(m, &a.hdr, TM)) || (rc = malloc_dev(m, &a.P, TMW)) || (rc = malloc_dev(m, &a.Q, TMW)) || (rc = malloc_dev(m, &a.NC, TMW)) ||
+        (rc = malloc_dev(m, &a.n_nodes, (size_t)d.T)) || (rc = malloc_dev(m, &a.root_pose, 3 * (size_t)d.T)) ||
+        (rc = malloc_dev(m, &a.path_node, TP)) || (rc = malloc_dev(m, &a.path_slot, TP)) || (rc = malloc_dev(m, &a.path_action, TP)) ||
+        (rc = malloc_dev(m, &a.path_reward, TP)) || (rc = malloc_dev(m, &a.leaf, (size_t)d.T * IPP_MCTS_LEAF_WORDS)) ||
+        (rc = malloc_dev(m, &m->d_env_index, (size_t)d.T)) || (rc = malloc_dev(m, &m->d_budgets, (size_t)d.T)))
+        return bail(rc);
+    iota_kernel<<<(d.T + 255) / 256, 256, 0, m->stream>>>(m->d_env_index, d.T, d.first_env);
+    m->launches++;
+    if (cudaStreamSynchronize(m->stream) != cudaSuccess) return bail(mfail(m, IPP_ERR_CUDA, "ipp_mcts_create: device initialisation failed"));
+    *out = m;
+    return IPP_OK;
+}
+
+extern "C" void ipp_mcts_destroy(ipp_mcts *m) {
+    if (!m) return;
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (void *p : m->owned) cudaFree(p);
+    delete m;
+}
+
+extern "C" const char *ipp_mcts_last_error(const ipp_mcts *m) { return m ? m->err.c_str() : g_mcts_create_err.c_str(); }
+
+extern "C" int ipp_mcts_get_info(const ipp_mcts *m, ipp_mcts_info *out) {
+    if (!m || !out) return IPP_ERR_INVALID;
+    memset(out, 0, sizeof *out);
+    out->n_trees = m->d.T;
+    out->max_nodes = m->d.M;
+    out->levels = m->d.L;
+    out->window_dim = m->d.D;
+    out->window_radius = m->d.r;
+    out->window_slots = m->d.W;
+    out->max_path = m->d.max_path;
+    out->simulations = m->simulations;
+    out->device_bytes = m->device_bytes;
+    out->launches = m->launches;
+    return IPP_OK;
+}
+
+extern "C" int ipp_mcts_begin(ipp_mcts *m, const double *root_poses, const float *budgets) {
+    if (!m || !budgets) return IPP_ERR_INVALID;
+    const TreeDims &d = m->d;
+    ipp_internal_step_params(m->env, &m->sp);  // belief pointers / flags of the engine as of now
+    std::vector<double> all;
+    if (!root_poses) {
+        ipp_info info;
+        ipp_get_info(m->env, &info);
+        all.resize(3 * (size_t)info.batch);
+        if (ipp_get_prev_pose(m->env, all.data()) != IPP_OK) return mfail(m, IPP_ERR_CUDA, "ipp_mcts_begin: %s", ipp_last_error(m->env));
+        root_poses = all.data() + 3 * (size_t)d.first_env;
+    }
+    MCU(m, cudaMemcpyAsync(m->a.root_pose, root_poses, 3 * (size_t)d.T * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    MCU(m, cudaMemcpyAsync(m->d_budgets, budgets, (size_t)d.T * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    mcts_begin_kernel<<<(d.T + 255) / 256, 256, 0, m->stream>>>(d, m->a, m->sp, m->d_budgets);
+    m->launches++;
+    MCU(m, cudaGetLastError());
+    MCU(m, cudaStreamSynchronize(m->stream));  // the host buffers may go away
+    m->simulations = 0;
+    m->begun = true;
+    m->pending = false;
+    return IPP_OK;
+}
+
+extern "C" int ipp_mcts_simulate_begin(ipp_mcts *m, int32_t *leaf_info) {
+    if (!m) return IPP_ERR_INVALID;
+    if (!m->begun) return mfail(m, IPP_ERR_INVALID, "ipp_mcts_simulate_begin: call ipp_mcts_begin first");
+    if (m->pending) return mfail(m, IPP_ERR_INVALID, "ipp_mcts_simulate_begin: the previous simulation has not been ended");
+    if (m->simulations >= m->cfg.num_simulations) return mfail(m, IPP_ERR_INVALID, "ipp_mcts_simulate_begin: node capacity (num_simulations) used up");
+    const TreeDims &d = m->d;
+    const int blocks = (d.T + kTreeWarps - 1) / kTreeWarps;
+    mcts_select_kernel<<<blocks, kTreeWarps * 32, 0, m->stream>>>(m->sp, d, m->a);
+    m->launches++;
+    MCU(m, cudaGetLastError());
+    // rewards of the path's prediction steps, from the env's current belief (nothing is written)
+    int rc = ipp_rollout_device(m->env, d.T, d.max_path, m->d_env_index, m->a.path_action, m->a.root_pose, m->a.path_reward,
+                                m->cfg.step_flags & (IPP_REWARD_MASK | IPP_FLAG_ADAPTIVE));
+    if (rc != IPP_OK) return mfail(m, rc, "ipp_mcts_simulate_begin: %s", ipp_last_error(m->env));
+    m->launches++;
+    if (leaf_info) {
+        MCU(m, cudaMemcpyAsync(leaf_info, m->a.leaf, (size_t)d.T * IPP_MCTS_LEAF_WORDS * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        MCU(m, cudaStreamSynchronize(m->stream));
+    }
+    m->pending = true;
+    return IPP_OK;
+}
+
+static int stage_in(ipp_mcts *m, float **slot, const float *src, size_t n, const float **dev) {
+    *dev = nullptr;
+    if (!src) return IPP_OK;
+    if (!*slot) {
+        int rc = malloc_dev(m, slot, n);
+        if (rc != IPP_OK) return rc;
+    }
+    MCU(m, cudaMemcpyAsync(*slot, src, n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    *dev = *slot;
+    return IPP_OK;
+}
+
+extern "C" int ipp_mcts_simulate_end(ipp_mcts *m, const float *priors_window, const float *priors_dense, const float *values,
+                                     const float *root_noise, int32_t inputs_are_device) {
+    if (!m) return IPP_ERR_INVALID;
+    if (!m->pending) return mfail(m, IPP_ERR_INVALID, "ipp_mcts_simulate_end: no simulation in flight");
+    if (priors_window && priors_dense) return mfail(m, IPP_ERR_INVALID, "ipp_mcts_simulate_end: give window OR dense priors");
+    const TreeDims &d = m->d;
+    const float *pw = priors_window, *pd = priors_dense, *pv = values, *pn = root_noise;
+    if (!inputs_are_device) {
+        int rc;
+        const size_t n_pri = priors_dense ? (size_t)d.T * m->num_actions : (size_t)d.T * d.W;
+        if (priors_window || priors_dense) {
+            if (m->cap_in_priors < n_pri) {  // (re)allocate the priors staging for the larger of the two forms
+                float *p = nullptr;
+                if ((rc = malloc_dev(m, &p, n_pri)) != IPP_OK) return rc;
+                m->d_in_priors = p;
+                m->cap_in_priors = n_pri;
+            }
+            MCU(m, cudaMemcpyAsync(m->d_in_priors, priors_window ? priors_window : priors_dense, n_pri * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+            pw = priors_window ? m->d_in_priors : nullptr;
+            pd = priors_dense ? m->d_in_priors : nullptr;
+        }
+        if ((rc = stage_in(m, &m->d_in_values, values, (size_t)d.T, &pv)) != IPP_OK) return rc;
+        if ((rc = stage_in(m, &m->d_in_noise, root_noise, (size_t)d.T * d.W, &pn)) != IPP_OK) return rc;
+    }
+    const int blocks = (d.T + kTreeWarps - 1) / kTreeWarps;
+    mcts_expand_kernel<<<blocks, kTreeWarps * 32, 0, m->stream>>>(m->sp, d, m->a, pw, pd, pv, pn, m->num_actions);
+    m->launches++;
+    MCU(m, cudaGetLastError());
+    if (!inputs_are_device) MCU(m, cudaStreamSynchronize(m->stream));  // host buffers may be reused by the caller
+    m->pending = false;
+    m->simulations++;
+    return IPP_OK;
+}
+
+extern "C" int ipp_mcts_root_stats(ipp_mcts *m, float *ps, float *qsa, int32_t *nsa, int32_t *action_ids, int32_t *ns) {
+    if (!m) return IPP_ERR_INVALID;
+    if (!m->begun) return mfail(m, IPP_ERR_INVALID, "ipp_mcts_root_stats: call ipp_mcts_begin first");
+    const TreeDims &d = m->d;
+    const size_t TW = (size_t)d.T * d.W;
+    int rc;
+    for (int k = 0; k < 2; ++k)
+        if (!m->d_out_f[k] && (rc = malloc_dev(m, &m->d_out_f[k], TW)) != IPP_OK) return rc;
+    for (int k = 0; k < 3; ++k)
+        if (!m->d_out_i[k] && (rc = malloc_dev(m, &m->d_out_i[k], k == 2 ? (size_t)d.T : TW)) != IPP_OK) return rc;
+    dim3 grid((unsigned)std::min(8, (d.W + 255) / 256), (unsigned)d.T);
+    if (d.T > 65535) return mfail(m, IPP_ERR_UNSUPPORTED, "ipp_mcts_root_stats: more than 65535 trees per call");
+    mcts_root_export_kernel<<<grid, 256, 0, m->stream>>>(m->sp, d, m->a, m->d_out_f[0], m->d_out_f[1], m->d_out_i[0], m->d_out_i[1], m->d_out_i[2]);
+    m->launches++;
+    MCU(m, cudaGetLastError());
+    if (ps) MCU(m, cudaMemcpyAsync(ps, m->d_out_f[0], TW * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    if (qsa) MCU(m, cudaMemcpyAsync(qsa, m->d_out_f[1], TW * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    if (nsa) MCU(m, cudaMemcpyAsync(nsa, m->d_out_i[0], TW * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    if (action_ids) MCU(m, cudaMemcpyAsync(action_ids, m->d_out_i[1], TW * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    if (ns) MCU(m, cudaMemcpyAsync(ns, m->d_out_i[2], (size_t)d.T * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    MCU(m, cudaStreamSynchronize(m->stream));
+    return IPP_OK;
+}
+
+extern "C" void *ipp_mcts_device_ptr(ipp_mcts *m, int32_t which) {
+    if (!m) return nullptr;
+    switch (which) {
+        case IPP_MCTS_PTR_LEAF_INFO: return m->a.leaf;
+        case IPP_MCTS_PTR_PATH_ACTIONS: return m->a.path_action;
+        case IPP_MCTS_PTR_PATH_REWARDS: return m->a.path_reward;
+        default: return nullptr;
+    }
+}

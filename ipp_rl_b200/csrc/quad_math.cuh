@@ -243,13 +243,18 @@ __device__ __forceinline__ Geom decode(const StepParams &p, int job) {
 // trapezoidal-profile time are fp32 (relative error ~1e-7, two orders below the parity tolerance).
 __device__ __forceinline__ float fast_sqrt(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
 
-__device__ __forceinline__ float job_cost(const StepParams &p, double px, double py, double ph, double qx, double qy, double qh) {
-    const float dx = (float)(px - qx), dy = (float)(py - qy), dz = (float)(ph - qh);
-    const float d = fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+__device__ __forceinline__ float job_cost_from_dist(const StepParams &p, float d) {
     if (p.cost_mode == IPP_COST_DISTANCE) return d;
     const float d_acc = fminf(d * 0.5f, p.d_acc_max);  // min(d/2, v^2 / (2a))
     const float d_const = d - 2.0f * d_acc;
     return fmaf(d_const, p.inv_v, 2.0f * fast_sqrt(2.0f * d_acc * p.inv_a));
+}
+__device__ __forceinline__ float job_dist(double px, double py, double ph, double qx, double qy, double qh) {
+    const float dx = (float)(px - qx), dy = (float)(py - qy), dz = (float)(ph - qh);
+    return fast_sqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+}
+__device__ __forceinline__ float job_cost(const StepParams &p, double px, double py, double ph, double qx, double qy, double qh) {
+    return job_cost_from_dist(p, job_dist(px, py, ph, qx, qy, qh));
 }
 
 // One axis of cv2 INTER_AREA decimation: output sample o of n_out integrates the input over

@@ -335,6 +335,23 @@ class BatchedEngine:
         self._ck(self._lib.ipp_predict(self._h, n, _ptr(ei), _ptr(ids), _ptr(poses), _ptr(pp), _ptr(reward), fl))
         return reward
 
+    def rollout(self, path_actions, env_index=None, prev_poses=None, reward_mode=capi.REWARD_TRACE, adaptive=False) -> np.ndarray:
+        """Path rollouts: ``path_actions`` (n_jobs, horizon) action ids (negative = end of path) replayed as chained
+        ``simulate_prediction_step`` calls from each env's current belief, WITHOUT changing it (what MCTS.simulate does
+        along one tree path, planning/mcts_zero/mcts.py:239-246).  Returns per-step rewards (n_jobs, horizon)."""
+        pa = np.ascontiguousarray(path_actions, dtype=np.int32)
+        if pa.ndim != 2:
+            raise ValueError("path_actions must be (n_jobs, horizon)")
+        n, h = pa.shape
+        ei = None if env_index is None else np.ascontiguousarray(env_index, dtype=np.int32)
+        if ei is not None and ei.shape != (n,):
+            raise ValueError("env_index must have one entry per job")
+        pp = None if prev_poses is None else np.ascontiguousarray(np.broadcast_to(np.asarray(prev_poses, np.float64), (n, 3)))
+        rewards = np.empty((n, h), np.float32)
+        fl = self._flags(reward_mode, adaptive)
+        self._ck(self._lib.ipp_rollout(self._h, n, h, _ptr(ei), _ptr(pa), _ptr(pp), _ptr(rewards), fl))
+        return rewards
+
     def eval(self) -> np.ndarray:
         out = np.empty((self.batch, capi.NUM_METRICS), np.float32)
         self._ck(self._lib.ipp_eval(self._h, _ptr(out)))

@@ -69,3 +69,13 @@ def smooth_field(rng, shape):
         f += rng.uniform(0.3, 1.0) * np.sin(kx * xx + ky * yy + rng.uniform(0, 6.28))
     f = (f - f.min()) / (f.max() - f.min())
     return f
+
+
+def stub_policy_value(prev, budget_ratio, num_actions):
+    """The deterministic stand-in for the policy/value network that tests/golden/make_golden_mcts.py used when it ran the
+    reference MCTS (same function, duplicated here because that script imports /root/reference)."""
+    k = int(round(prev[0] + 7 * prev[1] + 13 * prev[2])) + int(round(100 * budget_ratio))
+    a = np.arange(num_actions, dtype=np.float64)
+    s = np.sin(a * 12.9898 + k * 78.233) * 43758.5453
+    policy = 0.2 + (s - np.floor(s))
+    return policy / policy.sum(), 0.05 * (k % 7)

@@ -14,12 +14,16 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "ipp_b200.h")
+HEADERS = [HEADER, os.path.join(ROOT, "include", "ipp_mcts.h")]
 
 
 def _declared_functions():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ipp_[a-z_0-9]+)\s*\(", src)))
+    out = set()
+    for h in HEADERS:
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        out |= set(re.findall(r"\b(ipp_[a-z_0-9]+)\s*\(", src))
+    return sorted(out)
 
 
 def test_library_exports_every_declared_symbol():
@@ -29,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     declared = _declared_functions()
     assert len(declared) >= 24
     for name in declared:
-        assert hasattr(lib, name), f"{name} declared in include/ipp_b200.h but not exported"
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
     assert sorted(_capi.SIGNATURES) == declared, "ctypes SIGNATURES must list exactly the header's functions"
 
 
@@ -38,15 +42,17 @@ def test_ctypes_structs_match_the_header(tmp_path):
 
     probe = tmp_path / "sz.c"
     probe.write_text(
-        f'#include "{HEADER}"\n#include <stdio.h>\n#include <stddef.h>\n'
-        "int main(){printf(\"%zu %zu %zu %zu %zu\\n\", sizeof(ipp_config), sizeof(ipp_info), offsetof(ipp_config, resolution), "
-        "offsetof(ipp_config, seed), offsetof(ipp_info, altitude)); return 0;}\n"
+        f'#include "{HEADERS[1]}"\n#include <stdio.h>\n#include <stddef.h>\n'
+        "int main(){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(ipp_config), sizeof(ipp_info), offsetof(ipp_config, resolution), "
+        "offsetof(ipp_config, seed), offsetof(ipp_info, altitude), sizeof(ipp_mcts_config), sizeof(ipp_mcts_info), "
+        "offsetof(ipp_mcts_config, puct_init), offsetof(ipp_mcts_info, device_bytes)); return 0;}\n"
     )
     exe = tmp_path / "sz"
     subprocess.run(["gcc", str(probe), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ctypes.sizeof(_capi.ipp_config), ctypes.sizeof(_capi.ipp_info), _capi.ipp_config.resolution.offset,
-                     _capi.ipp_config.seed.offset, _capi.ipp_info.altitude.offset]
+                     _capi.ipp_config.seed.offset, _capi.ipp_info.altitude.offset, ctypes.sizeof(_capi.ipp_mcts_config),
+                     ctypes.sizeof(_capi.ipp_mcts_info), _capi.ipp_mcts_config.puct_init.offset, _capi.ipp_mcts_info.device_bytes.offset]
 
 
 def test_missing_library_fails_loudly(tmp_path):

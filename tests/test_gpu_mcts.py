@@ -1,0 +1,231 @@
+"""GPU tests of the path-rollout kernel (ipp_rollout) and of the batched MCTS-zero rollout loop (include/ipp_mcts.h):
+
+* rollouts == chained ``simulate_prediction_step`` of the reference-pinned oracle, state untouched (all layouts);
+* the batched search reproduces the REAL reference MCTS on the golden cases (root visit counts exact);
+* the batched search vs the oracle restatement on a deeper, larger problem (rf = 2 footprints, horizon 3);
+* size-independent properties with thousands of trees on the 200x200 grid.
+"""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import ipp_oracle as orc
+from oracle import mcts_oracle as morc
+from tests._util import engine_cfg, golden, make_params, oracle_cfg, params_from_json, stub_policy_value
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(params, batch, **kw):
+    from ipp_rl_b200 import BatchedEngine
+
+    return BatchedEngine(engine_cfg(params, batch, **kw))
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("adaptive,reward_mode", [(False, 0), (True, 0), (False, 1)])
+def test_rollout_matches_chained_oracle_steps(layout, adaptive, reward_mode):
+    X, Y = 27, 27  # square: the reference's action-id formula collides on non-square grids (oracle.enumerate_actions)
+    params = make_params(X, Y, 1.0, 8, 20, 6, kappa=0.3, thr=0.5)
+    cfg = oracle_cfg(params)
+    B, J, H = 6, 40, 5
+    rng = np.random.RandomState(4)
+    mean0 = rng.uniform(0, 1, (B, Y, X)).astype(np.float32)
+    var0 = rng.uniform(0.05, 2.0, (B, Y, X)).astype(np.float32)
+    tbl = orc.enumerate_actions(cfg)
+    N = X * Y
+    # paths of nearby actions (overlapping footprints on purpose), some short, incl. border cells
+    paths = np.full((J, H), -1, np.int32)
+    env_index = rng.randint(0, B, J).astype(np.int32)
+    for j in range(J):
+        col, row = rng.randint(0, X), rng.randint(0, min(X, Y))
+        for k in range(rng.randint(1, H + 1)):
+            col = int(np.clip(col + rng.randint(-6, 7), 0, X - 1))
+            row = int(np.clip(row + rng.randint(-6, 7), 0, min(X, Y) - 1))
+            paths[j, k] = rng.randint(0, 3) * N + X * col + row
+    prev = np.stack([rng.uniform(0, X, J), rng.uniform(0, Y, J), rng.choice([8.0, 14.0, 20.0], J)], axis=1)
+    with _engine(params, B, layout=layout) as eng:
+        eng.reset(0.5, 1.0)
+        eng.set_state(mean0, var0)
+        r = eng.rollout(paths, env_index=env_index, prev_poses=prev, reward_mode=reward_mode, adaptive=adaptive)
+        m1, v1 = eng.get_state()
+    assert np.array_equal(m1, mean0) and np.array_equal(v1, var0), "a rollout must not write the belief"
+    for j in range(J):
+        var = var0[env_index[j]].astype(np.float64)
+        mean = mean0[env_index[j]].astype(np.float64)
+        p = prev[j]
+        for k in range(H):
+            if paths[j, k] < 0:
+                assert r[j, k] == 0.0
+                continue
+            a = tbl[paths[j, k]]
+            ro, var = orc.simulate_prediction_step(cfg, var, p, a, mean=mean, adaptive=adaptive, reward_mode=reward_mode)
+            p = a
+            # adaptive: a mask decision within fp32 rounding of the threshold may flip one cell
+            tol = 1e-5 * max(1.0, abs(ro)) if not adaptive else 2e-2 * max(1.0, abs(ro))
+            assert abs(r[j, k] - ro) <= tol, (j, k, r[j, k], ro)
+
+
+def _dense_stub_evaluator(mcts, root_prev, budget0, num_actions, res, altitudes):
+    def ev(leaf):
+        pri = np.zeros((mcts.n_trees, num_actions), np.float32)
+        val = np.zeros(mcts.n_trees, np.float32)
+        for t in range(mcts.n_trees):
+            if leaf.kind[t] != 1:
+                continue
+            if leaf.level[t] < 0:
+                prev = root_prev[t]
+            else:
+                prev = np.array([res * leaf.col[t] + 0.5 * res, res * leaf.row[t] + 0.5 * res, altitudes[leaf.level[t]]])
+            p, v = stub_policy_value(prev, float(leaf.budget[t]) / budget0, num_actions)
+            pri[t], val[t] = p, v
+        return pri, val
+
+    return ev
+
+
+@pytest.mark.parametrize("case", ["A", "B", "C"])
+@pytest.mark.parametrize("layout", [1, 2])
+def test_batched_search_reproduces_the_reference_mcts(case, layout):
+    """Root statistics of the REAL reference MCTS (golden_mcts.npz) from the GPU search, three identical trees."""
+    from ipp_rl_b200.planning.mcts_zero import BatchedMCTS
+
+    g = golden("golden_mcts.npz")
+    params = params_from_json(g[f"{case}_cfg"])
+    hyper, meta = json.loads(str(g[f"{case}_hyper"])), json.loads(str(g[f"{case}_meta"]))
+    budget = meta["budget"]
+    T = 3
+    var0 = np.broadcast_to(g[f"{case}_var0"], (T, 5, 5)).astype(np.float32)
+    prev = np.broadcast_to(g[f"{case}_prev"], (T, 3)).copy()
+    noise_dense = g[f"{case}_noise"]
+    uav = params["experiment"].get("uav")
+    with _engine(params, T, layout=layout, max_v=None if uav is None else uav["max_v"], max_a=None if uav is None else uav["max_a"]) as eng:
+        eng.reset(0.5, 1.0)
+        eng.set_state(var=var0)
+        with BatchedMCTS(eng, hyper, meta) as mcts:
+            ev = _dense_stub_evaluator(mcts, prev, budget, 50, 4.0, eng.altitudes)
+            mcts.begin(np.full(T, budget, np.float32), prev)
+            ids0 = mcts._root_ids()
+            noise = np.where(ids0 >= 0, noise_dense[np.maximum(ids0, 0)], 0.0).astype(np.float32)
+            for deploy in (False, True):
+                tag = f"{case}_{'deploy' if deploy else 'train'}"
+                policy, ids, visits = mcts.get_policy(np.full(T, budget, np.float32), prev, evaluator=ev, temperature=1,
+                                                      deploy_time=deploy, root_noise=noise)
+                st = mcts.root_stats()
+                for t in range(T):
+                    dense = {k: np.zeros(50) for k in ("N", "Q", "P", "pol")}
+                    ok = ids[t] >= 0
+                    dense["N"][ids[t][ok]] = st["Nsa"][t][ok]
+                    dense["Q"][ids[t][ok]] = st["Qsa"][t][ok]
+                    dense["P"][ids[t][ok]] = np.maximum(st["Ps"][t][ok], 0.0)
+                    dense["pol"][ids[t][ok]] = policy[t][ok]
+                    assert np.array_equal(dense["N"], g[f"{tag}_Nsa"]), (tag, dense["N"], g[f"{tag}_Nsa"])
+                    assert np.array_equal(dense["P"] > 0, g[f"{tag}_Vs"] & (g[f"{tag}_Ps"] > 0))
+                    assert st["Ns"][t] == int(g[f"{tag}_Ns"])
+                    assert np.max(np.abs(dense["Q"] - g[f"{tag}_Qsa"])) <= 1e-5 * max(1.0, np.abs(g[f"{tag}_Qsa"]).max())
+                    vs = g[f"{tag}_Vs"]  # (the reference keeps exploration noise on invalid actions; they are masked in compute_uct)
+                    assert np.max(np.abs(dense["P"] - g[f"{tag}_Ps"])[vs]) <= 1e-6
+                    assert np.max(np.abs(dense["pol"] - g[f"{tag}_policy"])) <= 1e-6
+
+
+def test_batched_search_matches_oracle_on_a_deeper_problem():
+    """24x24 grid, altitudes {8,14,20} (rf 1 and 2), horizon 3, different beliefs / poses / budgets per tree."""
+    from ipp_rl_b200.planning.mcts_zero import BatchedMCTS
+
+    X = Y = 24
+    params = make_params(X, Y, 1.0, 8, 20, 6)
+    cfg = oracle_cfg(params)
+    hyper = dict(puct_init=6.0, puct_base=10000, num_mcts_simulations=48, gamma=0.95, dirichlet_alpha=0.3, dirichlet_eps=0.0,
+                 forced_playout_factor=2.0, max_valid_action_distance=7.5)
+    H = 3
+    meta = dict(episode_horizon=H, scenario_info=None)
+    T = 12
+    rng = np.random.RandomState(21)
+    var0 = rng.uniform(0.1, 2.0, (T, Y, X)).astype(np.float32)
+    prev = np.stack([rng.randint(2, X - 2, T) + 0.5, rng.randint(2, Y - 2, T) + 0.5, rng.choice([8.0, 14.0, 20.0], T)], axis=1)
+    budgets = rng.uniform(6.0, 40.0, T).astype(np.float32)
+    num_actions = 3 * X * Y
+
+    def policy_of(prev_pose, budget):
+        k = int(round(prev_pose[0] * 3 + prev_pose[1] * 5 + prev_pose[2])) + int(budget * 4)
+        a = np.arange(num_actions, dtype=np.float64)
+        s = np.sin(a * 0.731 + k * 1.37) * 1000.0
+        pol = 0.05 + (s - np.floor(s)) ** 4
+        return (pol / pol.sum()).astype(np.float32), np.float32(0.02 * (k % 11))
+
+    with _engine(params, T, layout=2) as eng:
+        eng.reset(0.5, 1.0)
+        eng.set_state(var=var0)
+        with BatchedMCTS(eng, hyper, meta) as mcts:
+            def ev(leaf):
+                pri = np.zeros((T, num_actions), np.float32)
+                val = np.zeros(T, np.float32)
+                for t in range(T):
+                    if leaf.kind[t] != 1:
+                        continue
+                    pp = prev[t] if leaf.level[t] < 0 else np.array([leaf.col[t] + 0.5, leaf.row[t] + 0.5, eng.altitudes[leaf.level[t]]])
+                    pri[t], val[t] = policy_of(pp, float(leaf.budget[t]))
+                return pri, val
+
+            mcts.begin(budgets, prev)
+            for _ in range(hyper["num_mcts_simulations"]):
+                mcts.simulate(ev)
+            st = mcts.root_stats()
+            assert mcts.launches >= 3 * hyper["num_mcts_simulations"]
+    exact = 0
+    for t in range(T):
+        o = morc.OracleMCTS(cfg, hyper, H, evaluator=lambda info: policy_of(info["previous_action"], np.float32(info["budget"])))
+        o.search(var0[t].astype(np.float64), prev[t], float(budgets[t]), hyper["num_mcts_simulations"])
+        dense_n = np.zeros(num_actions)
+        dense_q = np.zeros(num_actions)
+        ok = st["action_ids"][t] >= 0
+        dense_n[st["action_ids"][t][ok]] = st["Nsa"][t][ok]
+        dense_q[st["action_ids"][t][ok]] = st["Qsa"][t][ok]
+        assert dense_n.sum() == o.Nsa[()].sum() == st["Ns"][t]
+        if np.array_equal(dense_n, o.Nsa[()]):
+            exact += 1
+            assert np.max(np.abs(dense_q - o.Qsa[()])) <= 2e-4 * max(1.0, np.abs(o.Qsa[()]).max())
+        else:  # an fp32-vs-fp64 near-tie may send a few simulations elsewhere; the bulk of the visits must agree
+            assert np.abs(dense_n - o.Nsa[()]).sum() <= 0.25 * dense_n.sum(), (t, np.abs(dense_n - o.Nsa[()]).sum())
+    assert exact >= T - 3, f"only {exact}/{T} trees reproduce the oracle's visit counts exactly"
+
+
+def test_search_properties_at_scale():
+    """4096 trees on the 200x200 / 3-altitude workload: the search never touches the belief, is deterministic, and
+    every simulation after the root expansion adds exactly one root visit."""
+    from ipp_rl_b200.planning.mcts_zero import BatchedMCTS
+
+    X = Y = 200
+    params = make_params(X, Y, 1.0, 8, 20, 6)
+    hyper = dict(puct_init=15.0, puct_base=10000, num_mcts_simulations=24, gamma=1.0, dirichlet_alpha=0.3, dirichlet_eps=0.25,
+                 forced_playout_factor=2.0, max_valid_action_distance=11.5)
+    meta = dict(episode_horizon=5, scenario_info=None)
+    T = 4096
+    rng = np.random.RandomState(2)
+    with _engine(params, T, layout=1, seed=3) as eng:
+        eng.reset(0.5, 1.82)
+        eng.synth_ground_truth(5)
+        for _ in range(2):  # a non-trivial belief
+            eng.step(rng.randint(0, eng.num_actions, T).astype(np.int32))
+        tr0 = eng.eval()[:, 4].copy()
+        m0, v0 = eng.get_state(0, 4)
+        budgets = rng.uniform(20, 200, T).astype(np.float32)
+        with BatchedMCTS(eng, hyper, meta) as mcts:
+            assert mcts.window_slots == 3 * 25 * 25
+            runs = []
+            for rep in range(2):
+                policy, ids, visits = mcts.get_policy(budgets, None, evaluator=None, temperature=1, deploy_time=True,
+                                                      rng=np.random.default_rng(7))
+                st = mcts.root_stats()
+                runs.append((policy.copy(), st["Nsa"].copy(), st["Qsa"].copy()))
+                assert np.all(st["Ns"] == hyper["num_mcts_simulations"] - 1)
+                assert np.all(st["Nsa"].sum(axis=1) == st["Ns"])
+                assert np.all((st["Nsa"] > 0) <= (st["Ps"] > 0))  # only valid actions are ever visited
+                assert np.allclose(policy.sum(axis=1), 1.0, atol=1e-6)
+                assert np.all(st["Qsa"][st["Nsa"] > 0] > 0)  # rewards are positive
+            for a, b in zip(runs[0], runs[1]):
+                assert np.array_equal(a, b)
+        tr1 = eng.eval()[:, 4]
+        m1, v1 = eng.get_state(0, 4)
+        assert np.array_equal(tr0, tr1) and np.array_equal(m0, m1) and np.array_equal(v0, v1)

@@ -164,3 +164,34 @@ def test_philox_known_answer():
         assert tuple(int(x) for x in got) == out
     n = orc.device_normals(1, 2, 3, 50000)
     assert abs(n.mean()) < 0.01 and abs(n.std() - 1) < 0.01
+
+
+# ---- MCTS-zero rollout loop: oracle/mcts_oracle.py vs the REAL reference MCTS (tests/golden/make_golden_mcts.py) ----------
+@pytest.mark.parametrize("case", ["A", "B", "C"])
+@pytest.mark.parametrize("deploy", [False, True])
+def test_mcts_oracle_matches_reference_search(case, deploy):
+    import json
+
+    from oracle import mcts_oracle as morc
+    from tests._util import stub_policy_value
+
+    g = golden("golden_mcts.npz")
+    params = params_from_json(g[f"{case}_cfg"])
+    cfg = oracle_cfg(params)
+    hyper, meta = json.loads(str(g[f"{case}_hyper"])), json.loads(str(g[f"{case}_meta"]))
+    budget, sims = meta["budget"], hyper["num_mcts_simulations"]
+    num_actions = 50
+    tag = f"{case}_{'deploy' if deploy else 'train'}"
+
+    def ev(info):
+        return stub_policy_value(info["previous_action"], info["budget"] / budget, num_actions)
+
+    o = morc.OracleMCTS(cfg, hyper, meta["episode_horizon"], evaluator=ev)
+    o.search(g[f"{case}_var0"].copy(), g[f"{case}_prev"].copy(), budget, sims, root_noise=g[f"{case}_noise"])
+    assert np.array_equal(o.Nsa[()], g[f"{tag}_Nsa"])  # visit counts: exact
+    assert np.array_equal(o.Vs[()], g[f"{tag}_Vs"])
+    assert o.Ns[()] == int(g[f"{tag}_Ns"]) and o.inference_counter == int(g[f"{tag}_inferences"])
+    assert np.max(np.abs(o.Qsa[()] - g[f"{tag}_Qsa"])) <= 1e-12
+    assert np.max(np.abs(o.Ps[()] - g[f"{tag}_Ps"])) <= 1e-15
+    pol, _ = o.policy_from_root(temperature=1, deploy_time=deploy)
+    assert np.max(np.abs(pol - g[f"{tag}_policy"])) <= 1e-15
