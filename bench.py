@@ -240,6 +240,53 @@ def run_ours(args, rank, world, local_rank):
         launches_e2e = eng.launches - launches_e2e0
         assert np.isfinite(out_np).all()
 
+    # ---- secondary leg (BASELINE.json configs[3], "C4"): mcts_zero rollouts on the same beliefs.  Lock-step search over
+    #      `--mcts-trees` envs, `--mcts-sims` simulations, episode_horizon 5, max_valid_action_distance 11.5 m, uniform
+    #      priors / zero values (no network: the policy/value net is outside this library).  Reported beside the headline.
+    mcts_res = None
+    if args.mcts_trees > 0:
+        from ipp_rl_b200.planning.mcts_zero import BatchedMCTS
+
+        Tm, Sm = min(args.mcts_trees, B), args.mcts_sims
+        hyper = dict(puct_init=15.0, puct_base=10000, num_mcts_simulations=Sm, gamma=1.0, dirichlet_alpha=0.3, dirichlet_eps=0.25,
+                     forced_playout_factor=2.0, max_valid_action_distance=11.5)
+        meta = dict(episode_horizon=5, scenario_info=None)
+        budgets = np.full(Tm, 150.0, np.float32)
+        with torch.cuda.stream(stream):
+            with BatchedMCTS(eng, hyper, meta, n_trees=Tm) as mcts:
+                # pass 1 (untimed, host-synchronous): count the prediction steps of the search (it is deterministic)
+                mcts.begin(budgets)
+                edges = 0
+                cells_by_level = np.array([(2 * r + 1) ** 2 for r in radii], np.float64)
+                cells = 0.0
+                for i in range(Sm):
+                    leaf = mcts.simulate(lambda lf: (None, None))
+                    edges += int(leaf.path_len.sum())
+                path_ids = None
+                # pass 2 (timed): device-only loop, CUDA events on the engine stream
+                mcts.begin(budgets)
+                l0 = mcts.launches
+                barrier()
+                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                m0.record(stream)
+                for i in range(Sm):
+                    mcts.simulate(None)
+                m1.record(stream)
+                barrier()
+                ms_m = m0.elapsed_time(m1)
+                tm = torch.tensor([ms_m], dtype=torch.float64, device="cuda")
+                if dist is not None:
+                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                ms_m = float(tm.item())
+                st = mcts.root_stats()
+                assert np.all(st["Ns"] == Sm - 1)
+                mcts_res = {"trees_per_gpu": Tm, "simulations": Sm, "episode_horizon": 5, "window_slots": mcts.window_slots,
+                            "tree_simulations_per_sec": world * Tm * Sm / (ms_m * 1e-3),
+                            "prediction_steps_per_sec": world * edges / (ms_m * 1e-3), "prediction_steps": edges,
+                            "ms_per_lockstep_simulation": ms_m / Sm, "gpu_launches": int(mcts.launches - l0),
+                            "tree_bytes_per_gpu": int(mcts.info.device_bytes),
+                            "evaluator": "uniform priors, zero values (network outside this library)"}
+
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -288,6 +335,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if mcts_res is not None:
+            line["mcts_rollouts"] = mcts_res
         print(json.dumps(line))
     eng.close()
     if dist is not None:
@@ -301,10 +350,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="envs per GPU")
-    ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "mv"), choices=["planes", "mv", "tiled"])
+    ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "tiled"), choices=["planes", "mv", "tiled"])
     ap.add_argument("--cpu-envs", type=int, default=4096, help="env sample of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=500, help="steps of the host-buffer (e2e) leg (<= --steps)")
+    ap.add_argument("--mcts-trees", type=int, default=4096, help="trees of the secondary mcts_zero rollout leg (0 = skip)")
+    ap.add_argument("--mcts-sims", type=int, default=32)
     ap.add_argument("--max-altitude", type=float, default=None, help="experiments only: override the top altitude of the action set")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -35,6 +35,13 @@ namespace ipp {
 #ifndef IPP_ASYNC_MAX_WARPS
 #define IPP_ASYNC_MAX_WARPS 16
 #endif
+// experiment switch: alias every env onto the first IPP_ASYNC_ALIAS + 1 envs (all traffic hits L2) to time the
+// compute side of the pipeline alone; results are meaningless in that build
+#ifdef IPP_ASYNC_ALIAS
+#define IPP_ENV_OF(job) ((job) & IPP_ASYNC_ALIAS)
+#else
+#define IPP_ENV_OF(job) (job)
+#endif
 constexpr int kAsyncSlots = IPP_ASYNC_SLOTS;         // footprints in flight per warp
 constexpr int kAsyncMaxWarps = IPP_ASYNC_MAX_WARPS;  // warps per CTA (1 CTA / SM), further limited by shared memory
 constexpr int kTicketChunk = 8;                      // tickets taken per atomic
@@ -141,62 +148,48 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
             if (lane < 3) cp_async_8(smem_u32(&c->prev[lane]), p.prev_state + 3 * (size_t)job + lane);
             const uint32_t tile = smem_u32(my_stages + (size_t)s * stage_bytes);
             if (TILED) {
-                // IPP_LAYOUT_TILED: the footprint covers a rectangle of 128-byte tiles.  Eight lanes take the eight
-                // 16-byte chunks of one tile, a warp instruction covers four tiles of a tile-row: whole 128 B lines,
-                // constant strides.  Chunks outside the (16-byte aligned) footprint rows are skipped, so the staged
-                // image is the same row-major aligned superset as with row-major 16-byte staging.
-                const int u = lane & 7, t4 = lane >> 3;
-                const int yd = yu + ny - 1, xr = xl + nx - 1;
-                const int ty0 = yu >> 2, nty = (yd >> 2) - ty0 + 1;
-                const int rin = u >> 1;  // row inside the tile
-                {   // belief: 4 x 4 cells of float2 per tile, chunk = 2 cells
-                    const int ox = xl & 1, pm = (ox + nx + 1) & ~1;
-                    const int tx0 = xl >> 2, ntx = (xr >> 2) - tx0 + 1;
-                    const float4 *src_row = reinterpret_cast<const float4 *>(mv_base + (size_t)job * p.plane) + ((size_t)(ty0 * p.txm + tx0 + t4) * 8 + u);
-                    int R = 4 * ty0 + rin;
-                    const int cc0 = 4 * (tx0 + t4) + 2 * (u & 1);  // first cell of this lane's chunk (absolute column)
-                    uint32_t dst_row = tile + 8u * (uint32_t)((R - yu) * pm + (cc0 - xl + ox));
-#pragma unroll 1
-                    for (int ty = 0; ty < nty; ++ty) {
-                        if (R >= yu && R <= yd) {
-                            const float4 *src = src_row;
-                            uint32_t dst = dst_row;
-                            int cc = cc0;
-                            for (int tx = t4; tx < ntx; tx += 4) {
-                                if (cc + 1 >= xl && cc <= xr) cp_async_16(dst, src);
-                                src += 32;   // four tiles
-                                dst += 128u;  // 16 cells
-                                cc += 16;
-                            }
+                // IPP_LAYOUT_TILED: same staging as the 16-byte row-major path below (lanes = RP row-segments of W
+                // chunks, rows advance by RP), only the source index differs: chunk (R, cc) of a plane with `tx` tiles
+                // per tile-row sits at float4 index ((R>>2)*tx + tile(cc))*8 + (R&3)*2 + half(cc); stepping R by RP
+                // adds 2*RP inside a tile and tx*8 + 2*(RP-4) across a tile boundary.
+                const int ox = xl & 1, oxg = xl & 3;
+                const int cm = (ox + nx + 1) >> 1, cg = (oxg + nx + 3) >> 2;  // 16 B chunks per row
+                {
+                    const int W = cm <= 8 ? 8 : (cm <= 16 ? 16 : 32), RP = 32 / W;
+                    const int lr = lane / W, lc = lane - lr * W;
+                    const int wrap = p.txm * 8 + 2 * (RP - 4);
+                    const float4 *plane = reinterpret_cast<const float4 *>(mv_base + (size_t)IPP_ENV_OF(job) * p.plane);
+                    for (int c0 = lc; c0 < cm; c0 += 32) {
+                        const int cc = xl - ox + 2 * c0;  // first cell of the chunk (even)
+                        int R = yu + lr;
+                        const float4 *src = plane + (size_t)(((R >> 2) * p.txm + (cc >> 2)) * 8 + (R & 3) * 2 + ((cc >> 1) & 1));
+                        uint32_t dst = tile + 16u * (uint32_t)(lr * cm + c0);
+#pragma unroll 2
+                        for (int r = lr; r < ny; r += RP) {
+                            cp_async_16(dst, src);
+                            src += ((R & 3) + RP >= 4) ? wrap : 2 * RP;
+                            R += RP;
+                            dst += 16u * (uint32_t)(RP * cm);
                         }
-                        src_row += (size_t)p.txm * 8;
-                        dst_row += 32u * (uint32_t)pm;  // four rows
-                        R += 4;
                     }
                 }
-                {   // ground truth: 8 (x) x 4 (y) floats per tile, chunk = 4 cells
-                    const int oxg = xl & 3, pg = (oxg + nx + 3) & ~3;
-                    const int tx0 = xl >> 3, ntx = (xr >> 3) - tx0 + 1;
-                    const float4 *src_row = reinterpret_cast<const float4 *>(p.gt + (size_t)job * p.plane_gt) + ((size_t)(ty0 * p.txg + tx0 + t4) * 8 + u);
-                    int R = 4 * ty0 + rin;
-                    const int cc0 = 8 * (tx0 + t4) + 4 * (u & 1);
-                    uint32_t dst_row = tile + (uint32_t)ap.mv_tile_bytes + 4u * (uint32_t)((R - yu) * pg + (cc0 - xl + oxg));
-#pragma unroll 1
-                    for (int ty = 0; ty < nty; ++ty) {
-                        if (R >= yu && R <= yd) {
-                            const float4 *src = src_row;
-                            uint32_t dst = dst_row;
-                            int cc = cc0;
-                            for (int tx = t4; tx < ntx; tx += 4) {
-                                if (cc + 3 >= xl && cc <= xr) cp_async_16(dst, src);
-                                src += 32;
-                                dst += 128u;  // 32 cells
-                                cc += 32;
-                            }
+                {
+                    const int W = cg <= 8 ? 8 : (cg <= 16 ? 16 : 32), RP = 32 / W;
+                    const int lr = lane / W, lc = lane - lr * W;
+                    const int wrap = p.txg * 8 + 2 * (RP - 4);
+                    const float4 *plane = reinterpret_cast<const float4 *>(p.gt + (size_t)IPP_ENV_OF(job) * p.plane_gt);
+                    for (int c0 = lc; c0 < cg; c0 += 32) {
+                        const int cc = xl - oxg + 4 * c0;  // first cell of the chunk (multiple of 4)
+                        int R = yu + lr;
+                        const float4 *src = plane + (size_t)(((R >> 2) * p.txg + (cc >> 3)) * 8 + (R & 3) * 2 + ((cc >> 2) & 1));
+                        uint32_t dst = tile + (uint32_t)ap.mv_tile_bytes + 16u * (uint32_t)(lr * cg + c0);
+#pragma unroll 2
+                        for (int r = lr; r < ny; r += RP) {
+                            cp_async_16(dst, src);
+                            src += ((R & 3) + RP >= 4) ? wrap : 2 * RP;
+                            R += RP;
+                            dst += 16u * (uint32_t)(RP * cg);
                         }
-                        src_row += (size_t)p.txg * 8;
-                        dst_row += 16u * (uint32_t)pg;
-                        R += 4;
                     }
                 }
             } else if (ap.vec16) {
@@ -205,7 +198,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 // and no L1 line allocation limiting the copies in flight.  Needs x_dim % 4 == 0.
                 const int ox = xl & 1, oxg = xl & 3;
                 const int cm = (ox + nx + 1) >> 1, cg = (oxg + nx + 3) >> 2;  // 16 B chunks per row
-                const size_t row0 = (size_t)job * p.plane + (size_t)(yu * X);
+                const size_t row0 = (size_t)IPP_ENV_OF(job) * p.plane + (size_t)(yu * X);
                 {
                     const int W = cm <= 8 ? 8 : (cm <= 16 ? 16 : 32), RP = 32 / W;
                     const int lr = lane / W, lc = lane - lr * W;
@@ -240,7 +233,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 const int W = nx <= 8 ? 8 : (nx <= 16 ? 16 : 32);
                 const int RP = 32 / W;
                 const int lr = lane / W, lc = lane - lr * W;
-                const size_t org = (size_t)job * p.plane + (size_t)(yu * X + xl);
+                const size_t org = (size_t)IPP_ENV_OF(job) * p.plane + (size_t)(yu * X + xl);
                 for (int c0 = lc; c0 < nx; c0 += 32) {  // one pass unless the footprint is wider than 32 cells
                     const float2 *src_mv = mv_base + org + (size_t)(lr * X + c0);
                     const float *src_gt = p.gt + org + (size_t)(lr * X + c0);
@@ -340,7 +333,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         // the host guarantees for every footprint that fits the shared-memory tiles (setup_async)
         const uint32_t magic_x = (uint32_t)(65536.0f * fast_rcp((float)nqx) * 1.00000012f) + 1u;
         const uint32_t magic_c = (uint32_t)(65536.0f * fast_rcp((float)out_c) * 1.00000012f) + 1u;
-        float2 *mv_g = mv_base + (size_t)job * p.plane + (TILED ? (size_t)0 : (size_t)(yu * X + xl));
+        float2 *mv_g = mv_base + (size_t)IPP_ENV_OF(job) * p.plane + (TILED ? (size_t)0 : (size_t)(yu * X + xl));
         const size_t nrow = (size_t)job * (size_t)p.noise_stride;
         float acc = 0.0f;
         float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four iterations

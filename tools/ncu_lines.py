@@ -21,8 +21,9 @@ LIB = os.path.join(ROOT, "ipp_rl_b200", "csrc", "libipp_b200.so")
 def sass_lines(mangled_substr):
     with tempfile.TemporaryDirectory() as d:
         subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=d, check=True, capture_output=True)
-        cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-        txt = subprocess.run(["nvdisasm", "--print-line-info", cubin], cwd=d, check=True, capture_output=True, text=True).stdout
+        txt = ""
+        for cubin in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):  # one cubin per translation unit
+            txt += subprocess.run(["nvdisasm", "--print-line-info", cubin], cwd=d, check=True, capture_output=True, text=True).stdout
     out, cur, active = [], None, False
     for ln in txt.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
