@@ -142,6 +142,16 @@ int ipp_set_ground_truth(ipp_engine *e, const float *gt, int32_t first_env, int3
  * [0,1] per env, a stand-in for simulations/ground_truths.py:14-33; not a parity item). */
 int ipp_synth_ground_truth(ipp_engine *e, uint64_t seed);
 
+/* Gaussian-random-field ground truth generated ON THE DEVICE for envs [first_env, first_env + n_env) — replaces
+ * GaussianRandomField.create_ground_truth_map (simulations/simulations.py:43-48) over
+ * gaussian_random_field (simulations/ground_truths.py:14-33): white noise -> fft2 -> * sqrt(k^-cluster_radius)
+ * (0 at k = 0) -> ifft2 -> real part -> min-max normalisation to [0, 1].  white_noise: host array
+ * [n_env][y_dim][x_dim] of standard normals (the reference's np.random.normal draw; parity mode), or NULL ->
+ * counter-based Philox4x32-10 normals keyed by (seed, global env id, cell), independent of how the batch is sharded.
+ * The FFTs are cuFFT (library; loaded with dlopen at first use -> IPP_ERR_UNSUPPORTED if absent). */
+int ipp_generate_ground_truth(ipp_engine *e, double cluster_radius, uint64_t seed, const float *white_noise,
+                              int32_t first_env, int32_t n_env);
+
 /* Read / write belief state as dense [n_env][y_dim][x_dim] fp32 arrays (either may be NULL).
  * Replaces reads/writes of grid_map.mean / np.diag(grid_map.cov_matrix)
  * (mapping/grid_maps.py:10-11). */

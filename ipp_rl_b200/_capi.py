@@ -152,6 +152,7 @@ SIGNATURES = {
     "ipp_set_ground_truth": (C.c_int, [_P, _P, _I32, _I32, _I32]),
     "ipp_get_ground_truth": (C.c_int, [_P, _P, _I32, _I32, _I32]),
     "ipp_synth_ground_truth": (C.c_int, [_P, C.c_uint64]),
+    "ipp_generate_ground_truth": (C.c_int, [_P, C.c_double, C.c_uint64, _P, _I32, _I32]),
     "ipp_get_state": (C.c_int, [_P, _P, _P, _I32, _I32, _I32]),
     "ipp_set_state": (C.c_int, [_P, _P, _P, _I32, _I32, _I32]),
     "ipp_set_prev_pose": (C.c_int, [_P, _P]),

@@ -217,6 +217,19 @@ class BatchedEngine:
     def synth_ground_truth(self, seed: int = 0) -> None:
         self._ck(self._lib.ipp_synth_ground_truth(self._h, seed))
 
+    def generate_ground_truth(self, cluster_radius: float, seed: int = 0, white_noise=None, first_env: int = 0,
+                              n_env: Optional[int] = None) -> None:
+        """Gaussian random fields generated on the device (GaussianRandomField.create_ground_truth_map,
+        simulations/simulations.py:43-48).  ``white_noise`` (n, y_dim, x_dim) standard normals = the reference's
+        ``np.random.normal`` draw (parity mode); None = device Philox stream keyed by (seed, global env id)."""
+        n = self.batch - first_env if n_env is None else n_env
+        wn = None
+        if white_noise is not None:
+            wn = _f32(white_noise).reshape(-1, self.y_dim, self.x_dim)
+            if wn.shape[0] != n:
+                raise ValueError(f"white_noise must hold {n} maps")
+        self._ck(self._lib.ipp_generate_ground_truth(self._h, float(cluster_radius), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(wn), first_env, n))
+
     def get_ground_truth(self, first_env: int = 0, n_env: Optional[int] = None) -> np.ndarray:
         n = self.batch - first_env if n_env is None else n_env
         out = np.empty((n, self.y_dim, self.x_dim), np.float32)

@@ -195,3 +195,17 @@ def test_mcts_oracle_matches_reference_search(case, deploy):
     assert np.max(np.abs(o.Ps[()] - g[f"{tag}_Ps"])) <= 1e-15
     pol, _ = o.policy_from_root(temperature=1, deploy_time=deploy)
     assert np.max(np.abs(pol - g[f"{tag}_policy"])) <= 1e-15
+
+
+def test_host_ground_truth_generator_matches_reference():
+    """ipp_rl_b200/simulations/ground_truths.py (host, vectorised) vs the reference's gaussian_random_field under the same seed."""
+    from ipp_rl_b200.simulations import ground_truths as gtgen
+
+    g = golden("golden_grf.npz")
+    for name in g["names"]:
+        X, Y = (int(v) for v in g[f"{name}_dims"])
+        r = float(g[f"{name}_radius"])
+        np.random.seed(int(g[f"{name}_seed"]))
+        f = gtgen.gaussian_random_field(lambda k: k ** (-r), X, Y)
+        assert f.shape == (Y, X)
+        assert np.max(np.abs(f - g[f"{name}_field"])) <= 1e-12
