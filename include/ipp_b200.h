@@ -232,6 +232,16 @@ int ipp_rollout_device(ipp_engine *e, int32_t n_jobs, int32_t horizon, const int
 int ipp_eval(ipp_engine *e, float *metrics);
 int ipp_eval_device(ipp_engine *e, float *metrics);
 
+/* Observation (network-input) planes of the current belief for envs [first_env, first_env + n_env), NCHW fp32
+ * out[n_env][C][y_dim][x_dim] — the per-cell restriction of generate_input_feature_planes
+ * (planning/common/features.py:83-151) for one history entry: {variance / max variance (adaptive-masked with
+ * IPP_FLAG_ADAPTIVE, :94-99), x / (x_dim*res), y / (x_dim*res) [sic :51], (h - min_alt)/(max_alt - min_alt),
+ * budget_ratio} and, with IPP_OBS_COSTS, the min-max normalised action-cost plane (:61-71); C = 5 or 6.
+ * poses[n_env][3] (host; NULL -> the envs' stored previous actions), budget_ratio[n_env] (host; NULL -> 1). */
+#define IPP_OBS_COSTS 256u
+int ipp_observe(ipp_engine *e, int32_t first_env, int32_t n_env, const double *poses, const float *budget_ratio,
+                uint32_t flags, float *out, int32_t out_is_device);
+
 /* ---- interop ----------------------------------------------------------------------------------- */
 #define IPP_PTR_MEAN 0   /* PLANES: float[B][Y][X];  MV: float2[B][Y][X] base (mean at .x);  TILED: float2 tiles */
 #define IPP_PTR_VAR 1    /* PLANES: float[B][Y][X];  MV / TILED: same base + 1 float (stride 2) */

@@ -26,6 +26,7 @@ FLAG_NO_DSIZE_QUIRK = 8
 FLAG_LOGODDS = 16
 FLAG_NO_COMMIT = 32
 FLAG_KEEP_PREV = 64
+OBS_COSTS = 256
 
 LAYOUT_PLANES = 0
 LAYOUT_MV = 1
@@ -165,6 +166,7 @@ SIGNATURES = {
     "ipp_predict_device": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _U32]),
     "ipp_rollout": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _U32]),
     "ipp_rollout_device": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _U32]),
+    "ipp_observe": (C.c_int, [_P, _I32, _I32, _P, _P, _U32, _P, _I32]),
     "ipp_eval": (C.c_int, [_P, _P]),
     "ipp_eval_device": (C.c_int, [_P, _P]),
     "ipp_device_ptr": (_P, [_P, _I32]),

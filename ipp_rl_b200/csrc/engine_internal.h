@@ -8,3 +8,4 @@ int ipp_internal_step_params(const ipp_engine *e, ipp::StepParams *out);
 cudaStream_t ipp_internal_stream(const ipp_engine *e);
 void ipp_internal_count_launches(ipp_engine *e, int n);
 int ipp_internal_fail(ipp_engine *e, int code, const char *msg);
+int ipp_internal_layout(const ipp_engine *e);

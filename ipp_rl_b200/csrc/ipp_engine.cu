@@ -1162,6 +1162,7 @@ int ipp_internal_step_params(const ipp_engine *e, ipp::StepParams *out) {
 cudaStream_t ipp_internal_stream(const ipp_engine *e) { return e->stream; }
 void ipp_internal_count_launches(ipp_engine *e, int n) { e->launches += (uint64_t)n; }
 int ipp_internal_fail(ipp_engine *e, int code, const char *msg) { return fail(e, code, "%s", msg); }
+int ipp_internal_layout(const ipp_engine *e) { return e->cfg.layout; }
 
 extern "C" int ipp_eval_device(ipp_engine *e, float *metrics) {
     if (!e || !metrics) return IPP_ERR_INVALID;

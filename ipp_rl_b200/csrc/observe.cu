@@ -1,0 +1,172 @@
+// observe.cu — observation (network-input) planes straight from the belief in HBM (sm_100a).
+//
+// Reference: generate_input_feature_planes (planning/common/features.py:83-151) builds, per history entry, N x N
+// planes from the dense covariance: [min-max normalised state, x, y, z position planes, budget plane] and one
+// N x N action-cost plane (:61-71).  A per-cell engine has no N x N state; this kernel emits the (y_dim, x_dim)
+// restriction of each of those planes for the CURRENT belief, in NCHW order, one CTA per env:
+//
+//   0  variance / max(variance)      = the diagonal of min_max_normalize(state) for a diagonal state (whose N x N
+//                                       minimum is the off-diagonal 0); cells failing the adaptive mask
+//                                       (mean + kappa * var >= threshold, rewards.py:8-12) are zeroed first (:94-99)
+//   1  x / (x_dim * res)    2  y / (x_dim * res)  [sic, features.py:51]    3  (h - min_alt) / (max_alt - min_alt)
+//   4  remaining budget / initial budget
+//   5  (optional) cost from the current pose, dropped to min_altitude, to every cell centre at min_altitude,
+//      min-max normalised = any column of the reference's cost plane, re-indexed from action id to (row, col)
+//
+// History (input_history_length > 1) is the caller's ring buffer of these outputs.  HBM traffic: 8 B/cell read
+// (twice: max, then write pass) + 4 B/cell/plane written.
+#include <cmath>
+
+#include "engine_internal.h"
+
+using namespace ipp;
+
+namespace {
+
+constexpr int kObsThreads = 256;
+
+struct ObsParams {
+    StepParams sp;
+    int layout;
+    int first_env;
+    int planes;  // 5 or 6
+    int adaptive;
+    double min_alt, max_alt;
+    const double *poses;   // [n][3] or nullptr -> sp.prev_state of the env
+    const float *budgets;  // [n] remaining / initial
+    float *out;            // [n][planes][Y][X]
+};
+
+__device__ __forceinline__ float block_max(float v, float *smem) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = smem[0];
+    for (int w = 1; w < kObsThreads / 32; ++w) r = fmaxf(r, smem[w]);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kObsThreads) observe_kernel(const __grid_constant__ ObsParams op) {
+    __shared__ float smem[kObsThreads / 32];
+    const StepParams &p = op.sp;
+    const int j = blockIdx.x, env = op.first_env + j;
+    const int X = p.X, Y = p.Y;
+    const size_t N = (size_t)X * Y;
+    const bool planes_layout = op.layout == IPP_LAYOUT_PLANES, tiled = op.layout == IPP_LAYOUT_TILED;
+    const float *mean_pl = p.mean + (size_t)env * p.plane, *var_pl = p.var + (size_t)env * p.plane;
+    const float2 *mv = reinterpret_cast<const float2 *>(p.mean) + (size_t)env * p.plane;
+    auto load = [&](size_t i, float &m, float &v) {
+        if (planes_layout) {
+            m = mean_pl[i];
+            v = var_pl[i];
+        } else {
+            const int R = (int)(i / X), C = (int)(i - (size_t)R * X);
+            const float2 t = mv[tiled ? (size_t)tiled_mv_index(p.txm, R, C) : i];
+            m = t.x;
+            v = t.y;
+        }
+    };
+    const double *pose = op.poses ? op.poses + 3 * (size_t)j : p.prev_state + 3 * (size_t)env;
+    const double px = pose[0], py = pose[1], ph = pose[2];
+
+    // pass 1: max of the (masked) variance; extremes of the cost plane
+    float vmax = 0.0f, cmax = 0.0f, cmin_neg = -INFINITY;
+    for (size_t i = threadIdx.x; i < N; i += kObsThreads) {
+        float m, v;
+        load(i, m, v);
+        if (op.adaptive && !(fmaf(p.kappa, v, m) >= p.thr)) v = 0.0f;
+        vmax = fmaxf(vmax, v);
+        if (op.planes > 5) {
+            const int R = (int)(i / X), C = (int)(i - (size_t)R * X);
+            const double cx = __dadd_rn(__dmul_rn(p.res, (double)C), __dmul_rn(0.5, p.res));
+            const double cy = __dadd_rn(__dmul_rn(p.res, (double)R), __dmul_rn(0.5, p.res));
+            const float c = job_cost(p, cx, cy, op.min_alt, px, py, op.min_alt);
+            cmax = fmaxf(cmax, c);
+            cmin_neg = fmaxf(cmin_neg, -c);
+        }
+    }
+    vmax = block_max(vmax, smem);
+    if (op.planes > 5) {
+        cmax = block_max(cmax, smem);
+        cmin_neg = block_max(cmin_neg, smem);
+    }
+    const float cmin = -cmin_neg;
+    // min_max_normalize (features.py:74-81): min == max -> x / max
+    const float xs = (float)(px / ((double)X * p.res)), ys = (float)(py / ((double)X * p.res));
+    const float zs = (float)((ph - op.min_alt) / (op.max_alt - op.min_alt));
+    const float bs = op.budgets ? op.budgets[j] : 1.0f;
+    float *o = op.out + (size_t)j * op.planes * N;
+    for (size_t i = threadIdx.x; i < N; i += kObsThreads) {
+        float m, v;
+        load(i, m, v);
+        if (op.adaptive && !(fmaf(p.kappa, v, m) >= p.thr)) v = 0.0f;
+        o[i] = v / vmax;  // the N x N minimum of a diagonal state is the off-diagonal 0
+        o[N + i] = xs;
+        o[2 * N + i] = ys;
+        o[3 * N + i] = zs;
+        o[4 * N + i] = bs;
+        if (op.planes > 5) {
+            const int R = (int)(i / X), C = (int)(i - (size_t)R * X);
+            const double cx = __dadd_rn(__dmul_rn(p.res, (double)C), __dmul_rn(0.5, p.res));
+            const double cy = __dadd_rn(__dmul_rn(p.res, (double)R), __dmul_rn(0.5, p.res));
+            const float c = job_cost(p, cx, cy, op.min_alt, px, py, op.min_alt);
+            o[5 * N + i] = cmax > cmin ? (c - cmin) / (cmax - cmin) : c / cmax;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int ipp_observe(ipp_engine *e, int32_t first_env, int32_t n_env, const double *poses, const float *budget_ratio, uint32_t flags,
+                           float *out, int32_t out_is_device) {
+    if (!e || !out) return IPP_ERR_INVALID;
+    ObsParams op;
+    ipp_internal_step_params(e, &op.sp);
+    if (first_env < 0 || n_env < 0 || first_env + n_env > op.sp.batch) return ipp_internal_fail(e, IPP_ERR_INVALID, "ipp_observe: env range outside the batch");
+    if (n_env == 0) return IPP_OK;
+    cudaStream_t stream = ipp_internal_stream(e);
+    op.layout = ipp_internal_layout(e);
+    op.first_env = first_env;
+    op.planes = (flags & IPP_OBS_COSTS) ? 6 : 5;
+    op.adaptive = (flags & IPP_FLAG_ADAPTIVE) ? 1 : 0;
+    op.min_alt = op.sp.lut[0].alt;
+    op.max_alt = op.sp.lut[op.sp.n_levels - 1].alt;
+    const size_t N = (size_t)op.sp.X * op.sp.Y, total = (size_t)n_env * op.planes * N;
+    double *d_poses = nullptr;
+    float *d_budget = nullptr, *d_out = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_poses);
+        cudaFree(d_budget);
+        if (!out_is_device) cudaFree(d_out);
+    };
+    bool ok = true;
+    if (poses) {
+        ok = ok && cudaMalloc((void **)&d_poses, 3 * (size_t)n_env * sizeof(double)) == cudaSuccess;
+        if (ok) cudaMemcpyAsync(d_poses, poses, 3 * (size_t)n_env * sizeof(double), cudaMemcpyHostToDevice, stream);
+    }
+    if (budget_ratio) {
+        ok = ok && cudaMalloc((void **)&d_budget, (size_t)n_env * sizeof(float)) == cudaSuccess;
+        if (ok) cudaMemcpyAsync(d_budget, budget_ratio, (size_t)n_env * sizeof(float), cudaMemcpyHostToDevice, stream);
+    }
+    if (out_is_device)
+        d_out = out;
+    else
+        ok = ok && cudaMalloc((void **)&d_out, total * sizeof(float)) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        cleanup();
+        return ipp_internal_fail(e, IPP_ERR_NOMEM, "ipp_observe: staging allocation failed");
+    }
+    op.poses = d_poses;
+    op.budgets = d_budget;
+    op.out = d_out;
+    observe_kernel<<<n_env, kObsThreads, 0, stream>>>(op);
+    ipp_internal_count_launches(e, 1);
+    if (!out_is_device) cudaMemcpyAsync(out, d_out, total * sizeof(float), cudaMemcpyDeviceToHost, stream);
+    const cudaError_t s = cudaStreamSynchronize(stream);
+    cleanup();
+    if (s != cudaSuccess || cudaGetLastError() != cudaSuccess) return ipp_internal_fail(e, IPP_ERR_CUDA, "ipp_observe: CUDA failure");
+    return IPP_OK;
+}

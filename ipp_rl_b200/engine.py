@@ -365,6 +365,20 @@ class BatchedEngine:
         self._ck(self._lib.ipp_rollout(self._h, n, h, _ptr(ei), _ptr(pa), _ptr(pp), _ptr(rewards), fl))
         return rewards
 
+    def observe(self, first_env: int = 0, n_env: Optional[int] = None, poses=None, budget_ratio=None, adaptive=False,
+                action_costs=True) -> np.ndarray:
+        """Network-input planes of the current belief, (n, C, y_dim, x_dim) fp32: the per-cell restriction of
+        ``generate_input_feature_planes`` (planning/common/features.py:83-151) for one history entry —
+        [variance / max, x, y, z position, budget ratio] (+ the action-cost plane)."""
+        n = self.batch - first_env if n_env is None else n_env
+        c = 6 if action_costs else 5
+        pp = None if poses is None else np.ascontiguousarray(np.broadcast_to(np.asarray(poses, np.float64), (n, 3)))
+        br = None if budget_ratio is None else np.ascontiguousarray(np.broadcast_to(np.asarray(budget_ratio, np.float32), (n,)))
+        out = np.empty((n, c, self.y_dim, self.x_dim), np.float32)
+        fl = (capi.FLAG_ADAPTIVE if adaptive else 0) | (capi.OBS_COSTS if action_costs else 0)
+        self._ck(self._lib.ipp_observe(self._h, first_env, n, _ptr(pp), _ptr(br), fl, _ptr(out), 0))
+        return out
+
     def eval(self) -> np.ndarray:
         out = np.empty((self.batch, capi.NUM_METRICS), np.float32)
         self._ck(self._lib.ipp_eval(self._h, _ptr(out)))
