@@ -149,49 +149,47 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
             const uint32_t tile = smem_u32(my_stages + (size_t)s * stage_bytes);
             if (TILED) {
                 // IPP_LAYOUT_TILED: same staging as the 16-byte row-major path below (lanes = RP row-segments of W
-                // chunks, rows advance by RP), only the source index differs: chunk (R, cc) of a plane with `tx` tiles
-                // per tile-row sits at float4 index ((R>>2)*tx + tile(cc))*8 + (R&3)*2 + half(cc); stepping R by RP
-                // adds 2*RP inside a tile and tx*8 + 2*(RP-4) across a tile boundary.
+                // chunks, rows advance by RP), only the source offset differs: chunk (R, cc) of a plane with `tx` tiles
+                // per tile-row sits at float4 index ((R>>2)*tx + tile(cc))*8 + (R&3)*2 + half(cc).  Stepping R by
+                // RP = 2 alternates between "+4" (inside a tile) and "+tx*8 - 4" (into the tile below); RP = 4 always adds
+                // tx*8: one add and one xor per row (step ^= step_a ^ step_b).  RP = 1 (footprints wider than 31 cells)
+                // takes the generic stride.
                 const int ox = xl & 1, oxg = xl & 3;
                 const int cm = (ox + nx + 1) >> 1, cg = (oxg + nx + 3) >> 2;  // 16 B chunks per row
-                {
-                    const int W = cm <= 8 ? 8 : (cm <= 16 ? 16 : 32), RP = 32 / W;
-                    const int lr = lane / W, lc = lane - lr * W;
-                    const int wrap = p.txm * 8 + 2 * (RP - 4);
-                    const float4 *plane = reinterpret_cast<const float4 *>(mv_base + (size_t)IPP_ENV_OF(job) * p.plane);
-                    for (int c0 = lc; c0 < cm; c0 += 32) {
-                        const int cc = xl - ox + 2 * c0;  // first cell of the chunk (even)
-                        int R = yu + lr;
-                        const float4 *src = plane + (size_t)(((R >> 2) * p.txm + (cc >> 2)) * 8 + (R & 3) * 2 + ((cc >> 1) & 1));
-                        uint32_t dst = tile + 16u * (uint32_t)(lr * cm + c0);
-#pragma unroll 2
+                auto stage = [&](const unsigned char *plane, int tx, int cw, int cc_first, int cc_step, int tile_shift, uint32_t dst0) {
+                    const int sh = cw <= 8 ? 3 : (cw <= 16 ? 4 : 5);  // W = 1 << sh lanes per row
+                    const int RP = 32 >> sh;
+                    const int lr = lane >> sh, lc = lane & ((1 << sh) - 1);
+                    if (lc >= cw) return;
+                    const int cc = cc_first + cc_step * lc;
+                    int R = yu + lr;
+                    uint32_t off = 16u * (uint32_t)(((R >> 2) * tx + (cc >> tile_shift)) * 8 + (R & 3) * 2 + ((cc >> (tile_shift - 1)) & 1));
+                    uint32_t dst = dst0 + 16u * (uint32_t)(lr * cw + lc);
+                    const uint32_t dstep = 16u * (uint32_t)(RP * cw);
+                    if (RP >= 2) {
+                        const uint32_t in_tile = 32u * (uint32_t)RP, cross = 16u * (uint32_t)(tx * 8) - 32u * (uint32_t)(4 - RP);
+                        uint32_t step = ((R & 3) + RP >= 4) ? cross : in_tile;
+                        const uint32_t flip = RP == 4 ? 0u : (in_tile ^ cross);
+#pragma unroll 1
                         for (int r = lr; r < ny; r += RP) {
-                            cp_async_16(dst, src);
-                            src += ((R & 3) + RP >= 4) ? wrap : 2 * RP;
-                            R += RP;
-                            dst += 16u * (uint32_t)(RP * cm);
+                            cp_async_16(dst, plane + off);
+                            off += step;
+                            step ^= flip;
+                            dst += dstep;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int r = lr; r < ny; ++r) {
+                            cp_async_16(dst, plane + off);
+                            off += ((R & 3) == 3) ? 16u * (uint32_t)(tx * 8) - 96u : 32u;
+                            ++R;
+                            dst += dstep;
                         }
                     }
-                }
-                {
-                    const int W = cg <= 8 ? 8 : (cg <= 16 ? 16 : 32), RP = 32 / W;
-                    const int lr = lane / W, lc = lane - lr * W;
-                    const int wrap = p.txg * 8 + 2 * (RP - 4);
-                    const float4 *plane = reinterpret_cast<const float4 *>(p.gt + (size_t)IPP_ENV_OF(job) * p.plane_gt);
-                    for (int c0 = lc; c0 < cg; c0 += 32) {
-                        const int cc = xl - oxg + 4 * c0;  // first cell of the chunk (multiple of 4)
-                        int R = yu + lr;
-                        const float4 *src = plane + (size_t)(((R >> 2) * p.txg + (cc >> 3)) * 8 + (R & 3) * 2 + ((cc >> 2) & 1));
-                        uint32_t dst = tile + (uint32_t)ap.mv_tile_bytes + 16u * (uint32_t)(lr * cg + c0);
-#pragma unroll 2
-                        for (int r = lr; r < ny; r += RP) {
-                            cp_async_16(dst, src);
-                            src += ((R & 3) + RP >= 4) ? wrap : 2 * RP;
-                            R += RP;
-                            dst += 16u * (uint32_t)(RP * cg);
-                        }
-                    }
-                }
+                };
+                stage(reinterpret_cast<const unsigned char *>(mv_base + (size_t)IPP_ENV_OF(job) * p.plane), p.txm, cm, xl - ox, 2, 2, tile);
+                stage(reinterpret_cast<const unsigned char *>(p.gt + (size_t)IPP_ENV_OF(job) * p.plane_gt), p.txg, cg, xl - oxg, 4, 3,
+                      tile + (uint32_t)ap.mv_tile_bytes);
             } else if (ap.vec16) {
                 // 16-byte copies that bypass L1 (cp.async.cg): every row is fetched as the 16-byte aligned
                 // superset of its footprint segment — the same 32 B sectors, a quarter of the copy instructions,
