@@ -9,9 +9,13 @@
 //   mcts_expand_kernel   mask + normalise the leaf's priors (mcts.py:196-237), back the value up
 //                        (mcts.py:248-265)
 //
-// Tree storage per tree: `max_nodes` nodes x W window slots (candidate actions = lattice cells
-// within max_valid_action_distance of the node, all altitude levels): prior P (float, -1 = invalid
-// action), Q (float), {child index, visit count} (2 x uint16) = 12 B per slot, plus a 16 B node header.
+// Tree storage per tree: `max_nodes` nodes, each with a 16 B header, the dense prior over its W window slots
+// (candidate actions = lattice cells within max_valid_action_distance of the node, all altitude levels;
+// -1 = invalid action, -2 = already an edge) and its best not-yet-visited slot; plus a pool of at most
+// num_simulations EDGES {parent node, slot, prior, Q, N, child} (a simulation adds at most one).  An unvisited
+// action has Q = N = 0, so among them the arg max of the PUCT score is the arg max of the prior: a descent
+// step compares the node's visited children (a scan of the small edge pool) with that one cached candidate
+// instead of scanning W (~1 900) slots; the prior array is rescanned only at the node that grows a new edge.
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -27,26 +31,35 @@ using namespace ipp;
 
 namespace {
 
-constexpr uint32_t kNoChild = 0xFFFFu;
 constexpr int kTreeWarps = 4;  // trees per CTA
 
 struct TreeDims {
     int T, M, W, D, r, L, H;  // trees, nodes per tree, window slots, window width, radius, levels, episode horizon
+    int E;                    // edge-pool capacity per tree
     int max_path;             // H + 1
     int first_env;
     float c_init, c_base, gamma, forced_k, max_dist, dir_eps;
 };
 
+struct __align__(16) Edge {
+    int parent, slot;
+    float prior, q;
+    int n, child;
+    int pad[2];
+};
+static_assert(sizeof(Edge) == 32, "Edge layout");
+constexpr int kNoNode = -1;
+
 struct TreeArrays {
     int4 *hdr;       // [T][M]  {packed position, budget bits, Ns, depth | expanded << 8}
-    float *P;        // [T][M][W]
-    float *Q;        // [T][M][W]
-    uint32_t *NC;    // [T][M][W]  child << 16 | visits
+    float *P;        // [T][M][W]  masked normalised priors; -1 invalid, -2 visited (prior moved into the edge)
+    int2 *bu;        // [T][M]  best unvisited slot of the node {slot (-1: none), prior bits}
+    Edge *edges;     // [T][E]
+    int *n_edges;    // [T]
     int *n_nodes;    // [T]
     double *root_pose;  // [T][3]
     // per-simulation scratch
-    int *path_node;    // [T][max_path]
-    int *path_slot;    // [T][max_path]
+    int *path_edge;    // [T][max_path]
     int *path_action;  // [T][max_path]  (-1 padded)
     float *path_reward;  // [T][max_path]
     int *leaf;           // [T][IPP_MCTS_LEAF_WORDS]
@@ -120,13 +133,14 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             kind = IPP_MCTS_LEAF_EVAL;
             break;
         }
-        const size_t base = ((size_t)t * d.M + node) * d.W;
-        const float *P = a.P + base, *Q = a.Q + base;
-        uint32_t *NC = a.NC + base;
-        // normalize_q_values (mcts.py:267-278) over the dense action vector: unvisited and out-of-window actions are 0
+        float *P = a.P + ((size_t)t * d.M + node) * d.W;
+        Edge *edges = a.edges + (size_t)t * d.E;
+        const int ne = a.n_edges[t];
+        // normalize_q_values (mcts.py:267-278) over the dense action vector: every action that is not an edge has Q = 0
         float qmin = 0.0f, qmax = 0.0f;
-        for (int s = lane; s < d.W; s += 32) {
-            const float q = Q[s];
+        for (int e = lane; e < ne; e += 32) {
+            if (edges[e].parent != node) continue;
+            const float q = edges[e].q;
             qmin = fminf(qmin, q);
             qmax = fmaxf(qmax, q);
         }
@@ -136,31 +150,78 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
         }
         const float qscale = qmax > qmin ? 1.0f / (qmax - qmin) : 0.0f;  // all zero -> values unchanged (= 0)
-        // compute_uct (mcts.py:280-296)
+        // compute_uct (mcts.py:280-296): the node's edges, then its best unvisited action (Q = N = 0)
         const float prior_c = d.c_init + logf(((float)Ns + d.c_base + 1.0f) / d.c_base);
         const float sq = sqrtf((float)Ns + 1.0f);
         const bool force = depth == 0;
         float best = -INFINITY;
-        int best_s = 0x7fffffff;
-        for (int s = lane; s < d.W; s += 32) {
-            const float pr = P[s];
-            if (pr < 0.0f) continue;  // ~Vs -> -inf
-            const float n = (float)(NC[s] & 0xFFFFu);
-            float u = (Q[s] - qmin) * qscale + prior_c * pr * (sq / (1.0f + n));
-            if (force && n > 0.0f && n < ceilf(sqrtf(d.forced_k * pr * (float)Ns))) u = INFINITY;
-            if (u > best) {
+        int best_s = 0x7fffffff, best_e = -1;
+        for (int e = lane; e < ne; e += 32) {
+            const Edge ed = edges[e];
+            if (ed.parent != node) continue;
+            const float n = (float)ed.n;
+            float u = (ed.q - qmin) * qscale + prior_c * ed.prior * (sq / (1.0f + n));
+            if (force && n > 0.0f && n < ceilf(sqrtf(d.forced_k * ed.prior * (float)Ns))) u = INFINITY;
+            if (u > best || (u == best && ed.slot < best_s)) {
                 best = u;
-                best_s = s;
+                best_s = ed.slot;
+                best_e = e;
+            }
+        }
+        const int2 bu = a.bu[(size_t)t * d.M + node];
+        if (lane == 0 && bu.x >= 0) {
+            const float u = (0.0f - qmin) * qscale + prior_c * __int_as_float(bu.y) * sq;
+            if (u > best || (u == best && bu.x < best_s)) {
+                best = u;
+                best_s = bu.x;
+                best_e = -1;
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ob = __shfl_xor_sync(0xffffffffu, best, o);
             const int os = __shfl_xor_sync(0xffffffffu, best_s, o);
+            const int oe = __shfl_xor_sync(0xffffffffu, best_e, o);
             if (ob > best || (ob == best && os < best_s)) {
                 best = ob;
                 best_s = os;
+                best_e = oe;
             }
+        }
+        int child = kNoNode;
+        if (best_e < 0) {
+            // a new edge: move the slot's prior into the pool and find the node's next best unvisited action
+            best_e = ne;
+            if (lane == 0) {
+                Edge ed;
+                ed.parent = node, ed.slot = best_s, ed.prior = __int_as_float(bu.y), ed.q = 0.0f, ed.n = 0, ed.child = kNoNode;
+                ed.pad[0] = ed.pad[1] = 0;
+                edges[ne] = ed;
+                a.n_edges[t] = ne + 1;
+                P[best_s] = -2.0f;
+            }
+            __syncwarp();
+            float bp = -1.0f;
+            int bs = 0x7fffffff;
+            for (int s = lane; s < d.W; s += 32) {
+                const float pr = P[s];
+                if (pr >= 0.0f && pr > bp) {  // strict: the lowest slot among equal priors stays
+                    bp = pr;
+                    bs = s;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float op = __shfl_xor_sync(0xffffffffu, bp, o);
+                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                if (op > bp || (op == bp && os < bs)) {
+                    bp = op;
+                    bs = os;
+                }
+            }
+            if (lane == 0) a.bu[(size_t)t * d.M + node] = make_int2(bp >= 0.0f ? bs : -1, __float_as_int(bp));
+        } else {
+            child = edges[best_e].child;
         }
         // the chosen edge
         const Slot c = slot_cell(d, p, best_s, ccol, crow);
@@ -170,13 +231,11 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
         const float cost = job_cost(p, ax, ay, ah, nx, ny, nh);
         const float child_budget = budget - cost;  // mcts.py:247
         if (lane == 0) {
-            a.path_node[(size_t)t * d.max_path + len] = node;
-            a.path_slot[(size_t)t * d.max_path + len] = best_s;
+            a.path_edge[(size_t)t * d.max_path + len] = best_e;
             a.path_action[(size_t)t * d.max_path + len] = c.lvl * (p.X * p.Y) + p.X * c.col + c.row;
         }
         ++len;
-        const uint32_t child = NC[best_s] >> 16;
-        if (child == kNoChild) {
+        if (child == kNoNode) {
             const int n_nodes = a.n_nodes[t];
             if (depth + 1 > d.H || !(child_budget > 0.0f) || n_nodes >= d.M) {
                 kind = IPP_MCTS_LEAF_TERMINAL;  // simulate() returns 0 before any node exists (mcts.py:175-176)
@@ -188,7 +247,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             }
             if (lane == 0) {
                 hdr[n_nodes] = make_int4(pack_pos(c.col, c.row, c.lvl), __float_as_int(child_budget), 0, depth + 1);
-                NC[best_s] = ((uint32_t)n_nodes << 16) | (NC[best_s] & 0xFFFFu);
+                a.bu[(size_t)t * d.M + n_nodes] = make_int2(-1, 0);
+                edges[best_e].child = n_nodes;
                 a.n_nodes[t] = n_nodes + 1;
             }
             __syncwarp();
@@ -199,7 +259,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             kind = IPP_MCTS_LEAF_EVAL;
             break;
         }
-        node = (int)child;
+        node = child;
     }
     if (lane == 0) {
         for (int k = len; k < d.max_path; ++k) a.path_action[(size_t)t * d.max_path + k] = -1;
@@ -235,9 +295,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
         const float budget = __int_as_float(h.y);
         double nx, ny, nh;
         node_pose(p, a, t, node, ccol, crow, lvl, nx, ny, nh);
-        const size_t base = ((size_t)t * d.M + node) * d.W;
-        float *P = a.P + base, *Q = a.Q + base;
-        uint32_t *NC = a.NC + base;
+        float *P = a.P + ((size_t)t * d.M + node) * d.W;
         const bool noisy = node == 0 && root_noise != nullptr && d.dir_eps > 0.0f;
         // get_next_actions_mask (mcts.py:148-158) and policy * mask (mcts.py:220)
         float sum = 0.0f;
@@ -262,8 +320,6 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
                 }
             }
             P[s] = pr;
-            Q[s] = 0.0f;
-            NC[s] = kNoChild << 16;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -277,11 +333,31 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
             const float total = noisy ? sum + d.dir_eps : sum;
             const float scale = total > 0.0f ? 1.0f / total : 0.0f;
             const float uniform = 1.0f / (float)n_valid;
+            float bp = -1.0f;  // best (largest prior, lowest slot) action: the node's first unvisited candidate
+            int bs = 0x7fffffff;
             for (int s = lane; s < d.W; s += 32) {
-                const float pr = P[s];
-                if (pr >= 0.0f) P[s] = total > 0.0f ? pr * scale : uniform;
+                float pr = P[s];
+                if (pr < 0.0f) continue;
+                pr = total > 0.0f ? pr * scale : uniform;
+                P[s] = pr;
+                if (pr > bp) {
+                    bp = pr;
+                    bs = s;
+                }
             }
-            if (lane == 0) hdr[node] = make_int4(h.x, h.y, 0, (h.w & 0xFF) | (1 << 8));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float op = __shfl_xor_sync(0xffffffffu, bp, o);
+                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                if (op > bp || (op == bp && os < bs)) {
+                    bp = op;
+                    bs = os;
+                }
+            }
+            if (lane == 0) {
+                hdr[node] = make_int4(h.x, h.y, 0, (h.w & 0xFF) | (1 << 8));
+                a.bu[(size_t)t * d.M + node] = make_int2(bs, __float_as_int(bp));
+            }
             value = values ? values[t] : 0.0f;
         }
     }
@@ -289,13 +365,11 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
     if (lane == 0) {
         for (int k = len - 1; k >= 0; --k) {
             value = a.path_reward[(size_t)t * d.max_path + k] + d.gamma * value;
-            const int n = a.path_node[(size_t)t * d.max_path + k], s = a.path_slot[(size_t)t * d.max_path + k];
-            const size_t i = ((size_t)t * d.M + n) * d.W + s;
-            const uint32_t nc = a.NC[i];
-            const uint32_t visits = nc & 0xFFFFu;
-            a.Q[i] = visits > 0 ? ((float)visits * a.Q[i] + value) / (float)(visits + 1) : value;
-            a.NC[i] = (nc & 0xFFFF0000u) | min(visits + 1u, 0xFFFFu);
-            hdr[n].z += 1;
+            Edge *ed = a.edges + (size_t)t * d.E + a.path_edge[(size_t)t * d.max_path + k];
+            const int visits = ed->n;
+            ed->q = visits > 0 ? ((float)visits * ed->q + value) / (float)(visits + 1) : value;
+            ed->n = visits + 1;
+            hdr[ed->parent].z += 1;
         }
     }
 }
@@ -306,26 +380,40 @@ __global__ void mcts_begin_kernel(TreeDims d, TreeArrays a, const StepParams p, 
     const double x = a.root_pose[3 * t], y = a.root_pose[3 * t + 1];
     const int col = clampi((int)floor(__ddiv_rn(x, p.res)), 0, p.X - 1), row = clampi((int)floor(__ddiv_rn(y, p.res)), 0, p.Y - 1);
     a.hdr[(size_t)t * d.M] = make_int4(pack_pos(col, row, -1), __float_as_int(budgets[t]), 0, 0);
+    a.bu[(size_t)t * d.M] = make_int2(-1, 0);
     a.n_nodes[t] = 1;
+    a.n_edges[t] = 0;
 }
 
+// dense root statistics from the prior array and the root's edges: one CTA per tree
 __global__ void mcts_root_export_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a, float *ps, float *qsa, int *nsa, int *ids,
                                         int *ns) {
-    const int t = blockIdx.y;
+    const int t = blockIdx.x;
     const int4 h = a.hdr[(size_t)t * d.M];
     int ccol, crow, lvl;
     unpack_pos(h.x, ccol, crow, lvl);
     const bool expanded = ((h.w >> 8) & 1) != 0;
     const size_t base = (size_t)t * d.M * d.W;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.W; s += gridDim.x * blockDim.x) {
+    for (int s = threadIdx.x; s < d.W; s += blockDim.x) {
         const Slot c = slot_cell(d, p, s, ccol, crow);
         const size_t o = (size_t)t * d.W + s;
         if (ps) ps[o] = expanded ? a.P[base + s] : -1.0f;
-        if (qsa) qsa[o] = expanded ? a.Q[base + s] : 0.0f;
-        if (nsa) nsa[o] = expanded ? (int)(a.NC[base + s] & 0xFFFFu) : 0;
+        if (qsa) qsa[o] = 0.0f;
+        if (nsa) nsa[o] = 0;
         if (ids) ids[o] = c.in_grid ? c.lvl * (p.X * p.Y) + p.X * c.col + c.row : -1;
     }
-    if (ns && blockIdx.x == 0 && threadIdx.x == 0) ns[t] = h.z;
+    __syncthreads();
+    const Edge *edges = a.edges + (size_t)t * d.E;
+    const int ne = a.n_edges[t];
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+        const Edge ed = edges[e];
+        if (ed.parent != 0) continue;
+        const size_t o = (size_t)t * d.W + ed.slot;
+        if (ps) ps[o] = ed.prior;
+        if (qsa) qsa[o] = ed.q;
+        if (nsa) nsa[o] = ed.n;
+    }
+    if (ns && threadIdx.x == 0) ns[t] = h.z;
 }
 
 __global__ void iota_kernel(int *out, int n, int first) {
@@ -415,6 +503,7 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
     TreeDims &d = m->d;
     d.T = cfg->n_trees;
     d.M = cfg->num_simulations + 1;
+    d.E = cfg->num_simulations;
     d.L = info.num_altitude_levels;
     d.r = (int)std::floor(cfg->max_valid_action_distance / m->sp.res) + 1;
     d.D = 2 * d.r + 1;
@@ -437,9 +526,10 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
     const size_t TM = (size_t)d.T * d.M, TMW = TM * d.W, TP = (size_t)d.T * d.max_path;
     int rc;
     TreeArrays &a = m->a;
-    if ((rc = malloc_dev(m, &a.hdr, TM)) || (rc = malloc_dev(m, &a.P, TMW)) || (rc = malloc_dev(m, &a.Q, TMW)) || (rc = malloc_dev(m, &a.NC, TMW)) ||
+    if ((rc = malloc_dev(m, &a.hdr, TM)) || (rc = malloc_dev(m, &a.P, TMW)) || (rc = malloc_dev(m, &a.bu, TM)) ||
+        (rc = malloc_dev(m, &a.edges, (size_t)d.T * d.E)) || (rc = malloc_dev(m, &a.n_edges, (size_t)d.T)) ||
         (rc = malloc_dev(m, &a.n_nodes, (size_t)d.T)) || (rc = malloc_dev(m, &a.root_pose, 3 * (size_t)d.T)) ||
-        (rc = malloc_dev(m, &a.path_node, TP)) || (rc = malloc_dev(m, &a.path_slot, TP)) || (rc = malloc_dev(m, &a.path_action, TP)) ||
+        (rc = malloc_dev(m, &a.path_edge, TP)) || (rc = malloc_dev(m, &a.path_action, TP)) ||
         (rc = malloc_dev(m, &a.path_reward, TP)) || (rc = malloc_dev(m, &a.leaf, (size_t)d.T * IPP_MCTS_LEAF_WORDS)) ||
         (rc = malloc_dev(m, &m->d_env_index, (size_t)d.T)) || (rc = malloc_dev(m, &m->d_budgets, (size_t)d.T)))
         return bail(rc);
@@ -578,9 +668,7 @@ extern "C" int ipp_mcts_root_stats(ipp_mcts *m, float *ps, float *qsa, int32_t *
         if (!m->d_out_f[k] && (rc = malloc_dev(m, &m->d_out_f[k], TW)) != IPP_OK) return rc;
     for (int k = 0; k < 3; ++k)
         if (!m->d_out_i[k] && (rc = malloc_dev(m, &m->d_out_i[k], k == 2 ? (size_t)d.T : TW)) != IPP_OK) return rc;
-    dim3 grid((unsigned)std::min(8, (d.W + 255) / 256), (unsigned)d.T);
-    if (d.T > 65535) return mfail(m, IPP_ERR_UNSUPPORTED, "ipp_mcts_root_stats: more than 65535 trees per call");
-    mcts_root_export_kernel<<<grid, 256, 0, m->stream>>>(m->sp, d, m->a, m->d_out_f[0], m->d_out_f[1], m->d_out_i[0], m->d_out_i[1], m->d_out_i[2]);
+    mcts_root_export_kernel<<<d.T, 256, 0, m->stream>>>(m->sp, d, m->a, m->d_out_f[0], m->d_out_f[1], m->d_out_i[0], m->d_out_i[1], m->d_out_i[2]);
     m->launches++;
     MCU(m, cudaGetLastError());
     if (ps) MCU(m, cudaMemcpyAsync(ps, m->d_out_f[0], TW * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
