@@ -1,12 +1,17 @@
 #!/bin/bash
-# Evidence for profiles/: launch list of the bench command, DRAM traffic of the step kernel at the full batch, DRAM probe.
+# Evidence for profiles/: launch list of the bench command, DRAM traffic of the step kernel at the full batch (both layouts),
+# one full ncu capture of the step kernel (default layout), DRAM probe.   usage (under gpurun): bash tools/gpu_profiles.sh TAG
+TAG=${1:-r01}
 O=gpurun_out
 mkdir -p $O
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r01_launches.csv \
-  python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 2 --mcts-sims 8 > $O/r01_launches_bench.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches.csv \
+  python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 2 --mcts-sims 8 > $O/${TAG}_launches_bench.log 2>&1
 for L in mv tiled; do
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:ipp_step_async -s 8 -c 4 --csv \
-  --log-file $O/r01_traffic_$L.csv python bench.py --steps 12 --warmup 3 --no-cpu-baseline --e2e-steps 2 --mcts-trees 0 --layout $L > $O/r01_traffic_bench_$L.log 2>&1
+  --log-file $O/${TAG}_traffic_$L.csv python bench.py --steps 12 --warmup 3 --no-cpu-baseline --e2e-steps 2 --mcts-trees 0 --layout $L > $O/${TAG}_traffic_bench_$L.log 2>&1
 done
-timeout 300 build/dram_probe2 24 32 > $O/r01_dram_probe2.txt 2>&1
-ls -la $O
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ipp_step_async -s 6 -c 1 -f -o $O/${TAG}_async_tiled \
+  python bench.py --steps 8 --warmup 3 --batch 16384 --no-cpu-baseline --e2e-steps 2 --mcts-trees 0 --layout tiled > $O/${TAG}_ncu_bench.log 2>&1
+timeout 300 build/dram_probe2 24 32 > $O/${TAG}_dram_probe2.txt 2>&1
+python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; cat $O/${TAG}_bench.json
+ls -la $O | tail -12
