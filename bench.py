@@ -212,6 +212,9 @@ def run_ours(args, rank, world, local_rank):
         out_pinned = torch.empty(world * B if dist is not None else B, dtype=torch.float32).pin_memory()
         ids_np, out_np = ids_pinned.numpy(), out_pinned.numpy()
         eng.reset(PRIOR_MEAN, PRIOR_VAR)
+        if args.zero_copy is not None:
+            eng.set_zero_copy(rewards="r" in args.zero_copy, ids="i" in args.zero_copy)
+        zc0 = eng.zero_copy_steps
 
         def e2e_step(t):
             if dist is None:
@@ -238,6 +241,7 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
         launches_e2e = eng.launches - launches_e2e0
+        zero_copy_steps = eng.zero_copy_steps - zc0
         assert np.isfinite(out_np).all()
 
     # ---- secondary leg (BASELINE.json configs[3], "C4"): mcts_zero rollouts on the same beliefs.  Lock-step search over
@@ -327,7 +331,9 @@ def run_ours(args, rank, world, local_rank):
                          "mean_cells_per_env_step": cells_timed_total / (B * K), "kernel": "ipp_step_async_kernel" if eng.step_path == "async" else "ipp_step_kernel<MV, KALMAN>", "step_path": eng.step_path},
             "e2e": {"value": world * B * KE / e2e_s, "steps": KE, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * B * world,
                     "d2h_bytes_per_step": 4 * B * world * (world if dist is not None else 1),
-                    "path": "BatchedEngine.step (ipp_step: pinned host ids -> H2D -> fused kernel -> D2H rewards)" if dist is None else
+                    "path": ("BatchedEngine.step (ipp_step: pinned host ids -> H2D -> fused kernel -> "
+                             + ("rewards written by the kernel into the caller's pinned buffer [zero-copy D2H, 4 B/env over PCIe])"
+                                if zero_copy_steps > 0 else "D2H rewards)")) if dist is None else
                             "pinned host ids -> H2D -> ipp_step_device -> NCCL all_gather(rewards) -> D2H"},
             "gpu_launches": int(results["entropy"]["launches"]),
             "gpu_launches_e2e": int(launches_e2e),
@@ -354,6 +360,8 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=4096, help="env sample of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=500, help="steps of the host-buffer (e2e) leg (<= --steps)")
+    ap.add_argument("--zero-copy", default=None, choices=["", "r", "i", "ri"],
+                    help="e2e leg: host buffers the kernel accesses in place (r = rewards, i = action ids); default = the engine's (r)")
     ap.add_argument("--mcts-trees", type=int, default=4096, help="trees of the secondary mcts_zero rollout leg (0 = skip)")
     ap.add_argument("--mcts-sims", type=int, default=32)
     ap.add_argument("--max-altitude", type=float, default=None, help="experiments only: override the top altitude of the action set")

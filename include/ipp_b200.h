@@ -262,6 +262,16 @@ void *ipp_device_ptr(ipp_engine *e, int32_t which);
 #define IPP_OPT_STEP_PATH 1
 #define IPP_OPT_LAUNCHES_LSU 2
 #define IPP_OPT_LAUNCHES_ASYNC 3
+/* IPP_OPT_ZERO_COPY: bit mask of the ipp_step host buffers that the kernel accesses IN PLACE when the caller
+ * passes page-locked, mapped host memory (ipp_host_alloc, cudaHostAlloc/cudaHostRegister, torch pin_memory):
+ * rewards are then written by the fused kernel straight into the caller's buffer (4 B per env over PCIe, inside
+ * the kernel) and action ids are read from it, instead of separate stream copies around the launch.  Pageable
+ * buffers always take the copy path.  Default IPP_ZERO_COPY_REWARDS; env IPP_ZERO_COPY="" | "r" | "i" | "ri".
+ * IPP_OPT_ZERO_COPY_STEPS (read only) counts the steps whose rewards went out that way. */
+#define IPP_ZERO_COPY_REWARDS 1
+#define IPP_ZERO_COPY_IDS 2
+#define IPP_OPT_ZERO_COPY 4
+#define IPP_OPT_ZERO_COPY_STEPS 5
 int ipp_set_option(ipp_engine *e, int32_t option, int64_t value);
 int64_t ipp_get_option(const ipp_engine *e, int32_t option);
 

@@ -36,7 +36,7 @@ struct ipp_engine {
     float *d_var = nullptr;   // PLANES only
     float *d_gt = nullptr;
     double *d_prev = nullptr;  // [B][3]
-    int *d_status = nullptr;
+    int *d_status = nullptr;  // device alias of h_status (mapped pinned host word: no copy needed to read it back)
     // staging for the host entry points
     int32_t *d_actions = nullptr;  // [cap_jobs]
     double *d_poses = nullptr;     // [cap_jobs][3]
@@ -50,7 +50,9 @@ struct ipp_engine {
     float *d_metrics = nullptr;
     float *d_scratch = nullptr;  // dense [n][plane] staging for MV get/set
     size_t cap_scratch = 0;
-    int *h_status = nullptr;  // pinned
+    int *h_status = nullptr;  // pinned + mapped
+    int zero_copy = IPP_ZERO_COPY_REWARDS;  // IPP_OPT_ZERO_COPY / env IPP_ZERO_COPY
+    uint64_t zero_copy_steps = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // cp.async-staged persistent path (step_async.cuh) and the path switch
@@ -588,12 +590,18 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         cudaMemsetAsync(e->d_mean, 0, 2 * cells * sizeof(float), e->stream);
     }
     if ((rc = dev_alloc(e, &e->d_prev, 3 * (size_t)cfg->batch)) != IPP_OK) return bail(rc);
-    if ((rc = dev_alloc(e, &e->d_status, 1)) != IPP_OK) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_metrics, (size_t)cfg->batch * IPP_NUM_METRICS)) != IPP_OK) return bail(rc);
-    s = cudaMemsetAsync(e->d_status, 0, sizeof(int), e->stream);
-    if (s == cudaSuccess) s = cudaHostAlloc((void **)&e->h_status, sizeof(int), cudaHostAllocDefault);
+    // status word: mapped pinned host memory, written by the kernels only on the (rare) error path, read by the
+    // host after a stream synchronisation without a device->host copy
+    s = cudaHostAlloc((void **)&e->h_status, sizeof(int), cudaHostAllocMapped);
+    if (s == cudaSuccess) s = cudaHostGetDevicePointer((void **)&e->d_status, e->h_status, 0);
     if (s != cudaSuccess) return bail(fail(e, IPP_ERR_CUDA, "status init: %s", cudaGetErrorString(s)));
     *e->h_status = 0;
+    if (const char *zc = getenv("IPP_ZERO_COPY")) {
+        e->zero_copy = 0;
+        if (strchr(zc, 'r')) e->zero_copy |= IPP_ZERO_COPY_REWARDS;
+        if (strchr(zc, 'i')) e->zero_copy |= IPP_ZERO_COPY_IDS;
+    }
     if ((rc = setup_async(e)) != IPP_OK) return bail(rc);
     if (const char *sp = getenv("IPP_STEP_PATH")) {
         if (!strcmp(sp, "lsu")) e->step_path = IPP_PATH_LSU;
@@ -606,7 +614,7 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
 extern "C" void ipp_destroy(ipp_engine *e) {
     if (!e) return;
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *ptrs[] = {e->d_mean, e->d_var, e->d_gt, e->d_prev, e->d_status, e->d_actions, e->d_poses, e->d_prev_in, e->d_env_index,
+    void *ptrs[] = {e->d_mean, e->d_var, e->d_gt, e->d_prev, e->d_actions, e->d_poses, e->d_prev_in, e->d_env_index,
                     e->d_reward, e->d_noise, e->d_z, e->d_metrics, e->d_scratch, e->d_tickets, e->d_level_taps};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -652,12 +660,10 @@ static TiledDims tiled_dims(const ipp_engine *e) {
 }
 
 static int check_status(ipp_engine *e) {
-    // device status word -> host (after a synchronising copy)
-    CU(e, cudaMemcpyAsync(e->h_status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    // the status word lives in mapped host memory: visible here once the stream has drained
     CU(e, cudaStreamSynchronize(e->stream));
-    if (*e->h_status & 1) {
-        CU(e, cudaMemsetAsync(e->d_status, 0, sizeof(int), e->stream));
-        *e->h_status = 0;
+    if (*(volatile int *)e->h_status & 1) {
+        *(volatile int *)e->h_status = 0;
         return fail(e, IPP_ERR_UNSUPPORTED,
                     "footprint needs cv2 INTER_AREA with an up-sampling axis (non-square FoV/grid corner case); not supported");
     }
@@ -969,6 +975,20 @@ static int ensure_job_buffers(ipp_engine *e, size_t n) {
     return IPP_OK;
 }
 
+// Device alias of a caller's HOST buffer when it is page-locked and mapped (cudaHostAlloc / cudaHostRegister /
+// torch pin_memory under unified addressing), else NULL.  Lets the fused kernel read its action ids from and write
+// its rewards to the caller's buffer directly: the transfer rides inside the kernel (4 B per env each way) instead
+// of being two more stream operations around it.
+static void *mapped_alias(const void *host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 extern "C" int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise, int32_t noise_stride, float *reward,
                         float *measurements, uint32_t flags) {
     int rc = validate_step_args(e, action_ids, poses, "ipp_step");
@@ -977,7 +997,15 @@ extern "C" int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *
     if ((rc = ensure_job_buffers(e, B)) != IPP_OK) return rc;
     if ((noise || measurements) && noise_stride < e->max_meas)
         return fail(e, IPP_ERR_INVALID, "ipp_step: noise_stride %d < max_measurements %d", noise_stride, e->max_meas);
-    if (action_ids) CU(e, cudaMemcpyAsync(e->d_actions, action_ids, B * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    // zero-copy: mapped pinned caller buffers go to the kernel as they are (IPP_OPT_ZERO_COPY)
+    const int32_t *ids_dev = nullptr;
+    float *reward_dev = nullptr;
+    if (action_ids && (e->zero_copy & IPP_ZERO_COPY_IDS)) ids_dev = (const int32_t *)mapped_alias(action_ids);
+    if (reward && (e->zero_copy & IPP_ZERO_COPY_REWARDS)) reward_dev = (float *)mapped_alias(reward);
+    if (action_ids && !ids_dev) {
+        CU(e, cudaMemcpyAsync(e->d_actions, action_ids, B * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        ids_dev = e->d_actions;
+    }
     if (poses) CU(e, cudaMemcpyAsync(e->d_poses, poses, 3 * B * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     if (noise) {
         if ((rc = ensure(e, &e->d_noise, &e->cap_noise, B * (size_t)noise_stride)) != IPP_OK) return rc;
@@ -985,10 +1013,13 @@ extern "C" int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *
     }
     if (measurements)
         if ((rc = ensure(e, &e->d_z, &e->cap_z, B * (size_t)noise_stride)) != IPP_OK) return rc;
-    rc = ipp_step_device(e, action_ids ? e->d_actions : nullptr, poses ? e->d_poses : nullptr, noise ? e->d_noise : nullptr, noise_stride,
-                         e->d_reward, measurements ? e->d_z : nullptr, flags);
+    rc = ipp_step_device(e, ids_dev, poses ? e->d_poses : nullptr, noise ? e->d_noise : nullptr, noise_stride,
+                         reward_dev ? reward_dev : e->d_reward, measurements ? e->d_z : nullptr, flags);
     if (rc != IPP_OK) return rc;
-    if (reward) CU(e, cudaMemcpyAsync(reward, e->d_reward, B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (reward_dev)
+        e->zero_copy_steps++;
+    else if (reward)
+        CU(e, cudaMemcpyAsync(reward, e->d_reward, B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     if (measurements) CU(e, cudaMemcpyAsync(measurements, e->d_z, B * (size_t)noise_stride * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     return check_status(e);
 }
@@ -1203,6 +1234,11 @@ extern "C" int ipp_set_option(ipp_engine *e, int32_t option, int64_t value) {
             if (value < IPP_PATH_LSU || value > IPP_PATH_ASYNC) return fail(e, IPP_ERR_INVALID, "ipp_set_option: step path %lld unknown", (long long)value);
             e->step_path = (int)value;
             return IPP_OK;
+        case IPP_OPT_ZERO_COPY:
+            if (value < 0 || value > (IPP_ZERO_COPY_REWARDS | IPP_ZERO_COPY_IDS))
+                return fail(e, IPP_ERR_INVALID, "ipp_set_option: zero-copy mask %lld unknown", (long long)value);
+            e->zero_copy = (int)value;
+            return IPP_OK;
         default:
             return fail(e, IPP_ERR_INVALID, "ipp_set_option: unknown option %d", option);
     }
@@ -1214,6 +1250,8 @@ extern "C" int64_t ipp_get_option(const ipp_engine *e, int32_t option) {
         case IPP_OPT_STEP_PATH: return effective_path(e);
         case IPP_OPT_LAUNCHES_LSU: return (int64_t)e->path_launches[IPP_PATH_LSU];
         case IPP_OPT_LAUNCHES_ASYNC: return (int64_t)e->path_launches[IPP_PATH_ASYNC];
+        case IPP_OPT_ZERO_COPY: return e->zero_copy;
+        case IPP_OPT_ZERO_COPY_STEPS: return (int64_t)e->zero_copy_steps;
         default: return -1;
     }
 }

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four iterations
 
         if (unsupported) {
-            if (lane == 0) atomicOr(p.status, 1);
+            if (lane == 0) *(volatile int *)p.status = 1;  // mapped host word, bit 0 is the only bit
         } else {
 #pragma unroll 1
             for (int q = lane; q < nq; q += 32) {

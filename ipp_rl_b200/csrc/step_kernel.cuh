@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
     tapv.cols = s_taps[wib] + 3 * kTapCap;
     if (MODE != MODE_PREDICT && need_taps) {
         if (out_r > g.ny || out_c > g.nx) {
-            if (lane == 0) atomicOr(p.status, 1);
+            if (lane == 0) *(volatile int *)p.status = 1;  // mapped host word, bit 0 is the only bit
             return;
         }
         tap_mode = build_tap_tables<kTapCap>(s_taps[wib], lane, g.ny, g.nx, out_r, out_c);

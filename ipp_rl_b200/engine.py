@@ -200,6 +200,17 @@ class BatchedEngine:
     def path_launches(self, path: str) -> int:
         return int(self._lib.ipp_get_option(self._h, capi.OPT_LAUNCHES_LSU + self.PATHS[path]))
 
+    def set_zero_copy(self, rewards: bool = True, ids: bool = False) -> None:
+        """Which pinned+mapped host buffers of ``step`` the kernel accesses in place (no stream copies around the
+        launch): rewards written straight to the caller's buffer, action ids read from it.  Pageable buffers always
+        take the copy path."""
+        mask = (capi.ZERO_COPY_REWARDS if rewards else 0) | (capi.ZERO_COPY_IDS if ids else 0)
+        self._ck(self._lib.ipp_set_option(self._h, capi.OPT_ZERO_COPY, mask))
+
+    @property
+    def zero_copy_steps(self) -> int:
+        return int(self._lib.ipp_get_option(self._h, capi.OPT_ZERO_COPY_STEPS))
+
     # -- reset / world -------------------------------------------------------------------------
     def reset(self, prior_mean: float = 0.5, prior_var: float = 1.82, prior_var_per_env=None, init_pose=None) -> None:
         pv = None if prior_var_per_env is None else _f32(prior_var_per_env, (self.batch,))

@@ -298,3 +298,58 @@ def test_error_paths():
             eng.set_ground_truth(np.zeros((2, 5, 5), np.float32))
         with pytest.raises(IppError):
             eng.set_ground_truth(np.zeros((3, 12, 12), np.float32))
+
+
+def test_unsupported_footprint_is_reported_through_the_status_word():
+    """FoV 60 x 20 degrees at 14 m: 17 x 5 cells at rf = 2; with the reference's dsize swap cv2 would have to UP-sample the
+    5-cell axis to 9 (bilinear branch, not INTER_AREA) — the engine refuses (IPP_ERR_UNSUPPORTED), on both kernels, and
+    keeps working afterwards."""
+    from ipp_rl_b200 import IppError
+
+    params = make_params(40, 40, 1.0, 8, 14, 6, angle=(60.0, 20.0))
+    for layout in (0, 2):
+        with _engine(params, 4, layout=layout) as eng:
+            eng.reset()
+            eng.set_ground_truth(np.full((4, 40, 40), 0.5, np.float32))
+            ids_hi = np.full(4, 1600 + 40 * 20 + 20, np.int32)  # level 1 (14 m), centre cell
+            with pytest.raises(IppError):
+                eng.step(ids_hi)
+            ids_lo = np.full(4, 40 * 20 + 20, np.int32)  # level 0 (8 m, rf = 1): fine, and the status word was cleared
+            r = eng.step(ids_lo)
+            assert np.isfinite(r).all() and (r > 0).all()
+
+
+@pytest.mark.parametrize("layout", [1, 2])
+def test_zero_copy_host_buffers_are_bit_identical_to_the_copy_path(layout):
+    """ipp_step with pinned+mapped caller buffers (rewards written by the kernel in place, ids read in place) gives
+    the same bits as the staged-copy path with pageable buffers; the counter proves which path ran."""
+    import torch
+
+    params = make_params(64, 64, 1.0, 8, 20, 6)
+    B = 512
+    rng = np.random.RandomState(5)
+    gt = np.stack([smooth_field(rng, (64, 64)) for _ in range(8)]).astype(np.float32)[rng.randint(0, 8, B)]
+    results = {}
+    for mode in ("copy", "r", "ri"):
+        with _engine(params, B, layout=layout, seed=99) as eng:
+            eng.set_zero_copy(rewards="r" in mode, ids="i" in mode)
+            eng.reset()
+            eng.set_ground_truth(gt)
+            idrng = np.random.RandomState(17)
+            ids_pin = torch.empty(B, dtype=torch.int32).pin_memory()
+            out_pin = torch.empty(B, dtype=torch.float32).pin_memory()
+            rs = []
+            for t in range(4):
+                ids = idrng.randint(0, eng.num_actions, B).astype(np.int32)
+                if mode == "copy":
+                    rs.append(eng.step(ids).copy())  # pageable buffers
+                else:
+                    ids_pin.numpy()[:] = ids
+                    out_pin.numpy()[:] = np.nan
+                    eng.step(ids_pin.numpy(), out=out_pin.numpy())
+                    rs.append(out_pin.numpy().copy())
+            assert eng.zero_copy_steps == (0 if mode == "copy" else 4)
+            results[mode] = (np.stack(rs),) + eng.get_state()
+    for mode in ("r", "ri"):
+        for a, b in zip(results["copy"], results[mode]):
+            assert np.array_equal(a, b), mode
