@@ -3,7 +3,7 @@
  * ("experience format + inference batching").
  *
  * Replaces, for whole batches of envs at once, the reference's self-play data path
- *   EpisodeGenerator.execute value targets          planning/mcts_zero/episode_generators.py:159-169
+ *   EpisodeGenerator.execute value targets          planning/mcts_zero/episode_generators.py:158-164
  *   scale_value_target                               planning/common/rewards.py:34-35
  *   save_sample_to_disk (one bz2 pickle per sample)  planning/mcts_zero/episode_generators.py:186-192
  *   ReplayBuffer / ExperienceReplayBuffer /
@@ -49,7 +49,7 @@ void ipp_ring_destroy(ipp_ring *r);
 const char *ipp_ring_last_error(const ipp_ring *r);
 int ipp_ring_get_info(const ipp_ring *r, ipp_ring_info *out);
 
-/* Value targets of finished episodes (episode_generators.py:159-166), rewards[n_episodes][max_steps] row-major,
+/* Value targets of finished episodes (episode_generators.py:158-164), rewards[n_episodes][max_steps] row-major,
  * lengths[n_episodes] <= max_steps:
  *   values[e][i] = sqrt(1 + sum_{j=i}^{min(i+horizon, len)-1} gamma^j * rewards[e][j]) - 1
  * (the exponent is the ABSOLUTE step j as in the reference, :164; scaling = scale_value_target), 0 past the end;

@@ -136,6 +136,33 @@ class ipp_mcts_info(C.Structure):
     ]
 
 
+class ipp_ring_config(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_uint32),
+        ("device", C.c_int32),
+        ("capacity", C.c_int64),
+        ("channels", C.c_int32),
+        ("y_dim", C.c_int32),
+        ("x_dim", C.c_int32),
+        ("policy_slots", C.c_int32),
+        ("stream", C.c_void_p),
+    ]
+
+
+class ipp_ring_info(C.Structure):
+    _fields_ = [
+        ("capacity", C.c_int64),
+        ("size", C.c_int64),
+        ("head", C.c_int64),
+        ("pushed", C.c_uint64),
+        ("device_bytes", C.c_uint64),
+        ("launches", C.c_uint64),
+    ]
+
+
+(RING_PTR_OBS, RING_PTR_POLICY, RING_PTR_MASK, RING_PTR_VALUE, RING_PTR_REWARD, RING_PTR_PRIORITY, RING_PTR_LAST_INDICES,
+ RING_PTR_LAST_WEIGHTS, RING_PTR_STREAM) = range(9)
+
 MCTS_MAX_PATH = 8
 MCTS_LEAF_TERMINAL, MCTS_LEAF_EVAL = 0, 1
 MCTS_LEAF_WORDS = 8
@@ -186,6 +213,19 @@ SIGNATURES = {
     "ipp_mcts_simulate_end": (C.c_int, [_P, _P, _P, _P, _P, _I32]),
     "ipp_mcts_root_stats": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ipp_mcts_device_ptr": (_P, [_P, _I32]),
+    # include/ipp_experience.h
+    "ipp_ring_create": (C.c_int, [C.POINTER(ipp_ring_config), C.POINTER(_P)]),
+    "ipp_ring_destroy": (None, [_P]),
+    "ipp_ring_last_error": (C.c_char_p, [_P]),
+    "ipp_ring_get_info": (C.c_int, [_P, C.POINTER(ipp_ring_info)]),
+    "ipp_ring_value_targets": (C.c_int, [_P, _P, _P, _I32, _I32, C.c_double, _I32, _P, _P, _I32]),
+    "ipp_ring_push": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _F32, _I32]),
+    "ipp_ring_reset_priorities": (C.c_int, [_P]),
+    "ipp_ring_sample": (C.c_int, [_P, _I32, C.c_double, C.c_double, _P, C.c_uint64, _P, _P, _I32]),
+    "ipp_ring_gather": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32]),
+    "ipp_ring_update_priorities": (C.c_int, [_P, _I32, _P, _P, _I32]),
+    "ipp_ring_get_priorities": (C.c_int, [_P, _P]),
+    "ipp_ring_device_ptr": (_P, [_P, _I32]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -8,12 +8,14 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libipp_b200.so")
-SOURCES = ["ipp_engine.cu", "mcts.cu", "grf.cu", "observe.cu"]
-HEADERS = ["step_kernel.cuh", "step_async.cuh", "quad_math.cuh", "rollout_kernel.cuh", "engine_internal.h", os.path.join("..", "..", "include", "ipp_mcts.h"), os.path.join("..", "..", "include", "ipp_b200.h")]
+SOURCES = ["ipp_engine.cu", "mcts.cu", "grf.cu", "observe.cu", "experience.cu"]
+HEADERS = ["step_kernel.cuh", "step_async.cuh", "quad_math.cuh", "rollout_kernel.cuh", "engine_internal.h", os.path.join("..", "..", "include", "ipp_mcts.h"), os.path.join("..", "..", "include", "ipp_b200.h"),
+           os.path.join("..", "..", "include", "ipp_experience.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-ldl",
+    "-diag-suppress", "128",  # "loop is not reachable" in constant-folded template instantiations
 ]
 
 

@@ -1,7 +1,7 @@
 // experience.cu — device-resident experience ring (include/ipp_experience.h), sm_100a.
 //
 // Reference data path replaced (all file:line into the reference tree):
-//   value targets            planning/mcts_zero/episode_generators.py:158-166, planning/common/rewards.py:34-35
+//   value targets            planning/mcts_zero/episode_generators.py:158-164, planning/common/rewards.py:34-35
 //   one bz2 pickle / sample  episode_generators.py:186-192  ->  rows of a ring in HBM (plain stream copies)
 //   uniform / prioritised sampling, importance weights, priority update   planning/mcts_zero/replay_buffers.py:83-141
 //   random-shift augmentation (ReplicationPad2d(4) + RandomCrop)          replay_buffers.py:58-77
@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cub/device/device_scan.cuh>
+#include <algorithm>
 #include <string>
 
 #include "../../include/ipp_experience.h"
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const double *__restrict__
             if (lo > size - 1) lo = size - 1;
         }
         idx_out[k] = lo;
-        if (weights) weights[k] = (float)wt;  // raw; normalised below
+        if (weights) weights[k] = 1.0f;  // uniform draw; the prioritised weights are normalised below
         my_max = fmax(my_max, wt);
     }
     for (int o = 16; o > 0; o >>= 1) my_max = fmax(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const double *__restrict__
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) mx = fmax(mx, s_max[k]);
     if (weights && cdf)
         for (int k = threadIdx.x; k < n; k += blockDim.x) {
-            // same thread wrote weights[k] above; recompute in fp64 for the reference's rounding (float32 of w / max)
+            // idx_out[k] was written by this very thread; fp64 ratio rounded once to float32 as in replay_buffers.py:132
             const int64_t i = idx_out[k];
             const double wt = pow((w[i] / total) * (double)size, -beta);
             weights[k] = (float)(wt / mx);
@@ -273,13 +274,18 @@ __global__ void gather_rows_kernel(const T *__restrict__ src, const int64_t *__r
     }
 }
 
+// priorities[idx[k]] = values[k]; of duplicate indices the LAST occurrence wins, as in NumPy's fancy assignment
+// (replay_buffers.py:141) — decided by a forward scan (n is a training batch).
 __global__ void scatter_priorities_kernel(float *prio, const int64_t *__restrict__ idx, const float *__restrict__ values, int n, int64_t size,
                                           float *running_max) {
     float m = 0.0f;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int64_t i = idx[k];
-        if (i >= 0 && i < size) {
-            prio[i] = values[k];  // duplicates: last writer wins, as NumPy fancy assignment leaves one of them
+        if (i < 0 || i >= size) continue;
+        bool last = true;
+        for (int j = k + 1; j < n && last; ++j) last = idx[j] != i;
+        if (last) {
+            prio[i] = values[k];
             m = fmaxf(m, values[k]);
         }
     }
@@ -298,7 +304,7 @@ static inline int blocks_for(size_t work, int cap = 148 * 8) {
 extern "C" int ipp_ring_create(const ipp_ring_config *cfg, ipp_ring **out) {
     if (!cfg || !out) return rfail(nullptr, IPP_ERR_INVALID, "ipp_ring_create: NULL argument");
     *out = nullptr;
-    if (cfg->struct_bytes != sizeof(ipp_ring_config)) return rfail(nullptr, IPP_ERR_ABI, "ipp_ring_create: struct_bytes mismatch");
+    if (cfg->struct_bytes != sizeof(ipp_ring_config)) return rfail(nullptr, IPP_ERR_INVALID, "ipp_ring_create: struct_bytes mismatch (header / library version skew)");
     if (cfg->capacity < 1 || cfg->channels < 1 || cfg->y_dim < 1 || cfg->x_dim < 1 || cfg->policy_slots < 1)
         return rfail(nullptr, IPP_ERR_INVALID, "ipp_ring_create: capacity, channels, dims and policy_slots must be >= 1");
     cudaError_t s = cudaSetDevice(cfg->device);

@@ -44,7 +44,18 @@ namespace ipp {
 #endif
 constexpr int kAsyncSlots = IPP_ASYNC_SLOTS;         // footprints in flight per warp
 constexpr int kAsyncMaxWarps = IPP_ASYNC_MAX_WARPS;  // warps per CTA (1 CTA / SM), further limited by shared memory
-constexpr int kTicketChunk = 8;                      // tickets taken per atomic
+#ifndef IPP_TICKET_CHUNK
+#define IPP_TICKET_CHUNK 8
+#endif
+#ifndef IPP_TICKET_GUIDE
+#define IPP_TICKET_GUIDE 4  // 0: fixed chunks of IPP_TICKET_CHUNK
+#endif
+#ifndef IPP_QUAD_UNROLL
+#define IPP_QUAD_UNROLL 1
+#endif
+#define IPP_PRAGMA_(x) _Pragma(#x)
+#define IPP_UNROLL(n) IPP_PRAGMA_(unroll n)
+constexpr int kTicketChunk = IPP_TICKET_CHUNK;       // tickets taken per atomic
 constexpr int kLevelTabs = 4;       // altitude levels whose interior tap tables are staged in smem
 constexpr int kTapFloats2 = 2 * kTapCap * 3;  // float2 per tap-table pair (rows + cols)
 
@@ -255,11 +266,15 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
     };
 
     // ---- prologue: one ticket chunk; fill every slot -----------------------------------------------
-    static_assert(kTicketChunk > kAsyncSlots, "the first chunk must cover the prologue fills plus one ticket");
+    // The prologue takes kAsyncSlots + 1 tickets; later chunks shrink with the work that is left ("guided" self-scheduling):
+    // chunk = clamp(remaining / (IPP_TICKET_GUIDE * warps in the grid), 1, kTicketChunk).  An env takes a warp ~5 us, so fixed
+    // chunks of 8 left warps up to 40 us of work after the counter ran dry while the rest of the GPU idled (a 145 us launch).
     unsigned int chunk_base = 0;
-    if (lane == 0) chunk_base = atomicAdd(ticket, (unsigned)kTicketChunk);
+    if (lane == 0) chunk_base = atomicAdd(ticket, (unsigned)(kAsyncSlots + 1));
     chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
-    int chunk_used = kAsyncSlots + 1;
+    int chunk_size = kAsyncSlots + 1, chunk_used = kAsyncSlots + 1;
+    const int guide_div = IPP_TICKET_GUIDE * (int)gridDim.x * ap.warps;
+    const float inv_guide = 1.0f / (float)guide_div;
 #pragma unroll
     for (int k = 0; k < kAsyncSlots; ++k) {
         const unsigned int t = chunk_base + k;
@@ -275,9 +290,16 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         //     chunk of tickets — both are consumed only after this env has been fused
         const int job_n = tk < (unsigned)n_jobs ? (int)tk : -1;
         const int id_n = job_n >= 0 ? __ldg(p.action_ids + job_n) : 0;
-        const bool need_chunk = chunk_used == kTicketChunk;
+        const bool need_chunk = chunk_used == chunk_size;
         unsigned int fresh = 0;
-        if (need_chunk && lane == 0) fresh = atomicAdd(ticket, (unsigned)kTicketChunk);
+        int req = kTicketChunk;
+        if (need_chunk) {
+            if (IPP_TICKET_GUIDE > 0) {
+                const int left = n_jobs - (int)min(chunk_base, (unsigned)n_jobs);  // as of this warp's previous chunk
+                req = min(kTicketChunk, max(1, (int)((float)left * inv_guide)));
+            }
+            if (lane == 0) fresh = atomicAdd(ticket, (unsigned)req);
+        }
 
         cp_async_wait<kAsyncSlots - 1>();  // this lane's copies into slot s have landed
         __syncwarp();                      // ... and so have every other lane's (and lane 0's SlotCtl)
@@ -339,7 +361,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         if (unsupported) {
             if (lane == 0) *(volatile int *)p.status = 1;  // mapped host word, bit 0 is the only bit
         } else {
-#pragma unroll 1
+            IPP_UNROLL(IPP_QUAD_UNROLL)
             for (int q = lane; q < nq; q += 32) {
                 const int qy = (int)(((uint32_t)q * magic_x) >> 16);
                 const int qx = q - qy * nqx;
@@ -454,6 +476,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         fill(s, job_n, id_n);
         if (need_chunk) {
             chunk_base = __shfl_sync(0xffffffffu, fresh, 0);
+            chunk_size = req;
             chunk_used = 0;
         }
         tk = chunk_base + (unsigned)chunk_used;

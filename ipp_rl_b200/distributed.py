@@ -42,27 +42,43 @@ def sharded_config(cfg: EngineConfig, total_envs: int, world_size: int, rank: in
     return EngineConfig(**kw)
 
 
-def gather_rewards(local, total_envs: int, group=None):
-    """All-gather the per-env rewards of every rank into one (total_envs,) tensor, ordered by global
-    env id.  ``local`` is this rank's 1-D torch tensor (CUDA with the nccl backend, CPU with gloo)."""
+def gather_rows(local, total_envs: int, group=None):
+    """All-gather per-env rows of every rank into one (total_envs, ...) tensor ordered by global env id.  ``local`` is
+    this rank's torch tensor whose first dimension is its env slice (CUDA with the nccl backend, CPU with gloo)."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     counts = all_shard_counts(total_envs, world)
-    if local.numel() != counts[dist.get_rank(group)]:
-        raise ValueError(f"local rewards have {local.numel()} entries, this rank owns {counts[dist.get_rank(group)]} envs")
+    mine = counts[dist.get_rank(group)]
+    if local.shape[0] != mine:
+        raise ValueError(f"local rows: {local.shape[0]}, this rank owns {mine} envs")
+    tail = tuple(local.shape[1:])
     if len(set(counts)) == 1:
-        out = torch.empty(total_envs, dtype=local.dtype, device=local.device)
+        out = torch.empty((total_envs,) + tail, dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
     # uneven split: pad every shard to the largest one, gather, drop the padding
     width = max(counts)
-    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
-    padded[: local.numel()] = local
-    out = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    padded = torch.zeros((width,) + tail, dtype=local.dtype, device=local.device)
+    padded[:mine] = local
+    out = torch.empty((world * width,) + tail, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded, group=group)
     return torch.cat([out[r * width : r * width + c] for r, c in enumerate(counts)])
+
+
+def gather_rewards(local, total_envs: int, group=None):
+    """The one exchange of the step path: per-env rewards (4 B per env per step) of all ranks, ordered by global env id."""
+    if local.dim() != 1:
+        raise ValueError("rewards must be 1-D (one per env of this rank)")
+    return gather_rows(local, total_envs, group)
+
+
+def gather_experience(local: dict, total_envs: int, group=None) -> dict:
+    """Experience rows of all ranks for the learner's ring (the reference sums what its worker processes
+    pickled to disk, mcts_zero_mission.py:504-521): every tensor of ``local`` ({"obs": (n, C, Y, X), "values": (n,), ...},
+    first dimension = this rank's env slice) is all-gathered in global env order."""
+    return {k: gather_rows(v, total_envs, group) for k, v in local.items()}
 
 
 class ShardedEngine:

@@ -14,7 +14,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "ipp_b200.h")
-HEADERS = [HEADER, os.path.join(ROOT, "include", "ipp_mcts.h")]
+HEADERS = [HEADER, os.path.join(ROOT, "include", "ipp_mcts.h"), os.path.join(ROOT, "include", "ipp_experience.h")]
 
 
 def _declared_functions():
@@ -42,17 +42,20 @@ def test_ctypes_structs_match_the_header(tmp_path):
 
     probe = tmp_path / "sz.c"
     probe.write_text(
-        f'#include "{HEADERS[1]}"\n#include <stdio.h>\n#include <stddef.h>\n'
-        "int main(){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(ipp_config), sizeof(ipp_info), offsetof(ipp_config, resolution), "
+        f'#include "{HEADERS[1]}"\n#include "{HEADERS[2]}"\n#include <stdio.h>\n#include <stddef.h>\n'
+        "int main(){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(ipp_config), sizeof(ipp_info), offsetof(ipp_config, resolution), "
         "offsetof(ipp_config, seed), offsetof(ipp_info, altitude), sizeof(ipp_mcts_config), sizeof(ipp_mcts_info), "
-        "offsetof(ipp_mcts_config, puct_init), offsetof(ipp_mcts_info, device_bytes)); return 0;}\n"
+        "offsetof(ipp_mcts_config, puct_init), offsetof(ipp_mcts_info, device_bytes), sizeof(ipp_ring_config), sizeof(ipp_ring_info), "
+        "offsetof(ipp_ring_config, stream), offsetof(ipp_ring_info, pushed)); return 0;}\n"
     )
     exe = tmp_path / "sz"
     subprocess.run(["gcc", str(probe), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ctypes.sizeof(_capi.ipp_config), ctypes.sizeof(_capi.ipp_info), _capi.ipp_config.resolution.offset,
                      _capi.ipp_config.seed.offset, _capi.ipp_info.altitude.offset, ctypes.sizeof(_capi.ipp_mcts_config),
-                     ctypes.sizeof(_capi.ipp_mcts_info), _capi.ipp_mcts_config.puct_init.offset, _capi.ipp_mcts_info.device_bytes.offset]
+                     ctypes.sizeof(_capi.ipp_mcts_info), _capi.ipp_mcts_config.puct_init.offset, _capi.ipp_mcts_info.device_bytes.offset,
+                     ctypes.sizeof(_capi.ipp_ring_config), ctypes.sizeof(_capi.ipp_ring_info), _capi.ipp_ring_config.stream.offset,
+                     _capi.ipp_ring_info.pushed.offset]
 
 
 def test_missing_library_fails_loudly(tmp_path):
@@ -216,7 +219,7 @@ _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
 import torch, torch.distributed as dist
-from ipp_rl_b200.distributed import gather_rewards, shard_bounds
+from ipp_rl_b200.distributed import gather_experience, gather_rewards, shard_bounds
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
 for total in (10, 7):
@@ -224,6 +227,10 @@ for total in (10, 7):
     local = torch.arange(first, first + count, dtype=torch.float32) * 1.5   # "reward" of global env i = 1.5 i
     out = gather_rewards(local, total)
     assert torch.equal(out, torch.arange(total, dtype=torch.float32) * 1.5), (rank, out)
+    ids = torch.arange(first, first + count, dtype=torch.float32)
+    exp = gather_experience({{"obs": ids[:, None, None].expand(count, 2, 3) + 0.25, "values": ids * 2}}, total)
+    full = torch.arange(total, dtype=torch.float32)
+    assert torch.equal(exp["obs"], full[:, None, None].expand(total, 2, 3) + 0.25) and torch.equal(exp["values"], full * 2)
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)

@@ -209,3 +209,26 @@ def test_host_ground_truth_generator_matches_reference():
         f = gtgen.gaussian_random_field(lambda k: k ** (-r), X, Y)
         assert f.shape == (Y, X)
         assert np.max(np.abs(f - g[f"{name}_field"])) <= 1e-12
+
+
+# --------------------------------------------------------------------------------------------------
+# experience path: value targets, prioritised replay, shift augmentation
+# --------------------------------------------------------------------------------------------------
+def test_experience_oracle_matches_reference():
+    from oracle import experience_oracle as xo
+
+    g = golden("golden_experience.npz")
+    for k in g["vt_cases"]:
+        gamma, H = g[f"vt{k}_params"]
+        vals, total = xo.value_targets(g[f"vt{k}_rewards"], float(gamma), int(H))
+        assert np.max(np.abs(vals - g[f"vt{k}_values"])) <= 1e-14
+        assert abs(total - float(g[f"vt{k}_total"])) <= 1e-13
+    alpha = float(g["per_alpha"])
+    for t in range(int(g["per_rounds"])):
+        idx, w = xo.prioritized_sample(g[f"per{t}_priorities"], alpha, float(g[f"per{t}_beta"]), g[f"per{t}_uniforms"])
+        assert np.array_equal(idx, g[f"per{t}_indices"])
+        assert np.array_equal(w, g[f"per{t}_weights"])
+        assert np.array_equal(g["per_states"][idx], g[f"per{t}_states"])
+    base = g["per_states"][g["aug_sel"]]
+    expect = np.vstack([base] + [xo.shift_with_replication(base, int(dy), int(dx)) for dy, dx in g["aug_offsets"]])
+    assert np.array_equal(expect, g["aug_states"])
