@@ -58,7 +58,7 @@ struct ipp_engine {
     // cp.async-staged persistent path (step_async.cuh) and the path switch
     bool async_ok = false;
     int step_path = IPP_PATH_ASYNC;  // requested path (ipp_set_option / IPP_STEP_PATH)
-    int async_warps = 0, async_mv_tile = 0, async_gt_tile = 0;
+    int async_warps = 0, async_double_warps = 0, async_mv_tile = 0, async_gt_tile = 0;
     bool async_vec16 = false;
     float2 *d_level_taps = nullptr;
     int level_tap_mode[kLevelTabs] = {-1, -1, -1, -1};
@@ -442,16 +442,24 @@ static int setup_async(ipp_engine *e) {
         if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;
     }
     const int mv_tile = round_up(mv_cells * 8, 16), gt_tile = round_up(gt_cells * 4, 16);
-    const size_t per_warp = (size_t)kAsyncSlots * (mv_tile + gt_tile) + kAsyncSlots * sizeof(SlotCtl) + kTapFloats2 * sizeof(float2);
+    // shared memory = [slots] stage tiles + SlotCtl | [warps] per-env tap tables | level tap tables.  Every warp owns one
+    // slot; what is left becomes second (prefetch) slots of the first `double_warps` warps.
+    const size_t per_slot = (size_t)(mv_tile + gt_tile) + sizeof(SlotCtl);
+    const size_t per_warp_fixed = kTapFloats2 * sizeof(float2);
     const size_t per_cta = (size_t)kLevelTabs * kTapFloats2 * sizeof(float2);
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device) != cudaSuccess) return IPP_OK;
-    if ((size_t)dev_smem < per_cta + 4 * per_warp) return IPP_OK;  // footprints too large to pipeline in shared memory
-    const int warps = (int)std::min<size_t>(kAsyncMaxWarps, ((size_t)dev_smem - per_cta) / per_warp);
+    if ((size_t)dev_smem < per_cta + 4 * (2 * per_slot + per_warp_fixed)) return IPP_OK;  // footprints too large to pipeline in shared memory
+    int warps = kAsyncMaxWarps;
+    if (const char *wenv = getenv("IPP_ASYNC_WARPS")) warps = std::max(4, std::min(kAsyncMaxWarps, atoi(wenv)));
+    warps = (int)std::min<size_t>(warps, ((size_t)dev_smem - per_cta) / (per_slot + per_warp_fixed));
+    const size_t spare = (size_t)dev_smem - per_cta - (size_t)warps * (per_slot + per_warp_fixed);
+    const int double_warps = (int)std::min<size_t>(warps, spare / per_slot);
     e->async_warps = warps;
+    e->async_double_warps = double_warps;
     e->async_mv_tile = mv_tile;
     e->async_gt_tile = gt_tile;
-    e->async_smem = per_warp * warps + per_cta;
+    e->async_smem = per_slot * (warps + double_warps) + per_warp_fixed * warps + per_cta;
     for (int v = 0; v < 16; ++v)
         if (cudaFuncSetAttribute(async_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->async_smem) != cudaSuccess) {
             cudaGetLastError();
@@ -491,6 +499,7 @@ static int launch_async(ipp_engine *e, const StepParams &p) {
     memcpy(ap.level_tap_mode, e->level_tap_mode, sizeof ap.level_tap_mode);
     ap.parity = e->ticket_parity;
     ap.warps = e->async_warps;
+    ap.double_warps = e->async_double_warps;
     ap.mv_tile_bytes = e->async_mv_tile;
     ap.gt_tile_bytes = e->async_gt_tile;
     ap.vec16 = e->async_vec16 ? 1 : 0;

@@ -65,6 +65,7 @@ struct AsyncParams {
     const float2 *level_taps;  // [kLevelTabs][kTapFloats2] tap tables of the unclipped footprints
     int parity;                // counter consumed by this launch; the other one is zeroed for the next
     int warps;                 // warps per CTA
+    int double_warps;          // warps [0, double_warps) own two staging slots (prefetch one env ahead), the rest one
     int mv_tile_bytes;         // per-slot tile capacities (multiples of 16 B)
     int gt_tile_bytes;
     int vec16;                 // 1: 16-byte L1-bypassing staging copies (x_dim % 4 == 0)
@@ -121,10 +122,15 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
     const StepParams &p = ap.base;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int stage_bytes = ap.mv_tile_bytes + ap.gt_tile_bytes;
-    unsigned char *my_stages = smem_raw + (size_t)w * kAsyncSlots * stage_bytes;
-    unsigned char *after = smem_raw + (size_t)ap.warps * kAsyncSlots * stage_bytes;
-    SlotCtl *ctl = reinterpret_cast<SlotCtl *>(after) + w * kAsyncSlots;
-    float2 *tap_base = reinterpret_cast<float2 *>(after + (size_t)ap.warps * kAsyncSlots * sizeof(SlotCtl));
+    // slot pool: slot w is warp w's first slot, slot warps + w its second one (warps below double_warps only).  Shared
+    // memory holds fewer than 2 x warps footprints of the largest size; more resident warps with some of them
+    // un-prefetched hide more latency than fewer warps that all prefetch.
+    const int n_slots_cta = ap.warps + ap.double_warps;
+    const int nsl = w < ap.double_warps ? 2 : 1;  // staging slots of this warp
+    unsigned char *after = smem_raw + (size_t)n_slots_cta * stage_bytes;
+    SlotCtl *ctl_all = reinterpret_cast<SlotCtl *>(after);
+    float2 *tap_base = reinterpret_cast<float2 *>(after + (size_t)n_slots_cta * sizeof(SlotCtl));
+    auto slot_of = [&](int s) { return s == 0 ? w : ap.warps + w; };
     float2 *taps = tap_base + (size_t)w * kTapFloats2;                 // this warp's per-env tables
     const float2 *lvl_taps = tap_base + (size_t)ap.warps * kTapFloats2;  // shared, read-only after the barrier
 
@@ -151,13 +157,13 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
             const int yu = max(row - L.ry, 0), yd = min(row + L.ry, p.Y - 1);
             const int nx = xr - xl + 1, ny = yd - yu + 1;
             const int pitch = (nx + 1) & ~1;
-            SlotCtl *c = ctl + s;
+            SlotCtl *c = ctl_all + slot_of(s);
             if (lane == 0) {
                 *reinterpret_cast<int4 *>(&c->job) = make_int4(job, lvl, col, row);
                 *reinterpret_cast<int4 *>(&c->xl) = make_int4(xl, yu, nx, ny);
             }
             if (lane < 3) cp_async_8(smem_u32(&c->prev[lane]), p.prev_state + 3 * (size_t)job + lane);
-            const uint32_t tile = smem_u32(my_stages + (size_t)s * stage_bytes);
+            const uint32_t tile = smem_u32(smem_raw + (size_t)slot_of(s) * stage_bytes);
             if (TILED) {
                 // IPP_LAYOUT_TILED: same staging as the 16-byte row-major path below (lanes = RP row-segments of W
                 // chunks, rows advance by RP), only the source offset differs: chunk (R, cc) of a plane with `tx` tiles
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 }
             }
         } else if (lane == 0) {
-            ctl[s].job = -1;  // out of work: the loop ends when it reaches this slot
+            ctl_all[slot_of(s)].job = -1;  // out of work: the loop ends when it reaches this slot
         }
         cp_async_commit();  // always: keeps the group count in step with the slot rotation
     };
@@ -270,18 +276,20 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
     // chunk = clamp(remaining / (IPP_TICKET_GUIDE * warps in the grid), 1, kTicketChunk).  An env takes a warp ~5 us, so fixed
     // chunks of 8 left warps up to 40 us of work after the counter ran dry while the rest of the GPU idled (a 145 us launch).
     unsigned int chunk_base = 0;
-    if (lane == 0) chunk_base = atomicAdd(ticket, (unsigned)(kAsyncSlots + 1));
+    if (lane == 0) chunk_base = atomicAdd(ticket, (unsigned)(nsl + 1));
     chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
-    int chunk_size = kAsyncSlots + 1, chunk_used = kAsyncSlots + 1;
+    int chunk_size = nsl + 1, chunk_used = nsl + 1;
     const int guide_div = IPP_TICKET_GUIDE * (int)gridDim.x * ap.warps;
     const float inv_guide = 1.0f / (float)guide_div;
 #pragma unroll
     for (int k = 0; k < kAsyncSlots; ++k) {
-        const unsigned int t = chunk_base + k;
-        const int jb = t < (unsigned)n_jobs ? (int)t : -1;
-        fill(k, jb, jb >= 0 ? __ldg(p.action_ids + jb) : 0);
+        if (k < nsl) {
+            const unsigned int t = chunk_base + k;
+            const int jb = t < (unsigned)n_jobs ? (int)t : -1;
+            fill(k, jb, jb >= 0 ? __ldg(p.action_ids + jb) : 0);
+        }
     }
-    unsigned int tk = chunk_base + kAsyncSlots;  // ticket whose action id has not been loaded yet
+    unsigned int tk = chunk_base + nsl;  // ticket whose action id has not been loaded yet
     int s = 0;
 
 #pragma unroll 1
@@ -301,11 +309,14 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
             if (lane == 0) fresh = atomicAdd(ticket, (unsigned)req);
         }
 
-        cp_async_wait<kAsyncSlots - 1>();  // this lane's copies into slot s have landed
-        __syncwarp();                      // ... and so have every other lane's (and lane 0's SlotCtl)
+        if (nsl == 2)  // this lane's copies into slot s have landed (the younger group may still be in flight)
+            cp_async_wait<1>();
+        else
+            cp_async_wait<0>();
+        __syncwarp();  // ... and so have every other lane's (and lane 0's SlotCtl)
 
         // (B) fuse the env whose tiles sit in slot s
-        const SlotCtl *c = ctl + s;
+        const SlotCtl *c = ctl_all + slot_of(s);
         const int4 c0v = *reinterpret_cast<const int4 *>(&c->job);
         const int4 c1v = *reinterpret_cast<const int4 *>(&c->xl);
         const int job = c0v.x, lvl = c0v.y;
@@ -322,7 +333,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         const int nqx = (nx + 1) >> 1, nqy = (ny + 1) >> 1;
         const int nq = nqx * nqy;
         const int out_r = quirk ? nqx : nqy, out_c = quirk ? nqy : nqx;
-        const unsigned char *st = my_stages + (size_t)s * stage_bytes;
+        const unsigned char *st = smem_raw + (size_t)slot_of(s) * stage_bytes;
         const float2 *mv_t = reinterpret_cast<const float2 *>(st) + ox;
         const float *gt_t = reinterpret_cast<const float *>(st + ap.mv_tile_bytes) + oxg;
 
@@ -481,7 +492,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         }
         tk = chunk_base + (unsigned)chunk_used;
         ++chunk_used;
-        s = (s + 1 == kAsyncSlots) ? 0 : s + 1;
+        s = (s + 1 == nsl) ? 0 : s + 1;
     }
     cp_async_wait<0>();
 }
