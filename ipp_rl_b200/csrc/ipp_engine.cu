@@ -424,6 +424,7 @@ static int setup_async(ipp_engine *e) {
     if ((rc = dev_alloc(e, &e->d_tickets, 2)) != IPP_OK) return rc;
     CU(e, cudaMemsetAsync(e->d_tickets, 0, 2 * sizeof(unsigned int), e->stream));
     if (c.layout != IPP_LAYOUT_MV && c.layout != IPP_LAYOUT_TILED) return IPP_OK;
+    if (c.x_dim > 32767 || c.y_dim > 32767 || e->n_levels > 255) return IPP_OK;  // EnvPlan packs cell coordinates into 16 bits
     // tile capacities for the largest footprint; with 16-byte staging (x_dim % 4 == 0) the tiles hold the
     // aligned superset of each row: {mean,var} pitch = roundup(1 + fw, 2) cells, gt pitch = roundup(3 + fw, 4) floats
     e->async_vec16 = (c.x_dim % 4 == 0);
@@ -433,6 +434,7 @@ static int setup_async(ipp_engine *e) {
     int mv_cells = 0, gt_cells = 0;
     for (int k = 0; k < e->n_levels; ++k) {
         const int fw = std::min(2 * e->lut[k].rx + 1, c.x_dim), fh = std::min(2 * e->lut[k].ry + 1, c.y_dim);
+        if (fw > 255 || fh > 255) return IPP_OK;  // EnvPlan packs footprint sizes into 8 bits
         const int pm = e->async_vec16 ? round_up(fw + 1, 2) : round_up(fw, 2);
         const int pg = e->async_vec16 ? round_up(fw + 3, 4) : round_up(fw, 2);
         mv_cells = std::max(mv_cells, pm * fh);
@@ -442,10 +444,10 @@ static int setup_async(ipp_engine *e) {
         if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;
     }
     const int mv_tile = round_up(mv_cells * 8, 16), gt_tile = round_up(gt_cells * 4, 16);
-    // shared memory = [slots] stage tiles + SlotCtl | [warps] per-env tap tables | level tap tables.  Every warp owns one
-    // slot; what is left becomes second (prefetch) slots of the first `double_warps` warps.
-    const size_t per_slot = (size_t)(mv_tile + gt_tile) + sizeof(SlotCtl);
-    const size_t per_warp_fixed = kTapFloats2 * sizeof(float2);
+    // shared memory = [slots] stage tiles | [warps] plan ring | [warps] per-env tap tables | level tap tables.  Every warp
+    // owns one slot; what is left becomes second (prefetch) slots of the first `double_warps` warps.
+    const size_t per_slot = (size_t)(mv_tile + gt_tile);
+    const size_t per_warp_fixed = kTapFloats2 * sizeof(float2) + (kPlanRing + 1) * sizeof(EnvPlan);
     const size_t per_cta = (size_t)kLevelTabs * kTapFloats2 * sizeof(float2);
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device) != cudaSuccess) return IPP_OK;

@@ -1,29 +1,31 @@
 // step_async.cuh — the throughput path of the fused step (sm_100a): a persistent kernel whose warps
-// stage whole footprints in shared memory with asynchronous copies (cp.async / LDGSTS), double
-// buffered per warp, for the discrete action set (action ids, MV layout).
+// stage whole footprints in shared memory with asynchronous copies (cp.async / LDGSTS) for the
+// discrete action set (action ids; MV and TILED layouts).
 //
 // Why: the footprint gather is latency bound when a warp waits for its own loads quad by quad
 // (ncu, v1: 21 % of HBM peak, 17 resident warps/SM, one third of a footprint in flight per warp).
-// Here every warp keeps the COMPLETE footprint of its next env in flight — {mean,var} tile with 8-byte
-// and ground-truth tile with 4-byte asynchronous copies, all 32 lanes issuing, no registers held —
-// while it fuses the env whose tiles have already landed.  Two slots per warp, cp.async group
-// accounting, no block-level synchronisation in the loop.  Work is handed out through a global
-// ticket counter (dynamic load balance: footprints are 81 / 289 / 529 cells), fetched one env ahead
-// so that neither the atomic nor the action-id load is ever waited for.  Up to 2 x 16 footprints
-// (~140 KB) are in flight per SM independent of register pressure.  Results go back with 64-bit
-// stores (write-back L2).
+// Here a warp keeps the COMPLETE footprint of its next env in flight — 16-byte asynchronous copies of the
+// aligned superset of every footprint row ({mean,var} tile and ground-truth tile), all 32 lanes issuing,
+// no registers held — while it fuses the env whose tiles have already landed; cp.async group
+// accounting, no block-level synchronisation in the loop.  Shared memory is a pool of footprint slots:
+// every warp owns one, the rest are second (prefetch) slots of the first `double_warps` warps.
+//
+// Work distribution: a global ticket counter with guided self-scheduling (chunks shrink with the work that
+// is left).  When a warp takes a chunk, lane i PLANS ticket base + i: everything about an env-step that is
+// warp-uniform (action decode, clipped footprint, staging geometry, division magics, tap-table choice, the
+// cost term, the stored previous action) is computed once by one lane and kept as a 48-byte EnvPlan in
+// shared memory, instead of redundantly by all 32 lanes per env.
 //
 // The loop body is kept small on purpose (ncu: the first version, 63 KB of SASS, spent most of its
-// time in instruction-fetch stalls): per-slot state lives in shared memory so that the body exists
-// once, rarely used paths are out of line, index divisions use a 16-bit magic multiplier, and the
-// INTER_AREA tap tables of the unclipped footprints are precomputed per altitude level.
+// time in instruction-fetch stalls): rarely used paths are out of line, index divisions use a 16-bit
+// magic multiplier, and the INTER_AREA tap tables of the unclipped footprints are precomputed per level.
 //
 // (A TMA variant of the same pipeline — 3-D tensor-map box copies — was measured and retired:
 // the TMA unit spends ~40 cycles per 100-200 B box row, slower than even the plain LSU kernel on
 // these narrow footprints; profiles/attic/step_tma.cuh.txt, tools/tma_probe.cu, DESIGN.md.)
 //
 //   grid  = #SMs (persistent, 1 CTA / SM), block = up to 16 warps, dynamic smem ~ 225 KB
-//   smem  = [warp][slot]{mv tile, gt tile} | [warp][slot] SlotCtl | [warp] tap tables | level tap tables
+//   smem  = [slot]{mv tile, gt tile} | [warp] plan ring | [warp] tap tables | level tap tables
 #pragma once
 #include "step_kernel.cuh"
 
@@ -48,7 +50,7 @@ constexpr int kAsyncMaxWarps = IPP_ASYNC_MAX_WARPS;  // warps per CTA (1 CTA / S
 #define IPP_TICKET_CHUNK 8
 #endif
 #ifndef IPP_TICKET_GUIDE
-#define IPP_TICKET_GUIDE 4  // 0: fixed chunks of IPP_TICKET_CHUNK
+#define IPP_TICKET_GUIDE 3  // 0: fixed chunks of IPP_TICKET_CHUNK (measured: 2 -> 520, 3 -> 523, 4 -> 512, 6 -> 498 M env-steps/s)
 #endif
 #ifndef IPP_QUAD_UNROLL
 #define IPP_QUAD_UNROLL 1
@@ -72,14 +74,27 @@ struct AsyncParams {
     int level_tap_mode[kLevelTabs];  // TAPS_FAST / TAPS_WIDE, or -1: no table for this level
 };
 
-// per-(warp, slot) control block, written when the slot is filled, read when it is fused
-struct __align__(16) SlotCtl {
-    int job, lvl, col, row;
-    int xl, yu, nx, ny;
-    double prev[3];  // the env's previous action (cost term), fetched with cp.async
-    int pad[2];
+// Per-env plan: everything about an env-step that is the same for all 32 lanes — decoded action, clipped footprint,
+// staging geometry, division magics, tap-table choice, the cost term — computed ONCE, by one lane, when a warp takes
+// a chunk of tickets (lane i plans ticket base + i), instead of redundantly by the whole warp for every env
+// (ncu: ~250 of 1 400 warp-instructions per env-step were such warp-uniform arithmetic).  48 B in shared memory.
+struct __align__(16) EnvPlan {
+    int job;           // < 0: out of work
+    int geo;           // xl | yu << 16
+    int dims;          // nx | ny << 8 | nqx << 16 | nqy << 24
+    int outs;          // out_r | out_c << 8 | cm << 16 | cg << 24   (cm / cg: 16-byte chunks per staged row)
+    int magic_x;       // floor(65536 / nqx) + 1
+    int magic_c;       // floor(65536 / out_c) + 1
+    int misc;          // lvl | rf << 8 | (tap_mode + 1) << 16 (0: build the tables per env) | unsupported << 24
+    float inv_cost1;   // 1 / (cost + 1)
+    float R, invR, s2;
+    int pad;
 };
-static_assert(sizeof(SlotCtl) == 64, "SlotCtl layout");
+static_assert(sizeof(EnvPlan) == 48, "EnvPlan layout");
+#ifndef IPP_PLAN_RING
+#define IPP_PLAN_RING 12
+#endif
+constexpr int kPlanRing = IPP_PLAN_RING;  // live plans per warp: <= 2 in slots + <= 1 queued + a fresh chunk of <= 8 (+ 1 sentinel after the ring)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src) {
@@ -114,6 +129,55 @@ __global__ void build_level_taps_kernel(float2 *tabs, const int *dims /* [levels
     if (threadIdx.x == 0) modes[k] = mode;
 }
 
+// Plan one env-step (one lane): see EnvPlan.  Also advances the env's stored previous action (unless KEEP_PREV) and
+// raises the status word for footprints the INTER_AREA path cannot serve.
+__device__ __forceinline__ void plan_env(const AsyncParams &ap, bool quirk, bool keep_prev, int job, EnvPlan *out) {
+    const StepParams &p = ap.base;
+    if (job < 0) {
+        out->job = -1;
+        return;
+    }
+    const int id = __ldg(p.action_ids + job);
+    double *ps = p.prev_state + 3 * (size_t)job;
+    const double q0 = ps[0], q1 = ps[1], q2 = ps[2];
+    int lvl, col, row;
+    decode_id(p, id, lvl, col, row);
+    const AltLevel &L = p.lut[lvl];
+    const int xl = max(col - L.rx, 0), xr = min(col + L.rx, p.X - 1);
+    const int yu = max(row - L.ry, 0), yd = min(row + L.ry, p.Y - 1);
+    const int nx = xr - xl + 1, ny = yd - yu + 1;
+    const int cm = ((xl & 1) + nx + 1) >> 1, cg = ((xl & 3) + nx + 3) >> 2;
+    const int nqx = (nx + 1) >> 1, nqy = (ny + 1) >> 1;
+    const int out_r = quirk ? nqx : nqy, out_c = quirk ? nqy : nqx;
+    const int rf = L.rf;
+    int tap_mode = TAPS_FAST;
+    bool unsupported = false;
+    if (rf == 2) {
+        unsupported = out_r > ny || out_c > nx;
+        const int lmode = lvl < kLevelTabs ? ap.level_tap_mode[lvl] : -1;
+        const bool interior = lmode >= 0 && nx == 2 * L.rx + 1 && ny == 2 * L.ry + 1 && (quirk || nqx == nqy);
+        tap_mode = interior ? lmode : -1;  // -1: the warp builds this env's tables when it fuses it
+    }
+    // q / nqx and q / out_c with a 16-bit magic multiplier floor(65536/d)+1: exact for q*d < 65536, which
+    // the host guarantees for every footprint that fits the shared-memory tiles (setup_async)
+    const int magic_x = (int)((uint32_t)(65536.0f * fast_rcp((float)nqx) * 1.00000012f) + 1u);
+    const int magic_c = (int)((uint32_t)(65536.0f * fast_rcp((float)out_c) * 1.00000012f) + 1u);
+    const double px = __dadd_rn(__dmul_rn(p.res, (double)col), __dmul_rn(0.5, p.res));
+    const double py = __dadd_rn(__dmul_rn(p.res, (double)row), __dmul_rn(0.5, p.res));
+    const float cost = job_cost(p, px, py, L.alt, q0, q1, q2);
+    if (!keep_prev) {
+        ps[0] = px;
+        ps[1] = py;
+        ps[2] = L.alt;
+    }
+    if (unsupported) *(volatile int *)p.status = 1;  // mapped host word, bit 0 is the only bit
+    int4 *o = reinterpret_cast<int4 *>(out);
+    o[0] = make_int4(job, xl | (yu << 16), nx | (ny << 8) | (nqx << 16) | (nqy << 24), out_r | (out_c << 8) | (cm << 16) | (cg << 24));
+    o[1] = make_int4(magic_x, magic_c, lvl | (rf << 8) | ((tap_mode + 1) << 16) | ((unsupported ? 1 : 0) << 24),
+                     __float_as_int(fast_rcp(cost + 1.0f)));
+    o[2] = make_int4(__float_as_int(L.R), __float_as_int(fast_rcp(L.R)), __float_as_int(L.s2), 0);
+}
+
 // ENTROPY / ADAPTIVE: reward variant and adaptive mask as compile-time switches; EXTRAS: host-supplied noise
 // and measurement read-back (parity / test features, not on the throughput path).
 template <bool ENTROPY, bool ADAPTIVE, bool EXTRAS, bool TILED>
@@ -128,14 +192,15 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
     const int n_slots_cta = ap.warps + ap.double_warps;
     const int nsl = w < ap.double_warps ? 2 : 1;  // staging slots of this warp
     unsigned char *after = smem_raw + (size_t)n_slots_cta * stage_bytes;
-    SlotCtl *ctl_all = reinterpret_cast<SlotCtl *>(after);
-    float2 *tap_base = reinterpret_cast<float2 *>(after + (size_t)n_slots_cta * sizeof(SlotCtl));
-    auto slot_of = [&](int s) { return s == 0 ? w : ap.warps + w; };
+    EnvPlan *plans = reinterpret_cast<EnvPlan *>(after) + w * (kPlanRing + 1);  // ring + the "out of work" sentinel
+    float2 *tap_base = reinterpret_cast<float2 *>(after + (size_t)ap.warps * (kPlanRing + 1) * sizeof(EnvPlan));
     float2 *taps = tap_base + (size_t)w * kTapFloats2;                 // this warp's per-env tables
     const float2 *lvl_taps = tap_base + (size_t)ap.warps * kTapFloats2;  // shared, read-only after the barrier
+    auto slot_of = [&](int s) { return s == 0 ? w : ap.warps + w; };
 
     // stage the per-level tap tables (a few hundred bytes each) once per CTA
     for (int i = threadIdx.x; i < kLevelTabs * kTapFloats2; i += blockDim.x) const_cast<float2 *>(lvl_taps)[i] = __ldg(ap.level_taps + i);
+    if (lane == 0) plans[kPlanRing].job = -1;
     __syncthreads();
 
     unsigned int *ticket = ap.tickets + ap.parity;
@@ -147,32 +212,43 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
     const int X = p.X;
     float2 *mv_base = reinterpret_cast<float2 *>(p.mean);
 
-    // Start the asynchronous copies of job's footprint into slot s (all lanes), one commit group.
-    auto fill = [&](int s, int job, int id) {
+    // ---- plan queue: ring of planned, not yet staged env-steps ------------------------------------------
+    int q_head = 0, q_tail = 0, q_cnt = 0;
+    auto plan_chunk = [&](unsigned int base, int cnt) {  // lane i plans ticket base + i
+        if (lane < cnt) {
+            const unsigned int t = base + (unsigned)lane;
+            int pos = q_tail + lane;
+            pos -= pos >= kPlanRing ? kPlanRing : 0;
+            plan_env(ap, quirk, keep_prev, t < (unsigned)n_jobs ? (int)t : -1, plans + pos);
+        }
+        q_tail += cnt;
+        q_tail -= q_tail >= kPlanRing ? kPlanRing : 0;
+        q_cnt += cnt;
+        __syncwarp();
+    };
+    auto pop_plan = [&]() {
+        const int pos = q_head;
+        q_head = q_head + 1 == kPlanRing ? 0 : q_head + 1;
+        --q_cnt;
+        return pos;
+    };
+
+    // Start the asynchronous copies of a planned env's footprint into slot s (all lanes), one commit group.
+    auto fill = [&](int s, const EnvPlan *pl) {
+        const int4 a = *reinterpret_cast<const int4 *>(pl);
+        const int job = a.x;
         if (job >= 0) {
-            int lvl, col, row;
-            decode_id(p, id, lvl, col, row);
-            const AltLevel &L = p.lut[lvl];
-            const int xl = max(col - L.rx, 0), xr = min(col + L.rx, X - 1);
-            const int yu = max(row - L.ry, 0), yd = min(row + L.ry, p.Y - 1);
-            const int nx = xr - xl + 1, ny = yd - yu + 1;
-            const int pitch = (nx + 1) & ~1;
-            SlotCtl *c = ctl_all + slot_of(s);
-            if (lane == 0) {
-                *reinterpret_cast<int4 *>(&c->job) = make_int4(job, lvl, col, row);
-                *reinterpret_cast<int4 *>(&c->xl) = make_int4(xl, yu, nx, ny);
-            }
-            if (lane < 3) cp_async_8(smem_u32(&c->prev[lane]), p.prev_state + 3 * (size_t)job + lane);
+            const int xl = a.y & 0xffff, yu = a.y >> 16;
+            const int nx = a.z & 255, ny = (a.z >> 8) & 255;
             const uint32_t tile = smem_u32(smem_raw + (size_t)slot_of(s) * stage_bytes);
             if (TILED) {
-                // IPP_LAYOUT_TILED: same staging as the 16-byte row-major path below (lanes = RP row-segments of W
-                // chunks, rows advance by RP), only the source offset differs: chunk (R, cc) of a plane with `tx` tiles
-                // per tile-row sits at float4 index ((R>>2)*tx + tile(cc))*8 + (R&3)*2 + half(cc).  Stepping R by
+                // IPP_LAYOUT_TILED: lanes = RP row-segments of W chunks, rows advance by RP; chunk (R, cc) of a plane with `tx`
+                // tiles per tile-row sits at float4 index ((R>>2)*tx + tile(cc))*8 + (R&3)*2 + half(cc).  Stepping R by
                 // RP = 2 alternates between "+4" (inside a tile) and "+tx*8 - 4" (into the tile below); RP = 4 always adds
                 // tx*8: one add and one xor per row (step ^= step_a ^ step_b).  RP = 1 (footprints wider than 31 cells)
                 // takes the generic stride.
                 const int ox = xl & 1, oxg = xl & 3;
-                const int cm = (ox + nx + 1) >> 1, cg = (oxg + nx + 3) >> 2;  // 16 B chunks per row
+                const int cm = (a.w >> 16) & 255, cg = (a.w >> 24) & 255;  // 16 B chunks per row
                 auto stage = [&](const unsigned char *plane, int tx, int cw, int cc_first, int cc_step, int tile_shift, uint32_t dst0) {
                     const int sh = cw <= 8 ? 3 : (cw <= 16 ? 4 : 5);  // W = 1 << sh lanes per row
                     const int RP = 32 >> sh;
@@ -212,7 +288,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 // superset of its footprint segment — the same 32 B sectors, a quarter of the copy instructions,
                 // and no L1 line allocation limiting the copies in flight.  Needs x_dim % 4 == 0.
                 const int ox = xl & 1, oxg = xl & 3;
-                const int cm = (ox + nx + 1) >> 1, cg = (oxg + nx + 3) >> 2;  // 16 B chunks per row
+                const int cm = (a.w >> 16) & 255, cg = (a.w >> 24) & 255;  // 16 B chunks per row
                 const size_t row0 = (size_t)IPP_ENV_OF(job) * p.plane + (size_t)(yu * X);
                 {
                     const int W = cm <= 8 ? 8 : (cm <= 16 ? 16 : 32), RP = 32 / W;
@@ -245,6 +321,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
             } else {
                 // lanes are laid out as RP row-segments of W columns: a warp instruction covers RP rows of the
                 // footprint, each a coalesced run of 32 B sectors; addresses advance by constant strides
+                const int pitch = (nx + 1) & ~1;
                 const int W = nx <= 8 ? 8 : (nx <= 16 ? 16 : 32);
                 const int RP = 32 / W;
                 const int lr = lane / W, lc = lane - lr * W;
@@ -265,43 +342,35 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                     }
                 }
             }
-        } else if (lane == 0) {
-            ctl_all[slot_of(s)].job = -1;  // out of work: the loop ends when it reaches this slot
         }
         cp_async_commit();  // always: keeps the group count in step with the slot rotation
     };
 
-    // ---- prologue: one ticket chunk; fill every slot -----------------------------------------------
-    // The prologue takes kAsyncSlots + 1 tickets; later chunks shrink with the work that is left ("guided" self-scheduling):
-    // chunk = clamp(remaining / (IPP_TICKET_GUIDE * warps in the grid), 1, kTicketChunk).  An env takes a warp ~5 us, so fixed
-    // chunks of 8 left warps up to 40 us of work after the counter ran dry while the rest of the GPU idled (a 145 us launch).
+    // ---- prologue: nsl + 1 tickets, planned at once; fill every slot -------------------------------------
+    // Later chunks shrink with the work that is left ("guided" self-scheduling): chunk = clamp(remaining /
+    // (IPP_TICKET_GUIDE * warps in the grid), 1, kTicketChunk).  An env takes a warp ~5 us, so fixed chunks of 8 left warps up
+    // to 40 us of work after the counter ran dry while the rest of the GPU idled (a 145 us launch).
     unsigned int chunk_base = 0;
     if (lane == 0) chunk_base = atomicAdd(ticket, (unsigned)(nsl + 1));
     chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
-    int chunk_size = nsl + 1, chunk_used = nsl + 1;
-    const int guide_div = IPP_TICKET_GUIDE * (int)gridDim.x * ap.warps;
-    const float inv_guide = 1.0f / (float)guide_div;
-#pragma unroll
-    for (int k = 0; k < kAsyncSlots; ++k) {
-        if (k < nsl) {
-            const unsigned int t = chunk_base + k;
-            const int jb = t < (unsigned)n_jobs ? (int)t : -1;
-            fill(k, jb, jb >= 0 ? __ldg(p.action_ids + jb) : 0);
-        }
+    bool exhausted = chunk_base + (unsigned)(nsl + 1) >= (unsigned)n_jobs;  // no ticket left behind this chunk
+    plan_chunk(chunk_base, nsl + 1);
+    const float inv_guide = 1.0f / (float)(max(IPP_TICKET_GUIDE, 1) * (int)gridDim.x * ap.warps);
+    int sp0 = pop_plan(), sp1 = kPlanRing;  // plan held by slot 0 / slot 1
+    fill(0, plans + sp0);
+    if (nsl == 2) {
+        sp1 = pop_plan();
+        fill(1, plans + sp1);
     }
-    unsigned int tk = chunk_base + nsl;  // ticket whose action id has not been loaded yet
     int s = 0;
 
 #pragma unroll 1
     while (true) {
-        // (A) start the next fetches early: action id of ticket tk and, when the chunk is used up, a fresh
-        //     chunk of tickets — both are consumed only after this env has been fused
-        const int job_n = tk < (unsigned)n_jobs ? (int)tk : -1;
-        const int id_n = job_n >= 0 ? __ldg(p.action_ids + job_n) : 0;
-        const bool need_chunk = chunk_used == chunk_size;
+        // (A) ask for the next chunk of tickets early — the atomic's result is consumed only after this env has been fused
+        const bool request = q_cnt <= 1 && !exhausted;
         unsigned int fresh = 0;
         int req = kTicketChunk;
-        if (need_chunk) {
+        if (request) {
             if (IPP_TICKET_GUIDE > 0) {
                 const int left = n_jobs - (int)min(chunk_base, (unsigned)n_jobs);  // as of this warp's previous chunk
                 req = min(kTicketChunk, max(1, (int)((float)left * inv_guide)));
@@ -313,26 +382,27 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
             cp_async_wait<1>();
         else
             cp_async_wait<0>();
-        __syncwarp();  // ... and so have every other lane's (and lane 0's SlotCtl)
+        __syncwarp();  // ... and so have every other lane's
 
         // (B) fuse the env whose tiles sit in slot s
-        const SlotCtl *c = ctl_all + slot_of(s);
-        const int4 c0v = *reinterpret_cast<const int4 *>(&c->job);
-        const int4 c1v = *reinterpret_cast<const int4 *>(&c->xl);
-        const int job = c0v.x, lvl = c0v.y;
+        const EnvPlan *pl = plans + (s == 0 ? sp0 : sp1);
+        const int4 pa = *reinterpret_cast<const int4 *>(pl);
+        const int job = pa.x;
         if (job < 0) break;  // warp-uniform: tickets are monotonic, every later slot is empty too
-        const int xl = c1v.x, yu = c1v.y, nx = c1v.z, ny = c1v.w;
-        const AltLevel &L = p.lut[lvl];
-        const int rf = L.rf;
-        const float s2 = L.s2;
+        const int4 pb = *reinterpret_cast<const int4 *>(&pl->magic_x);
+        const float4 pc4 = *reinterpret_cast<const float4 *>(&pl->R);
+        const int xl = pa.y & 0xffff, yu = pa.y >> 16;
+        const int nx = pa.z & 255, ny = (pa.z >> 8) & 255, nqx = (pa.z >> 16) & 255, nqy = (pa.z >> 24) & 255;
+        const int out_r = pa.w & 255, out_c = (pa.w >> 8) & 255;
+        const int lvl = pb.z & 255, rf = (pb.z >> 8) & 255;
+        const bool unsupported = (pb.z >> 24) != 0;
+        const float s2 = pc4.z;
         // tile geometry: with 16-byte staging the tiles start at the aligned cell left of the footprint
         const bool aligned16 = TILED || ap.vec16;
         const int ox = aligned16 ? (xl & 1) : 0, oxg = aligned16 ? (xl & 3) : 0;
         const int pm = aligned16 ? ((ox + nx + 1) & ~1) : ((nx + 1) & ~1);  // {mean,var} tile pitch [cells]
         const int pg = aligned16 ? ((oxg + nx + 3) & ~3) : pm;              // ground-truth tile pitch [floats]
-        const int nqx = (nx + 1) >> 1, nqy = (ny + 1) >> 1;
         const int nq = nqx * nqy;
-        const int out_r = quirk ? nqx : nqy, out_c = quirk ? nqy : nqx;
         const unsigned char *st = smem_raw + (size_t)slot_of(s) * stage_bytes;
         const float2 *mv_t = reinterpret_cast<const float2 *>(st) + ox;
         const float *gt_t = reinterpret_cast<const float *>(st + ap.mv_tile_bytes) + oxg;
@@ -341,16 +411,11 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         TapView tapv;
         tapv.rows = taps;
         tapv.cols = taps + 3 * kTapCap;
-        int tap_mode = TAPS_FAST;
-        bool unsupported = false;
+        int tap_mode = ((pb.z >> 16) & 255) - 1;
         if (rf == 2) {
-            unsupported = out_r > ny || out_c > nx;
-            const int lmode = lvl < kLevelTabs ? ap.level_tap_mode[lvl] : -1;
-            const bool interior = lmode >= 0 && nx == 2 * L.rx + 1 && ny == 2 * L.ry + 1 && (quirk || nqx == nqy);
-            if (interior) {
+            if (tap_mode >= 0) {
                 tapv.rows = lvl_taps + (size_t)lvl * kTapFloats2;
                 tapv.cols = tapv.rows + 3 * kTapCap;
-                tap_mode = lmode;
             } else if (!unsupported) {
                 tap_mode = build_tap_tables<kTapCap>(taps, lane, ny, nx, out_r, out_c);
             }
@@ -358,20 +423,15 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
 
         FuseCtx fc;
         fc.rf = rf;
-        fc.R = L.R;
-        fc.invR = fast_rcp(L.R);
-        // q / nqx and q / out_c with a 16-bit magic multiplier floor(65536/d)+1: exact for q*d < 65536, which
-        // the host guarantees for every footprint that fits the shared-memory tiles (setup_async)
-        const uint32_t magic_x = (uint32_t)(65536.0f * fast_rcp((float)nqx) * 1.00000012f) + 1u;
-        const uint32_t magic_c = (uint32_t)(65536.0f * fast_rcp((float)out_c) * 1.00000012f) + 1u;
+        fc.R = pc4.x;
+        fc.invR = pc4.y;
+        const uint32_t magic_x = (uint32_t)pb.x, magic_c = (uint32_t)pb.y;
         float2 *mv_g = mv_base + (size_t)IPP_ENV_OF(job) * p.plane + (TILED ? (size_t)0 : (size_t)(yu * X + xl));
         const size_t nrow = (size_t)job * (size_t)p.noise_stride;
         float acc = 0.0f;
         float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four iterations
 
-        if (unsupported) {
-            if (lane == 0) *(volatile int *)p.status = 1;  // mapped host word, bit 0 is the only bit
-        } else {
+        if (!unsupported) {
             IPP_UNROLL(IPP_QUAD_UNROLL)
             for (int q = lane; q < nq; q += 32) {
                 const int qy = (int)(((uint32_t)q * magic_x) >> 16);
@@ -465,33 +525,28 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
             }
         }
 
-        // per-env information gain: fp32 partials per lane (<= 17 quads), fp64 tree across the warp
-        float accd = acc;  // fp32 tree: <= 32 partials of similar size, relative error ~3e-7
+        // per-env information gain: fp32 partials per lane (<= 17 quads), fp32 tree across the warp
+        // (<= 32 partials of similar size, relative error ~3e-7); the cost term comes from the plan
+        float accd = acc;
 #pragma unroll
         for (int sft = 16; sft > 0; sft >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, sft);
-        if (lane == 0) {
-            const double px = __dadd_rn(__dmul_rn(p.res, (double)c0v.z), __dmul_rn(0.5, p.res));
-            const double py = __dadd_rn(__dmul_rn(p.res, (double)c0v.w), __dmul_rn(0.5, p.res));
-            const float cost = job_cost(p, px, py, L.alt, c->prev[0], c->prev[1], c->prev[2]);
-            if (p.reward != nullptr) p.reward[job] = accd * fast_rcp(cost + 1.0f);
-            if (!keep_prev) {
-                double *ps = p.prev_state + 3 * (size_t)job;
-                ps[0] = px;
-                ps[1] = py;
-                ps[2] = L.alt;
-            }
-        }
-        __syncwarp();  // every lane is done with slot s (tiles, SlotCtl, tap tables)
+        if (lane == 0 && p.reward != nullptr) p.reward[job] = accd * __int_as_float(pb.w);
+        __syncwarp();  // every lane is done with slot s (tiles, plan, tap tables)
 
-        // (C) refill slot s with the job resolved at (A); (D) next ticket to resolve
-        fill(s, job_n, id_n);
-        if (need_chunk) {
+        // (C) refill slot s with the next planned env (the sentinel once the tickets have run out)
+        const int pos_n = q_cnt > 0 ? pop_plan() : kPlanRing;
+        if (s == 0)
+            sp0 = pos_n;
+        else
+            sp1 = pos_n;
+        fill(s, plans + pos_n);
+
+        // (D) plan the chunk requested at (A): lane i decodes ticket fresh + i
+        if (request) {
             chunk_base = __shfl_sync(0xffffffffu, fresh, 0);
-            chunk_size = req;
-            chunk_used = 0;
+            exhausted = chunk_base + (unsigned)req >= (unsigned)n_jobs;
+            if (chunk_base < (unsigned)n_jobs) plan_chunk(chunk_base, req);
         }
-        tk = chunk_base + (unsigned)chunk_used;
-        ++chunk_used;
         s = (s + 1 == nsl) ? 0 : s + 1;
     }
     cp_async_wait<0>();
