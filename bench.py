@@ -211,6 +211,7 @@ def run_ours(args, rank, world, local_rank):
         ids_pinned = torch.from_numpy(ids_e2e).pin_memory()
         out_pinned = torch.empty(world * B if dist is not None else B, dtype=torch.float32).pin_memory()
         ids_np, out_np = ids_pinned.numpy(), out_pinned.numpy()
+        id_rows = [ids_np[k] for k in range(POOL)]  # stable array objects (the engine caches their ctypes pointers)
         eng.reset(PRIOR_MEAN, PRIOR_VAR)
         if args.zero_copy is not None:
             eng.set_zero_copy(rewards="r" in args.zero_copy, ids="i" in args.zero_copy)
@@ -218,7 +219,7 @@ def run_ours(args, rank, world, local_rank):
 
         def e2e_step(t):
             if dist is None:
-                eng.step(ids_np[t % POOL], reward_mode=capi.REWARD_GAUSS_ENTROPY, out=out_np)
+                eng.step(id_rows[t % POOL], reward_mode=capi.REWARD_GAUSS_ENTROPY, out=out_np)
             else:
                 staged = ids_pinned[t % POOL].cuda(non_blocking=True)
                 eng.step_device(action_ids_ptr=staged.data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=capi.REWARD_GAUSS_ENTROPY)
