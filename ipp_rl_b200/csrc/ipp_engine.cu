@@ -443,7 +443,9 @@ static int setup_async(ipp_engine *e) {
         const int nqx = (fw + 1) / 2, nqy = (fh + 1) / 2;
         if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;
     }
-    const int mv_tile = round_up(mv_cells * 8, 16), gt_tile = round_up(gt_cells * 4, 16);
+    // TILED + IPP_DIRECT_MV: the belief is not staged at all (bulk L2 prefetch + direct loads), a slot holds the ground truth only
+    const bool direct_mv = c.layout == IPP_LAYOUT_TILED && (IPP_DIRECT_MV != 0);
+    const int mv_tile = direct_mv ? 0 : round_up(mv_cells * 8, 16), gt_tile = round_up(gt_cells * 4, 16);
     // shared memory = [slots] stage tiles | [warps] plan ring | [warps] per-env tap tables | level tap tables.  Every warp
     // owns one slot; what is left becomes second (prefetch) slots of the first `double_warps` warps.
     const size_t per_slot = (size_t)(mv_tile + gt_tile);

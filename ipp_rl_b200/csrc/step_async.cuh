@@ -52,6 +52,16 @@ constexpr int kAsyncMaxWarps = IPP_ASYNC_MAX_WARPS;  // warps per CTA (1 CTA / S
 #ifndef IPP_TICKET_GUIDE
 #define IPP_TICKET_GUIDE 3  // 0: fixed chunks of IPP_TICKET_CHUNK (measured: 2 -> 520, 3 -> 523, 4 -> 512, 6 -> 498 M env-steps/s)
 #endif
+// Experiment switch (TILED layout): 1 = only the ground truth is staged in shared memory; the belief — every cell is read
+// exactly once, by the lane that rewrites it — is pulled into L2 one env ahead (IPP_PF_MODE) and read from there with
+// ld.global.cg.  Measured and NOT adopted: slots shrink 7.4 -> 2.6 KB and 20+ warps fit with two slots each, but the L2
+// latency of the per-quad loads is exposed: 445 M env-steps/s at 20 warps (405 M without the prefetch) vs 524 M staged.
+#ifndef IPP_DIRECT_MV
+#define IPP_DIRECT_MV 0
+#endif
+#ifndef IPP_PF_MODE
+#define IPP_PF_MODE 1  // IPP_DIRECT_MV: 0 no prefetch, 1 bulk prefetch per tile row, 2 prefetch.global.L2 per tile, 3 per 32 B sector
+#endif
 #ifndef IPP_QUAD_UNROLL
 #define IPP_QUAD_UNROLL 1
 #endif
@@ -111,6 +121,9 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
 #endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {  // src 16 B aligned, bytes % 16 == 0
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -185,6 +198,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const StepParams &p = ap.base;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr bool kDirect = TILED && (IPP_DIRECT_MV != 0);  // belief read from L2, not staged (mv_tile_bytes == 0)
     const int stage_bytes = ap.mv_tile_bytes + ap.gt_tile_bytes;
     // slot pool: slot w is warp w's first slot, slot warps + w its second one (warps below double_warps only).  Shared
     // memory holds fewer than 2 x warps footprints of the largest size; more resident warps with some of them
@@ -280,7 +294,32 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                         }
                     }
                 };
-                stage(reinterpret_cast<const unsigned char *>(mv_base + (size_t)IPP_ENV_OF(job) * p.plane), p.txm, cm, xl - ox, 2, 2, tile);
+                if (kDirect) {
+                    // belief tiles -> L2: tile row k of the footprint is one contiguous run of ntx 128-byte tiles (warp-uniform)
+                    const int ty0 = yu >> 2, ntr = ((yu + ny - 1) >> 2) - ty0 + 1;
+                    const int tx0 = xl >> 2, ntx = ((xl + nx - 1) >> 2) - tx0 + 1;
+                    const unsigned char *run = reinterpret_cast<const unsigned char *>(mv_base + (size_t)IPP_ENV_OF(job) * p.plane) +
+                                               ((size_t)(ty0 * p.txm + tx0) << 7);
+#if IPP_PF_MODE == 1
+#pragma unroll 1
+                    for (int k = 0; k < ntr; ++k) {
+                        bulk_prefetch_l2(run, (uint32_t)ntx << 7);
+                        run += (size_t)p.txm << 7;
+                    }
+#elif IPP_PF_MODE == 2 || IPP_PF_MODE == 3
+                    // one prefetch per 128-byte tile (2) or per 32-byte sector (3), lanes side by side
+                    constexpr int kPer = IPP_PF_MODE == 3 ? 4 : 1;
+                    const uint32_t inv_ntx = 65536u / (uint32_t)ntx + 1u;
+                    for (int u = lane; u < ntr * ntx * kPer; u += 32) {
+                        const int t = u / kPer, sec = u - t * kPer;
+                        const int tr = (int)(((uint32_t)t * inv_ntx) >> 16), tc = t - tr * ntx;
+                        const unsigned char *a2 = run + (size_t)tr * ((size_t)p.txm << 7) + ((size_t)tc << 7) + sec * 32;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a2) : "memory");
+                    }
+#endif
+                } else {
+                    stage(reinterpret_cast<const unsigned char *>(mv_base + (size_t)IPP_ENV_OF(job) * p.plane), p.txm, cm, xl - ox, 2, 2, tile);
+                }
                 stage(reinterpret_cast<const unsigned char *>(p.gt + (size_t)IPP_ENV_OF(job) * p.plane_gt), p.txg, cg, xl - oxg, 4, 3,
                       tile + (uint32_t)ap.mv_tile_bytes);
             } else if (ap.vec16) {
@@ -441,9 +480,24 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 const bool ok[4] = {true, cok, rok, cok && rok};
                 const int r1 = min(r0 + 1, ny - 1);  // clamped: the tile has exactly ny rows
 
-                // ---- belief from the staged tile: two 128-bit shared loads (pitch is even) -------
+                // ---- belief: from L2 at the very addresses the results go back to (kDirect), else from the staged tile ----
                 float4 top, bot;
-                if (ox == 0) {  // warp-uniform: 16-byte aligned quad rows
+                const int R0 = yu + r0, C0 = xl + c0;
+                float2 *o = mv_g + (TILED ? tiled_mv_index(p.txm, R0, C0) : r0 * X + c0);
+                const int dR = (R0 & 3) == 3 ? 16 * p.txm - 12 : 4;  // next row: inside the tile, or the tile below
+                const int dC = (C0 & 3) == 3 ? 13 : 1;               // next column: inside the tile, or the tile to the right
+                if (kDirect) {
+                    if (ox == 0) {  // warp-uniform: (C0, C0+1) share a 16-byte chunk
+                        top = __ldcg(reinterpret_cast<const float4 *>(o));
+                        bot = rok ? __ldcg(reinterpret_cast<const float4 *>(o + dR)) : top;
+                    } else {
+                        const float2 zz = make_float2(0.f, 0.f);
+                        const float2 a = __ldcg(o), b = cok ? __ldcg(o + dC) : zz, c2 = rok ? __ldcg(o + dR) : zz,
+                                     d2 = ok[3] ? __ldcg(o + dR + dC) : zz;
+                        top = make_float4(a.x, a.y, b.x, b.y);
+                        bot = make_float4(c2.x, c2.y, d2.x, d2.y);
+                    }
+                } else if (ox == 0) {  // warp-uniform: 16-byte aligned quad rows
                     top = *reinterpret_cast<const float4 *>(mv_t + r0 * pm + c0);
                     bot = *reinterpret_cast<const float4 *>(mv_t + r1 * pm + c0);
                 } else {
@@ -497,9 +551,6 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                 for (int k = 0; k < 4; ++k) msk[k] = ok[k] && (!ADAPTIVE || (fmaf(p.kappa, v[k], m[k]) >= p.thr));
                 acc += kalman_quad<ENTROPY, ADAPTIVE>(fc, cok, rok, m, v, z, msk, mn, vn);
                 if (TILED) {
-                    const int R0 = yu + r0, C0 = xl + c0;
-                    float2 *o = mv_g + tiled_mv_index(p.txm, R0, C0);
-                    const int dR = (R0 & 3) == 3 ? 16 * p.txm - 12 : 4;  // next row: inside the tile, or the tile below
                     if (ox == 0) {  // warp-uniform: (C0, C0+1) share a 16-byte chunk
                         if (cok) {
                             *reinterpret_cast<float4 *>(o) = make_float4(mn[0], vn[0], mn[1], vn[1]);
@@ -509,14 +560,12 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                             if (rok) o[dR] = make_float2(mn[2], vn[2]);
                         }
                     } else {
-                        const int dC = (C0 & 3) == 3 ? 13 : 1;  // next column: inside the tile, or the tile to the right
                         o[0] = make_float2(mn[0], vn[0]);
                         if (cok) o[dC] = make_float2(mn[1], vn[1]);
                         if (rok) o[dR] = make_float2(mn[2], vn[2]);
                         if (ok[3]) o[dR + dC] = make_float2(mn[3], vn[3]);
                     }
                 } else {
-                    float2 *o = mv_g + r0 * X + c0;
                     o[0] = make_float2(mn[0], vn[0]);
                     if (cok) o[1] = make_float2(mn[1], vn[1]);
                     if (rok) o[X] = make_float2(mn[2], vn[2]);
