@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=500, help="steps of the host-buffer (e2e) leg (<= --steps)")
     ap.add_argument("--zero-copy", default=None, choices=["", "r", "i", "ri"],
                     help="e2e leg: host buffers the kernel accesses in place (r = rewards, i = action ids); default = the engine's (r)")
-    ap.add_argument("--mcts-trees", type=int, default=4096, help="trees of the secondary mcts_zero rollout leg (0 = skip)")
+    ap.add_argument("--mcts-trees", type=int, default=16384, help="trees of the secondary mcts_zero rollout leg = BASELINE.json C4 per-GPU share (0 = skip)")
     ap.add_argument("--mcts-sims", type=int, default=32)
     ap.add_argument("--max-altitude", type=float, default=None, help="experiments only: override the top altitude of the action set")
     args = ap.parse_args()
