@@ -245,6 +245,28 @@ def run_ours(args, rank, world, local_rank):
         zero_copy_steps = eng.zero_copy_steps - zc0
         assert np.isfinite(out_np).all()
 
+        # ---- e2e, pipelined (N = 1): the same per-step transfers through ipp_step_submit / ipp_step_wait, two slots — the host
+        #      uploads step t+1 while step t computes and waits for step t-1 before reusing its buffers (reported beside e2e.value)
+        pipe_s = None
+        if dist is None:
+            outs2 = [torch.empty(B, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+
+            def pipe_loop(lo, hi):
+                for t in range(lo, hi):
+                    sl = t & 1
+                    eng.step_wait(sl)
+                    eng.step_submit(sl, id_rows[t % POOL], outs2[sl], reward_mode=capi.REWARD_GAUSS_ENTROPY)
+                eng.step_wait(0)
+                eng.step_wait(1)
+
+            pipe_loop(0, W)
+            barrier()
+            t0 = time.perf_counter()
+            pipe_loop(W, W + KE)
+            barrier()
+            pipe_s = time.perf_counter() - t0
+            assert np.isfinite(outs2[0]).all() and np.isfinite(outs2[1]).all()
+
     # ---- secondary leg (BASELINE.json configs[3], "C4"): mcts_zero rollouts on the same beliefs.  Lock-step search over
     #      `--mcts-trees` envs, `--mcts-sims` simulations, episode_horizon 5, max_valid_action_distance 11.5 m, uniform
     #      priors / zero values (no network: the policy/value net is outside this library).  Reported beside the headline.
@@ -332,6 +354,9 @@ def run_ours(args, rank, world, local_rank):
                          "mean_cells_per_env_step": cells_timed_total / (B * K), "kernel": "ipp_step_async_kernel" if eng.step_path == "async" else "ipp_step_kernel<MV, KALMAN>", "step_path": eng.step_path},
             "e2e": {"value": world * B * KE / e2e_s, "steps": KE, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * B * world,
                     "d2h_bytes_per_step": 4 * B * world * (world if dist is not None else 1),
+                    "pipelined_value": (B * KE / pipe_s) if pipe_s else None,
+                    "pipelined_path": "ipp_step_submit / ipp_step_wait, 2 slots: same per-step H2D ids + rewards to pinned host memory, upload of "
+                                      "step t+1 under the kernel of step t" if pipe_s else None,
                     "path": ("BatchedEngine.step (ipp_step: pinned host ids -> H2D -> fused kernel -> "
                              + ("rewards written by the kernel into the caller's pinned buffer [zero-copy D2H, 4 B/env over PCIe])"
                                 if zero_copy_steps > 0 else "D2H rewards)")) if dist is None else

@@ -186,6 +186,17 @@ int ipp_step_device(ipp_engine *e, const int32_t *action_ids, const double *pose
                     const float *noise, int32_t noise_stride, float *reward, float *measurements,
                     uint32_t flags);
 
+/* Pipelined host steps (action ids only): ipp_step_submit queues, for one of IPP_STEP_SLOTS slots, the upload of the ids
+ * (on a copy stream, under whatever kernel is running), the fused step kernel and the delivery of the rewards (written by
+ * the kernel straight into `reward` when that is pinned + mapped, else a device->host copy), and returns at once;
+ * ipp_step_wait blocks until the step submitted to `slot` is complete (status errors surface here).  Steps execute in
+ * submission order.  The caller keeps `action_ids` / `reward` untouched between submit and wait.  With two slots the host
+ * prepares and uploads step t+1 while step t computes — what an actor loop that does not need reward t to choose
+ * action t+1 (random / open-loop / one-step-stale policies, data collection) gets over the synchronous ipp_step. */
+#define IPP_STEP_SLOTS 2
+int ipp_step_submit(ipp_engine *e, int32_t slot, const int32_t *action_ids, float *reward, uint32_t flags);
+int ipp_step_wait(ipp_engine *e, int32_t slot);
+
 /* The two halves of ipp_step as separate calls (host pointers), for callers that keep the
  * reference's two-call protocol (planning/greedy_mission.py:101-102):
  *   ipp_measure = Sensor.take_measurement(position)            sensors/cameras.py:108-116

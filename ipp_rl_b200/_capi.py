@@ -42,6 +42,7 @@ OPT_STEP_PATH = 1
 OPT_LAUNCHES_LSU, OPT_LAUNCHES_ASYNC = 2, 3
 OPT_ZERO_COPY, OPT_ZERO_COPY_STEPS = 4, 5
 ZERO_COPY_REWARDS, ZERO_COPY_IDS = 1, 2
+STEP_SLOTS = 2
 
 
 class IppLibraryError(RuntimeError):
@@ -189,6 +190,8 @@ SIGNATURES = {
     "ipp_get_prev_pose": (C.c_int, [_P, _P]),
     "ipp_step": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _U32]),
     "ipp_step_device": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _U32]),
+    "ipp_step_submit": (C.c_int, [_P, _I32, _P, _P, _U32]),
+    "ipp_step_wait": (C.c_int, [_P, _I32]),
     "ipp_measure": (C.c_int, [_P, _P, _P, _P, _I32, _P, _U32]),
     "ipp_update": (C.c_int, [_P, _P, _P, _P, _I32, _P, _U32]),
     "ipp_predict": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _U32]),

@@ -51,6 +51,12 @@ struct ipp_engine {
     float *d_scratch = nullptr;  // dense [n][plane] staging for MV get/set
     size_t cap_scratch = 0;
     int *h_status = nullptr;  // pinned + mapped
+    // pipelined host steps (ipp_step_submit / ipp_step_wait): H2D of the next step's ids on a copy stream under the running kernel
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[IPP_STEP_SLOTS] = {nullptr, nullptr}, ev_done[IPP_STEP_SLOTS] = {nullptr, nullptr};
+    int32_t *d_actions_slot[IPP_STEP_SLOTS] = {nullptr, nullptr};
+    float *d_reward_slot[IPP_STEP_SLOTS] = {nullptr, nullptr};
+    bool slot_busy[IPP_STEP_SLOTS] = {false, false};
     int zero_copy = IPP_ZERO_COPY_REWARDS;  // IPP_OPT_ZERO_COPY / env IPP_ZERO_COPY
     uint64_t zero_copy_steps = 0;
     cudaStream_t stream = nullptr;
@@ -632,6 +638,13 @@ extern "C" void ipp_destroy(ipp_engine *e) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->h_status) cudaFreeHost(e->h_status);
+    for (int k = 0; k < IPP_STEP_SLOTS; ++k) {
+        if (e->ev_h2d[k]) cudaEventDestroy(e->ev_h2d[k]);
+        if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
+        if (e->d_actions_slot[k]) cudaFree(e->d_actions_slot[k]);
+        if (e->d_reward_slot[k]) cudaFree(e->d_reward_slot[k]);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -675,6 +688,7 @@ static TiledDims tiled_dims(const ipp_engine *e) {
 static int check_status(ipp_engine *e) {
     // the status word lives in mapped host memory: visible here once the stream has drained
     CU(e, cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < IPP_STEP_SLOTS; ++k) e->slot_busy[k] = false;  // submitted steps run on this stream: drained too
     if (*(volatile int *)e->h_status & 1) {
         *(volatile int *)e->h_status = 0;
         return fail(e, IPP_ERR_UNSUPPORTED,
@@ -1035,6 +1049,55 @@ extern "C" int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *
         CU(e, cudaMemcpyAsync(reward, e->d_reward, B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     if (measurements) CU(e, cudaMemcpyAsync(measurements, e->d_z, B * (size_t)noise_stride * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     return check_status(e);
+}
+
+// Pipelined host steps.  ipp_step_submit(slot) queues {H2D of the ids on the copy stream, the fused kernel on the engine's
+// stream after it, rewards straight into the caller's pinned buffer or a D2H copy} and returns; ipp_step_wait(slot) blocks
+// until that step is complete.  With two slots the host prepares and uploads step t+1 while step t computes.
+extern "C" int ipp_step_submit(ipp_engine *e, int32_t slot, const int32_t *action_ids, float *reward, uint32_t flags) {
+    if (!e) return IPP_ERR_INVALID;
+    if (slot < 0 || slot >= IPP_STEP_SLOTS) return fail(e, IPP_ERR_INVALID, "ipp_step_submit: slot %d outside [0, %d)", slot, IPP_STEP_SLOTS);
+    if (!action_ids) return fail(e, IPP_ERR_INVALID, "ipp_step_submit: action_ids == NULL");
+    if (e->slot_busy[slot]) return fail(e, IPP_ERR_INVALID, "ipp_step_submit: slot %d is still in flight (ipp_step_wait first)", slot);
+    const size_t B = (size_t)e->cfg.batch;
+    int rc;
+    if (!e->copy_stream) {
+        CU(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < IPP_STEP_SLOTS; ++k) {
+            CU(e, cudaEventCreateWithFlags(&e->ev_h2d[k], cudaEventDisableTiming));
+            CU(e, cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
+            if ((rc = dev_alloc(e, &e->d_actions_slot[k], B)) != IPP_OK) return rc;
+            if ((rc = dev_alloc(e, &e->d_reward_slot[k], B)) != IPP_OK) return rc;
+        }
+    }
+    // the slot's id buffer was last read by the kernel of the step waited for before this call: free to overwrite
+    CU(e, cudaMemcpyAsync(e->d_actions_slot[slot], action_ids, B * sizeof(int32_t), cudaMemcpyHostToDevice, e->copy_stream));
+    CU(e, cudaEventRecord(e->ev_h2d[slot], e->copy_stream));
+    CU(e, cudaStreamWaitEvent(e->stream, e->ev_h2d[slot], 0));
+    float *reward_dev = (reward && (e->zero_copy & IPP_ZERO_COPY_REWARDS)) ? (float *)mapped_alias(reward) : nullptr;
+    rc = ipp_step_device(e, e->d_actions_slot[slot], nullptr, nullptr, 0, reward_dev ? reward_dev : e->d_reward_slot[slot], nullptr, flags);
+    if (rc != IPP_OK) return rc;
+    if (reward_dev)
+        e->zero_copy_steps++;
+    else if (reward)
+        CU(e, cudaMemcpyAsync(reward, e->d_reward_slot[slot], B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaEventRecord(e->ev_done[slot], e->stream));
+    e->slot_busy[slot] = true;
+    return IPP_OK;
+}
+
+extern "C" int ipp_step_wait(ipp_engine *e, int32_t slot) {
+    if (!e) return IPP_ERR_INVALID;
+    if (slot < 0 || slot >= IPP_STEP_SLOTS) return fail(e, IPP_ERR_INVALID, "ipp_step_wait: slot %d outside [0, %d)", slot, IPP_STEP_SLOTS);
+    if (!e->slot_busy[slot]) return IPP_OK;
+    CU(e, cudaEventSynchronize(e->ev_done[slot]));
+    e->slot_busy[slot] = false;
+    if (*(volatile int *)e->h_status & 1) {
+        *(volatile int *)e->h_status = 0;
+        return fail(e, IPP_ERR_UNSUPPORTED,
+                    "footprint needs cv2 INTER_AREA with an up-sampling axis (non-square FoV/grid corner case); not supported");
+    }
+    return IPP_OK;
 }
 
 // Measurement only (Sensor.take_measurement, sensors/cameras.py:108-116) and update with a

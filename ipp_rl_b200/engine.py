@@ -357,6 +357,21 @@ class BatchedEngine:
         self._ck(self._lib.ipp_step(self._h, cp(ids), _ptr(poses), _ptr(nz), stride, cp(reward), _ptr(z), fl))
         return (reward, z) if return_measurements else reward
 
+    def step_submit(self, slot: int, action_ids: np.ndarray, out: np.ndarray, reward_mode=capi.REWARD_TRACE, adaptive=False) -> None:
+        """Queue one step (``ipp_step_submit``) and return at once: ``action_ids`` int32 (batch,) and ``out`` float32 (batch,)
+        must stay untouched until ``step_wait(slot)``; use pinned arrays (``torch.Tensor.pin_memory().numpy()``) so that the
+        upload overlaps the running kernel and the rewards land in ``out`` without a copy.  Two slots: submit step t+1
+        before waiting for step t."""
+        if action_ids.dtype != np.int32 or action_ids.shape != (self.batch,) or not action_ids.flags.c_contiguous:
+            raise ValueError(f"action_ids must be a contiguous int32 array of shape ({self.batch},)")
+        if out.dtype != np.float32 or out.shape != (self.batch,) or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a contiguous float32 array of shape ({self.batch},)")
+        cp = self._cptr
+        self._ck(self._lib.ipp_step_submit(self._h, slot, cp(action_ids), cp(out), self._flags(reward_mode, adaptive)))
+
+    def step_wait(self, slot: int) -> None:
+        self._ck(self._lib.ipp_step_wait(self._h, slot))
+
     def measure(self, actions, noise=None, dsize_quirk=True) -> np.ndarray:
         ids, poses = self._split_actions(actions, self.batch)
         nz, stride = self._noise(noise)

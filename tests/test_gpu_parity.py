@@ -353,3 +353,50 @@ def test_zero_copy_host_buffers_are_bit_identical_to_the_copy_path(layout):
     for mode in ("r", "ri"):
         for a, b in zip(results["copy"], results[mode]):
             assert np.array_equal(a, b), mode
+
+
+def test_pipelined_submit_wait_equals_the_synchronous_step():
+    """ipp_step_submit / ipp_step_wait (two slots: upload of step t+1 under the kernel of step t) give the bits of ipp_step;
+    a slot cannot be re-submitted before it has been waited for; status errors surface at the wait."""
+    import torch
+
+    from ipp_rl_b200 import IppError
+
+    params = make_params(64, 64, 1.0, 8, 20, 6)
+    B, T = 768, 7
+    rng = np.random.RandomState(21)
+    gt = np.stack([smooth_field(rng, (64, 64)) for _ in range(8)]).astype(np.float32)[rng.randint(0, 8, B)]
+    ids_all = rng.randint(0, 3 * 64 * 64, (T, B)).astype(np.int32)
+    with _engine(params, B, layout=2, seed=3) as eng:
+        eng.reset()
+        eng.set_ground_truth(gt)
+        ref = np.stack([eng.step(ids_all[t], reward_mode=1).copy() for t in range(T)])
+        ref_state = eng.get_state()
+    with _engine(params, B, layout=2, seed=3) as eng:
+        eng.reset()
+        eng.set_ground_truth(gt)
+        ids_pin = [torch.from_numpy(ids_all[t].copy()).pin_memory().numpy() for t in range(T)]
+        outs = [torch.empty(B, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+        got = np.zeros((T, B), np.float32)
+        for t in range(T):
+            slot = t & 1
+            if t >= 2:
+                eng.step_wait(slot)
+                got[t - 2] = outs[slot]
+            eng.step_submit(slot, ids_pin[t], outs[slot], reward_mode=1)
+            if t == 3:
+                with pytest.raises(IppError):
+                    eng.step_submit(slot, ids_pin[t], outs[slot], reward_mode=1)  # still in flight
+        for t in (T - 2, T - 1):
+            eng.step_wait(t & 1)
+            got[t] = outs[t & 1]
+        assert np.array_equal(got, ref)
+        m, v = eng.get_state()
+        assert np.array_equal(m, ref_state[0]) and np.array_equal(v, ref_state[1])
+        # pageable buffers take the copy path inside the pipeline
+        ids_pg, out_pg = ids_all[0].copy(), np.empty(B, np.float32)
+        eng.step_submit(0, ids_pg, out_pg)
+        eng.step_wait(0)
+        assert np.isfinite(out_pg).all()
+        with pytest.raises(ValueError):
+            eng.step_submit(0, ids_pg.astype(np.int64), out_pg)
