@@ -400,3 +400,32 @@ def test_pipelined_submit_wait_equals_the_synchronous_step():
         assert np.isfinite(out_pg).all()
         with pytest.raises(ValueError):
             eng.step_submit(0, ids_pg.astype(np.int64), out_pg)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("G,B", [(1, 1), (2, 33), (3, 1), (6, 33), (12, 5), (23, 2)])
+def test_edge_grids_and_batches(layout, G, B):
+    """Grids smaller than every footprint (all footprints clipped to the whole map, down to a 1x1 map), batches of 1 and of
+    a warp plus one, action ids (the persistent kernel for layouts 1 / 2): cell-for-cell against the oracle."""
+    params = make_params(G, G, 1.0, 8, 20, 6)
+    cfg = oracle_cfg(params)
+    rng = np.random.RandomState(100 + G)
+    gt = rng.uniform(0, 1, (B, G, G))
+    tbl = orc.enumerate_actions(cfg)
+    seed = 77
+    with _engine(params, B, layout=layout, seed=seed) as eng:
+        eng.reset(0.5, 1.82)
+        eng.set_ground_truth(gt)
+        gt32 = eng.get_ground_truth().astype(np.float64)
+        m32, v32 = eng.get_state()
+        st = orc.BatchState(gt=gt32, mean=m32.astype(np.float64), var=v32.astype(np.float64), prev=np.tile([2.0, 2.0, 14.0], (B, 1)))
+        for t in range(4):
+            ids = rng.randint(0, len(tbl), B).astype(np.int32)
+            r = eng.step(ids, reward_mode=t & 1)
+            ro = orc.batched_full_step(cfg, st, tbl[ids], seed=seed, reward_mode=t & 1)
+            mean, var = eng.get_state()
+            assert _maxerr(mean, st.mean) <= ATOL and _maxerr(var, st.var) <= ATOL, (t, _maxerr(mean, st.mean), _maxerr(var, st.var))
+            assert np.all(np.abs(r - ro) <= RTOL * np.maximum(1.0, np.abs(ro))), (t, np.max(np.abs(r - ro)))
+            st.mean, st.var = mean.astype(np.float64), var.astype(np.float64)
+        jobs = eng.predict(np.zeros(0, np.int32), env_index=np.zeros(0, np.int32), commit=False)  # empty job list
+        assert jobs.shape == (0,)
