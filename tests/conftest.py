@@ -30,6 +30,17 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _cuda_extension_present():
+    """The C-ABI library is git-ignored: a fresh checkout that runs the tests before ``__graft_entry__.build()`` gets it
+    built here (nvcc cross-compiles sm_100a without a GPU).  Never rebuilt when present — the GPU box receives the .so."""
+    from ipp_rl_b200 import build as b
+
+    if not os.path.exists(b.LIB):
+        b.build_extension(force=True)
+    yield
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
