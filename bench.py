@@ -266,6 +266,46 @@ def run_ours(args, rank, world, local_rank):
             barrier()
             pipe_s = time.perf_counter() - t0
             assert np.isfinite(outs2[0]).all() and np.isfinite(outs2[1]).all()
+        else:
+            # N > 1: same idea with the exchange in the pipeline — the rewards all-gather (NCCL) and the D2H of the gathered vector
+            # of step t run on a side stream under the kernel of step t+1; the host waits for step t-1 before reusing its buffers
+            comm = torch.cuda.Stream()
+            ids_dev2 = [torch.empty(B, dtype=torch.int32, device="cuda") for _ in range(2)]
+            rew_dev2 = [torch.empty(B, dtype=torch.float32, device="cuda") for _ in range(2)]
+            gath2 = [torch.empty(world * B, dtype=torch.float32, device="cuda") for _ in range(2)]
+            outs2 = [torch.empty(world * B, dtype=torch.float32).pin_memory() for _ in range(2)]
+            ev_k = [torch.cuda.Event() for _ in range(2)]
+            ev_d = [torch.cuda.Event() for _ in range(2)]
+            used = [False, False]
+
+            def pipe_loop(lo, hi):
+                for t in range(lo, hi):
+                    sl = t & 1
+                    if used[sl]:
+                        ev_d[sl].synchronize()
+                    ids_dev2[sl].copy_(ids_pinned[t % POOL], non_blocking=True)
+                    eng.step_device(action_ids_ptr=ids_dev2[sl].data_ptr(), reward_ptr=rew_dev2[sl].data_ptr(), reward_mode=capi.REWARD_GAUSS_ENTROPY)
+                    ev_k[sl].record(stream)
+                    with torch.cuda.stream(comm):
+                        comm.wait_event(ev_k[sl])
+                        dist.all_gather_into_tensor(gath2[sl], rew_dev2[sl])
+                        outs2[sl].copy_(gath2[sl], non_blocking=True)
+                        ev_d[sl].record(comm)
+                    used[sl] = True
+                for sl in (0, 1):
+                    if used[sl]:
+                        ev_d[sl].synchronize()
+
+            pipe_loop(0, W)
+            barrier()
+            t0 = time.perf_counter()
+            pipe_loop(W, W + KE)
+            barrier()
+            pipe_s = time.perf_counter() - t0
+            tp = torch.tensor([pipe_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            pipe_s = float(tp.item())
+            assert np.isfinite(outs2[0].numpy()).all() and np.isfinite(outs2[1].numpy()).all()
 
     # ---- secondary leg (BASELINE.json configs[3], "C4"): mcts_zero rollouts on the same beliefs.  Lock-step search over
     #      `--mcts-trees` envs, `--mcts-sims` simulations, episode_horizon 5, max_valid_action_distance 11.5 m, uniform
@@ -354,9 +394,11 @@ def run_ours(args, rank, world, local_rank):
                          "mean_cells_per_env_step": cells_timed_total / (B * K), "kernel": "ipp_step_async_kernel" if eng.step_path == "async" else "ipp_step_kernel<MV, KALMAN>", "step_path": eng.step_path},
             "e2e": {"value": world * B * KE / e2e_s, "steps": KE, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * B * world,
                     "d2h_bytes_per_step": 4 * B * world * (world if dist is not None else 1),
-                    "pipelined_value": (B * KE / pipe_s) if pipe_s else None,
-                    "pipelined_path": "ipp_step_submit / ipp_step_wait, 2 slots: same per-step H2D ids + rewards to pinned host memory, upload of "
-                                      "step t+1 under the kernel of step t" if pipe_s else None,
+                    "pipelined_value": (world * B * KE / pipe_s) if pipe_s else None,
+                    "pipelined_path": ("ipp_step_submit / ipp_step_wait, 2 slots: same per-step H2D ids + rewards to pinned host memory, upload of "
+                                       "step t+1 under the kernel of step t") if dist is None else
+                                      ("2 slots: H2D ids -> ipp_step_device; NCCL all_gather(rewards) + D2H of step t on a side stream under the "
+                                       "kernel of step t+1"),
                     "path": ("BatchedEngine.step (ipp_step: pinned host ids -> H2D -> fused kernel -> "
                              + ("rewards written by the kernel into the caller's pinned buffer [zero-copy D2H, 4 B/env over PCIe])"
                                 if zero_copy_steps > 0 else "D2H rewards)")) if dist is None else
