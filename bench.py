@@ -13,6 +13,11 @@ N > 1: launched under torchrun, one rank per GPU, env-batch sharded (weak scalin
 GPU), no data-path collective in `value`; `e2e` adds the per-step NCCL all-gather of the rewards that
 a trainer's experience buffer needs.
 
+`e2e.value` is the synchronous call (host ids in, rewards back on the host before the next step is
+submitted); `e2e.pipelined_value` the same per-step transfers over two slots (ipp_step_submit /
+ipp_step_wait at N = 1; exchange + D2H on a side stream at N > 1).  `mcts_rollouts` is the secondary
+leg at BASELINE.json configs[3]'s per-GPU size (16 384 trees).
+
 `--impl reference` times the CPU port of the reference's algorithm (oracle/; the reference itself
 is pure Python and cannot travel to the GPU box) on all host cores, on a bounded sample.
 """
