@@ -246,3 +246,81 @@ def test_gather_rewards_two_processes_gloo(tmp_path):
     for p, (so, se) in zip(procs, outs):
         assert p.returncode == 0, se[-2000:]
         assert "ok" in so
+
+
+class _OracleRing:
+    """CPU stand-in for ExperienceRing (same methods, NumPy + oracle/experience_oracle.py): lets the host classes that mirror
+    the reference's replay buffers be checked without a GPU.  The CUDA ring itself is checked in tests/test_gpu_experience.py."""
+
+    def __init__(self, states, policies, values, rewards, masks):
+        self.s, self.p, self.v, self.r, self.m = states, policies, values, rewards, masks
+        self.pri = np.ones(len(states), np.float32)
+
+    def __len__(self):
+        return len(self.s)
+
+    def reset_priorities(self):
+        self.pri[:] = np.float32(1.0 / len(self.s))
+
+    def priorities(self):
+        return self.pri.copy()
+
+    def update_priorities(self, idx, pr):
+        self.pri[np.asarray(idx)] = np.asarray(pr, np.float32)
+
+    def sample_indices(self, n, alpha=-1.0, beta=0.0, uniforms=None, seed=0):
+        from oracle import experience_oracle as xo
+
+        if alpha < 0:
+            return xo.uniform_sample(len(self.s), uniforms), np.ones(n, np.float32)
+        return xo.prioritized_sample(self.pri.astype(np.float64), alpha, beta, uniforms)
+
+    def gather(self, indices=None, n=None, shifts=None, with_policy=True):
+        from oracle import experience_oracle as xo
+
+        idx = np.asarray(indices)
+        obs = self.s[idx].copy()
+        if shifts is not None:
+            obs = np.stack([xo.shift_with_replication(o, int(dy), int(dx)) for o, (dy, dx) in zip(obs, np.asarray(shifts))])
+        return obs, self.p[idx], self.m[idx].astype(np.uint8), self.v[idx], self.r[idx]
+
+
+def test_replay_buffer_classes_follow_the_reference_sequence():
+    """Host logic of ExperienceReplayBuffer / PrioritizedExperienceReplayBuffer (sample sizes, beta annealing, augmentation order,
+    return tuple) against the sequence the REAL reference buffer produced (golden_experience.npz), on a CPU stand-in ring."""
+    from ipp_rl_b200.planning.mcts_zero.replay_buffers import ExperienceReplayBuffer, PrioritizedExperienceReplayBuffer
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_experience.npz"))
+
+    class Scripted:
+        def __init__(self, uniforms=(), ints=()):
+            self.u, self.i = list(uniforms), list(ints)
+
+        def random_sample(self, n):
+            return self.u.pop(0)
+
+        def randint(self, lo, hi, size):
+            return np.asarray(self.i.pop(0))
+
+    ring = _OracleRing(g["per_states"], g["per_policies"], g["per_values"], g["per_rewards"], g["per_masks"])
+    rounds = int(g["per_rounds"])
+    buf = PrioritizedExperienceReplayBuffer(ring, batch_size=32, alpha=float(g["per_alpha"]), beta0=0.5, num_epochs=3,
+                                            rng=Scripted(uniforms=[g[f"per{t}_uniforms"] for t in range(rounds)]))
+    assert buf.sample_size == 32 and buf.total_steps == (257 // 32) * 3
+    for t in range(rounds):
+        assert abs(float(buf.beta) - float(g[f"per{t}_beta"])) < 1e-12
+        states, policies, values, rewards, msk, idx, w = buf.sample()
+        assert np.array_equal(idx, g[f"per{t}_indices"]) and np.allclose(w, g[f"per{t}_weights"], rtol=2e-6)
+        assert np.array_equal(states, g[f"per{t}_states"]) and msk.dtype == bool
+        buf.update(idx, g[f"per{t}_new_priorities"])
+        buf.step()
+    assert np.allclose(buf.priorities, g["per_final_priorities"], rtol=1e-6)
+    assert abs(float(buf.beta) - float(g["per_final_beta"])) < 1e-12
+
+    sel = g["aug_sel"]
+    u = (sel + 0.5) / len(ring)  # uniform draws that land on the reference's four samples
+    ubuf = ExperienceReplayBuffer(ring, batch_size=16, num_augmented_samples=3, rng=Scripted(uniforms=[u], ints=[g["aug_offsets"] + 4]))
+    assert ubuf.sample_size == 4
+    states, policies, values, rewards, msk, idx, w = ubuf.sample()
+    assert np.array_equal(idx, sel) and np.array_equal(states, g["aug_states"]) and np.all(w == 1)
+    assert np.array_equal(values, g["aug_values"]) and np.array_equal(policies, g["aug_policies"])
