@@ -150,7 +150,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     B, K, W = args.batch, args.steps, args.warmup
-    layout = {"mv": capi.LAYOUT_MV, "planes": capi.LAYOUT_PLANES, "tiled": capi.LAYOUT_TILED}[args.layout]
+    layout = capi.LAYOUT_NAMES[args.layout]
     stream = torch.cuda.Stream(device=local_rank)
     cfg = EngineConfig(batch=B, layout=layout, device=local_rank, seed=20260925, env_id_offset=rank * B, stream=stream.cuda_stream,
                        **WORKLOAD)
@@ -429,7 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="envs per GPU")
-    ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "tiled"), choices=["planes", "mv", "tiled"])
+    ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "tiled"), choices=["planes", "mv", "tiled", "super"])
     ap.add_argument("--cpu-envs", type=int, default=4096, help="env sample of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=500, help="steps of the host-buffer (e2e) leg (<= --steps)")

@@ -55,6 +55,11 @@ extern "C" {
                                row-major inside a tile.  L2 fetches whole 128 B lines from DRAM, so a footprint pulls in
                                ~1.4x its own bytes instead of ~2.1x with row-major maps.  Internal to the engine: the
                                state / ground-truth entry points still exchange dense [n][y_dim][x_dim] arrays. */
+#define IPP_LAYOUT_SUPER 3  /* 192-byte super-tiles: the {mean,var} float2 of a 4x4-cell tile (128 B) followed by the tile's
+                               16 ground-truth floats (64 B); super-tiles row-major over the map.  The tiles a footprint
+                               touches in one tile row are ONE contiguous run of ~0.6-1.3 KB holding everything the fused
+                               step reads: the persistent step kernel stages it with one cp.async.bulk (TMA) per tile row
+                               and DRAM serves ~1 KB bursts instead of 128-byte lines.  Internal like IPP_LAYOUT_TILED. */
 
 /* ---- cost model (planning/common/actions.py:8-41) ---------------------------------------- */
 #define IPP_COST_DISTANCE 0    /* uav_specifications is None -> Euclidean distance */

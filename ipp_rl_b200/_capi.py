@@ -31,6 +31,8 @@ OBS_COSTS = 256
 LAYOUT_PLANES = 0
 LAYOUT_MV = 1
 LAYOUT_TILED = 2
+LAYOUT_SUPER = 3
+LAYOUT_NAMES = {"planes": LAYOUT_PLANES, "mv": LAYOUT_MV, "tiled": LAYOUT_TILED, "super": LAYOUT_SUPER}
 COST_DISTANCE = 0
 COST_FLIGHT_TIME = 1
 MAX_ALTITUDE_LEVELS = 32

@@ -99,7 +99,8 @@ __global__ void spectrum_scale_kernel(float2 *spec, const float *amp, size_t hal
 }
 
 // one CTA per env: min / max of the field, then (f - min) / (max - min) into the engine's ground-truth layout
-__global__ void __launch_bounds__(256) normalise_kernel(const float *field, float *gt, size_t plane, size_t plane_gt, int X, int txg) {
+__global__ void __launch_bounds__(256) normalise_kernel(const float *field, float *gt, size_t plane, size_t plane_gt, int X, int txg, int ts_gt,
+                                                        int gw_shift) {
     __shared__ float s_min[8], s_max[8];
     const int env = blockIdx.x;
     const float *f = field + (size_t)env * plane;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256) normalise_kernel(const float *field, floa
     float *g = gt + (size_t)env * plane_gt;
     for (size_t i = threadIdx.x; i < plane; i += blockDim.x) {
         const int R = (int)(i / X), C = (int)(i - (size_t)R * X);
-        g[txg > 0 ? (size_t)tiled_gt_index(txg, R, C) : i] = (f[i] - lo) / span;
+        g[txg > 0 ? tiled_gt_index_rt(txg, ts_gt, gw_shift, R, C) : i] = (f[i] - lo) / span;
     }
 }
 
@@ -233,7 +234,7 @@ extern "C" int ipp_generate_ground_truth(ipp_engine *e, double cluster_radius, u
             rc = ipp_internal_fail(e, IPP_ERR_CUDA, "ipp_generate_ground_truth: cufftExecC2R failed");
             break;
         }
-        normalise_kernel<<<n, 256, 0, stream>>>(d_field, const_cast<float *>(p.gt) + (size_t)(first_env + done) * p.plane_gt, plane, p.plane_gt, X, p.txg);
+        normalise_kernel<<<n, 256, 0, stream>>>(d_field, const_cast<float *>(p.gt) + (size_t)(first_env + done) * p.plane_gt, plane, p.plane_gt, X, p.txg, p.ts_gt, p.gw_shift);
         launches += 4;
     }
     cudaError_t s = cudaStreamSynchronize(stream);

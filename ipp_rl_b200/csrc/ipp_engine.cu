@@ -14,6 +14,7 @@
 
 #include "rollout_kernel.cuh"
 #include "step_async.cuh"
+#include "step_bulk.cuh"
 #include "engine_internal.h"
 
 using namespace ipp;
@@ -31,10 +32,13 @@ struct ipp_engine {
     size_t plane_mv = 0;  // cells per env in the belief arrays (TILED: whole 4x4 tiles)
     size_t plane_gt = 0;  // cells per env in the ground-truth array (TILED: whole 8x4 tiles)
     int txm = 0, txg = 0, tiles_y = 0;
+    int ts_mv = 0, ts_gt = 0, gw_shift = 0;  // tile strides of the belief [float2] / ground truth [float], log2 gt tile width
+    bool tiled() const { return cfg.layout == IPP_LAYOUT_TILED || cfg.layout == IPP_LAYOUT_SUPER; }
     // HBM
     float *d_mean = nullptr;  // PLANES: float[B*plane]; MV / TILED: float2[B*plane_mv]
     float *d_var = nullptr;   // PLANES only
     float *d_gt = nullptr;
+    bool gt_aliases_mean = false;  // SUPER: d_gt points into d_mean's allocation
     double *d_prev = nullptr;  // [B][3]
     int *d_status = nullptr;  // device alias of h_status (mapped pinned host word: no copy needed to read it back)
     // staging for the host entry points
@@ -70,6 +74,11 @@ struct ipp_engine {
     int level_tap_mode[kLevelTabs] = {-1, -1, -1, -1};
     size_t async_smem = 0;
     uint64_t path_launches[2] = {0, 0};
+    // bulk-copy persistent path (step_bulk.cuh, IPP_LAYOUT_SUPER)
+    bool bulk_ok = false;
+    int bulk_warps = 0, bulk_ring = 0;
+    size_t bulk_smem = 0;
+    uint64_t bulk_predict_launches = 0;
     unsigned int *d_tickets = nullptr;
     int ticket_parity = 0;
     uint64_t launches = 0;
@@ -132,6 +141,7 @@ __global__ void reset_kernel(float *mean, float *var, int layout, size_t plane, 
     const size_t total = plane * (size_t)batch;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const float pv = prior_var_env ? prior_var_env[i / plane] : prior_var;
+        if (layout == IPP_LAYOUT_SUPER && (i % 24) >= 16) continue;  // the ground-truth third of a super-tile
         if (layout != IPP_LAYOUT_PLANES) {
             reinterpret_cast<float2 *>(mean)[i] = make_float2(prior_mean, pv);
         } else {
@@ -169,14 +179,14 @@ __global__ void mv_pack_kernel(float2 *mv, const float *mean, const float *var, 
 
 // dense [n][Y][X] <-> IPP_LAYOUT_TILED (quad_math.cuh): one thread per dense cell
 struct TiledDims {
-    int X, Y, txm, txg;
+    int X, Y, txm, txg, ts_mv, ts_gt, gw_shift;
     size_t plane, plane_mv, plane_gt;
 };
 __global__ void tiled_unpack_kernel(const float2 *mv, float *mean, float *var, TiledDims d, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t env = i / d.plane;
         const int c = (int)(i - env * d.plane), R = c / d.X, C = c - R * d.X;
-        const float2 t = mv[env * d.plane_mv + tiled_mv_index(d.txm, R, C)];
+        const float2 t = mv[env * d.plane_mv + tiled_mv_index_rt(d.txm, d.ts_mv, R, C)];
         if (mean) mean[i] = t.x;
         if (var) var[i] = t.y;
     }
@@ -185,7 +195,7 @@ __global__ void tiled_pack_kernel(float2 *mv, const float *mean, const float *va
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t env = i / d.plane;
         const int c = (int)(i - env * d.plane), R = c / d.X, C = c - R * d.X;
-        float2 *o = mv + env * d.plane_mv + tiled_mv_index(d.txm, R, C);
+        float2 *o = mv + env * d.plane_mv + tiled_mv_index_rt(d.txm, d.ts_mv, R, C);
         float2 t = *o;
         if (mean) t.x = mean[i];
         if (var) t.y = var[i];
@@ -197,7 +207,7 @@ __global__ void tiled_gt_kernel(float *tiled, float *dense, TiledDims d, size_t 
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t env = i / d.plane;
         const int c = (int)(i - env * d.plane), R = c / d.X, C = c - R * d.X;
-        float *t = tiled + env * d.plane_gt + tiled_gt_index(d.txg, R, C);
+        float *t = tiled + env * d.plane_gt + tiled_gt_index_rt(d.txg, d.ts_gt, d.gw_shift, R, C);
         if (to_tiled)
             *t = dense[i];
         else
@@ -215,8 +225,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 }
 
 // Smooth synthetic field in [0,1]: normalised sum of 6 random plane waves per env.
-__global__ void synth_gt_kernel(float *gt, size_t plane, size_t plane_gt, int X, int txg /* > 0: TILED */, int batch, uint32_t seed,
-                                uint32_t env_off) {
+__global__ void synth_gt_kernel(float *gt, size_t plane, size_t plane_gt, int X, int txg /* > 0: TILED / SUPER */, int ts_gt, int gw_shift,
+                                int batch, uint32_t seed, uint32_t env_off) {
     const int env = blockIdx.y;
     __shared__ float fx[6], fy[6], ph[6], am[6];
     if (threadIdx.x < 6) {
@@ -239,7 +249,7 @@ __global__ void synth_gt_kernel(float *gt, size_t plane, size_t plane_gt, int X,
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 6; ++k) s += am[k] * __sinf(fx[k] * x + fy[k] * y + ph[k]);
-        g[txg > 0 ? (size_t)tiled_gt_index(txg, R, C) : i] = fminf(fmaxf(0.5f + 0.5f * s / norm, 0.0f), 1.0f);
+        g[txg > 0 ? tiled_gt_index_rt(txg, ts_gt, gw_shift, R, C) : i] = fminf(fmaxf(0.5f + 0.5f * s / norm, 0.0f), 1.0f);
     }
 }
 
@@ -296,14 +306,14 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, c
     __shared__ double smem[(kEvalThreads / 32) * 10];
     const int env = blockIdx.x;
     const size_t plane = d.plane;
-    const bool tiled = layout == IPP_LAYOUT_TILED;
+    const bool tiled = layout == IPP_LAYOUT_TILED || layout == IPP_LAYOUT_SUPER;
     const float *g = gt + (size_t)env * d.plane_gt;
     const float *m = mean + (size_t)env * d.plane_mv * (layout != IPP_LAYOUT_PLANES ? 2 : 1);
     const float *v = layout != IPP_LAYOUT_PLANES ? m + 1 : var + (size_t)env * plane;
     const int es = layout != IPP_LAYOUT_PLANES ? 2 : 1;
     // cell i of the dense map -> offsets inside the env's belief / ground-truth arrays
-    auto bi = [&](size_t i) -> size_t { return tiled ? (size_t)tiled_mv_index(d.txm, (int)(i / d.X), (int)(i % d.X)) : i; };
-    auto gi_of = [&](size_t i) -> size_t { return tiled ? (size_t)tiled_gt_index(d.txg, (int)(i / d.X), (int)(i % d.X)) : i; };
+    auto bi = [&](size_t i) -> size_t { return tiled ? tiled_mv_index_rt(d.txm, d.ts_mv, (int)(i / d.X), (int)(i % d.X)) : i; };
+    auto gi_of = [&](size_t i) -> size_t { return tiled ? tiled_gt_index_rt(d.txg, d.ts_gt, d.gw_shift, (int)(i / d.X), (int)(i % d.X)) : i; };
 
     // pass 1: min(gt), min(mean), max(gt), sum(gt)
     double a[4] = {1e300, 1e300, -1e300, 0.0};
@@ -501,6 +511,78 @@ static int setup_async(ipp_engine *e) {
     return IPP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// bulk-copy persistent path (IPP_LAYOUT_SUPER)
+// ------------------------------------------------------------------------------------------------
+typedef void (*bulk_kernel_t)(const BulkParams);
+// bit 0: entropy reward, bit 1: adaptive mask, bit 2: extras (host noise / measurement read-back), bit 3: predict-only
+template <int V>
+static bulk_kernel_t bulk_variant_t() {
+    return ipp_step_bulk_kernel<(V & 8) ? MODE_PREDICT : MODE_KALMAN, (V & 1) != 0, (V & 2) != 0, (V & 4) != 0 && (V & 8) == 0>;
+}
+static bulk_kernel_t bulk_variant(int v) {
+    static const bulk_kernel_t table[16] = {bulk_variant_t<0>(),  bulk_variant_t<1>(),  bulk_variant_t<2>(),  bulk_variant_t<3>(),
+                                            bulk_variant_t<4>(),  bulk_variant_t<5>(),  bulk_variant_t<6>(),  bulk_variant_t<7>(),
+                                            bulk_variant_t<8>(),  bulk_variant_t<9>(),  bulk_variant_t<10>(), bulk_variant_t<11>(),
+                                            bulk_variant_t<8>(),  bulk_variant_t<9>(),  bulk_variant_t<10>(), bulk_variant_t<11>()};
+    return table[v & 15];
+}
+
+static int setup_bulk(ipp_engine *e) {
+    const ipp_config &c = e->cfg;
+    e->bulk_ok = false;
+    if (c.layout != IPP_LAYOUT_SUPER) return IPP_OK;
+    if (c.x_dim > 32767 || c.y_dim > 32767 || e->n_levels > 255) return IPP_OK;  // BulkPlan packs cell coordinates into 16 bits
+    int max_fp = 0;  // bytes of the largest staged footprint at its worst tile alignment
+    for (int k = 0; k < e->n_levels; ++k) {
+        const int fw = std::min(2 * e->lut[k].rx + 1, c.x_dim), fh = std::min(2 * e->lut[k].ry + 1, c.y_dim);
+        if (fw > 255 || fh > 255) return IPP_OK;  // BulkPlan packs footprint sizes into 8 bits
+        const int ntx = std::min(e->txm, (fw + 2) / 4 + 1), ntr = std::min(e->tiles_y, (fh + 2) / 4 + 1);
+        max_fp = std::max(max_fp, ntx * ntr * kSuperTileBytes);
+        const int nqx = (fw + 1) / 2, nqy = (fh + 1) / 2;
+        if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;  // 16-bit magic division of quad indices
+    }
+    int dev_smem = 0;
+    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device) != cudaSuccess) return IPP_OK;
+    const size_t per_warp_fixed = kBulkPlanRing * sizeof(BulkPlan) + kBulkTapFloats2 * sizeof(float2) + kBulkDepth * 8;
+    int warps = kBulkMaxWarps;
+    if (const char *wenv = getenv("IPP_BULK_WARPS")) warps = std::max(1, std::min(kBulkMaxWarps, atoi(wenv)));
+    while (warps > 1 && (size_t)dev_smem / warps < per_warp_fixed + (size_t)max_fp) --warps;
+    if ((size_t)dev_smem / warps < per_warp_fixed + (size_t)max_fp) return IPP_OK;  // footprints too large to stage in shared memory
+    int ring = (int)(((size_t)dev_smem / warps - per_warp_fixed) / 16 * 16);
+    if (const char *renv = getenv("IPP_BULK_RING")) ring = std::max(max_fp, std::min(ring, atoi(renv) / 16 * 16));
+    e->bulk_warps = warps;
+    e->bulk_ring = ring;
+    e->bulk_smem = (size_t)warps * ((size_t)ring + per_warp_fixed);
+    for (int v = 0; v < 12; ++v)
+        if (cudaFuncSetAttribute(bulk_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->bulk_smem) != cudaSuccess) {
+            cudaGetLastError();
+            return IPP_OK;
+        }
+    e->bulk_ok = true;
+    return IPP_OK;
+}
+
+static int launch_bulk(ipp_engine *e, const StepParams &p, bool predict) {
+    BulkParams bp;
+    bp.base = p;
+    bp.tickets = e->d_tickets;
+    bp.parity = e->ticket_parity;
+    bp.warps = e->bulk_warps;
+    bp.ring_bytes = e->bulk_ring;
+    const int needed = (p.n_jobs + e->bulk_warps - 1) / e->bulk_warps;
+    const int grid = std::max(1, std::min(e->sm_count, needed));
+    const int variant = (((p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY) ? 1 : 0) | ((p.flags & IPP_FLAG_ADAPTIVE) ? 2 : 0) |
+                        ((!predict && (p.noise != nullptr || p.z_out != nullptr)) ? 4 : 0) | (predict ? 8 : 0);
+    bulk_variant(variant)<<<grid, e->bulk_warps * 32, e->bulk_smem, e->stream>>>(bp);
+    e->ticket_parity ^= 1;
+    e->launches++;
+    e->path_launches[IPP_PATH_ASYNC]++;
+    if (predict) e->bulk_predict_launches++;
+    CU(e, cudaGetLastError());
+    return IPP_OK;
+}
+
 static int launch_async(ipp_engine *e, const StepParams &p) {
     AsyncParams ap;
     ap.base = p;
@@ -527,7 +609,7 @@ static int launch_async(ipp_engine *e, const StepParams &p) {
 
 // the path a Kalman step on action ids takes right now
 static int effective_path(const ipp_engine *e) {
-    if (e->step_path != IPP_PATH_LSU && e->async_ok) return IPP_PATH_ASYNC;
+    if (e->step_path != IPP_PATH_LSU && (e->async_ok || e->bulk_ok)) return IPP_PATH_ASYNC;
     return IPP_PATH_LSU;
 }
 
@@ -545,7 +627,7 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
     if (!(cfg->resolution > 0)) return fail(nullptr, IPP_ERR_INVALID, "ipp_create: environment.resolution must be > 0");
     if (!(cfg->angle_x_deg > 0 && cfg->angle_x_deg < 180 && cfg->angle_y_deg > 0 && cfg->angle_y_deg < 180))
         return fail(nullptr, IPP_ERR_INVALID, "ipp_create: field_of_view angles must be in (0, 180)");
-    if (cfg->layout != IPP_LAYOUT_PLANES && cfg->layout != IPP_LAYOUT_MV && cfg->layout != IPP_LAYOUT_TILED)
+    if (cfg->layout != IPP_LAYOUT_PLANES && cfg->layout != IPP_LAYOUT_MV && cfg->layout != IPP_LAYOUT_TILED && cfg->layout != IPP_LAYOUT_SUPER)
         return fail(nullptr, IPP_ERR_INVALID, "ipp_create: unknown layout %d", cfg->layout);
     if (cfg->cost_mode != IPP_COST_DISTANCE && cfg->cost_mode != IPP_COST_FLIGHT_TIME)
         return fail(nullptr, IPP_ERR_INVALID, "ipp_create: unknown cost_mode %d", cfg->cost_mode);
@@ -568,6 +650,17 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         e->tiles_y = (cfg->y_dim + 3) / 4;
         e->plane_mv = (size_t)e->tiles_y * e->txm * 16;
         e->plane_gt = (size_t)e->tiles_y * e->txg * 32;
+        e->ts_mv = 16;
+        e->ts_gt = 32;
+        e->gw_shift = 3;
+    } else if (cfg->layout == IPP_LAYOUT_SUPER) {  // one array: 192-byte super-tiles {mean,var} x 16 | gt x 16
+        e->txm = e->txg = (cfg->x_dim + 3) / 4;
+        e->tiles_y = (cfg->y_dim + 3) / 4;
+        e->plane_mv = (size_t)e->tiles_y * e->txm * 24;  // float2 units
+        e->plane_gt = (size_t)e->tiles_y * e->txm * 48;  // float units
+        e->ts_mv = 24;
+        e->ts_gt = 48;
+        e->gw_shift = 2;
     }
 
     auto bail = [&](int rc) {
@@ -603,7 +696,12 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         if ((rc = dev_alloc(e, &e->d_mean, cells)) != IPP_OK) return bail(rc);
         if ((rc = dev_alloc(e, &e->d_var, cells)) != IPP_OK) return bail(rc);
     }
-    if ((rc = dev_alloc(e, &e->d_gt, cells_gt)) != IPP_OK) return bail(rc);
+    if (cfg->layout == IPP_LAYOUT_SUPER) {
+        e->d_gt = e->d_mean + 32;  // the ground-truth third of super-tile 0 (same allocation)
+        e->gt_aliases_mean = true;
+        cudaMemsetAsync(e->d_mean, 0, 2 * cells * sizeof(float), e->stream);
+    } else if ((rc = dev_alloc(e, &e->d_gt, cells_gt)) != IPP_OK)
+        return bail(rc);
     if (cfg->layout == IPP_LAYOUT_TILED) {  // padding cells of partial tiles are staged (never used): keep them finite
         cudaMemsetAsync(e->d_gt, 0, cells_gt * sizeof(float), e->stream);
         cudaMemsetAsync(e->d_mean, 0, 2 * cells * sizeof(float), e->stream);
@@ -622,6 +720,7 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         if (strchr(zc, 'i')) e->zero_copy |= IPP_ZERO_COPY_IDS;
     }
     if ((rc = setup_async(e)) != IPP_OK) return bail(rc);
+    if ((rc = setup_bulk(e)) != IPP_OK) return bail(rc);
     if (const char *sp = getenv("IPP_STEP_PATH")) {
         if (!strcmp(sp, "lsu")) e->step_path = IPP_PATH_LSU;
         if (!strcmp(sp, "async")) e->step_path = IPP_PATH_ASYNC;
@@ -633,7 +732,7 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
 extern "C" void ipp_destroy(ipp_engine *e) {
     if (!e) return;
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *ptrs[] = {e->d_mean, e->d_var, e->d_gt, e->d_prev, e->d_actions, e->d_poses, e->d_prev_in, e->d_env_index,
+    void *ptrs[] = {e->d_mean, e->d_var, e->gt_aliases_mean ? nullptr : e->d_gt, e->d_prev, e->d_actions, e->d_poses, e->d_prev_in, e->d_env_index,
                     e->d_reward, e->d_noise, e->d_z, e->d_metrics, e->d_scratch, e->d_tickets, e->d_level_taps};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -679,6 +778,9 @@ static TiledDims tiled_dims(const ipp_engine *e) {
     d.Y = e->cfg.y_dim;
     d.txm = e->txm;
     d.txg = e->txg;
+    d.ts_mv = e->ts_mv;
+    d.ts_gt = e->ts_gt;
+    d.gw_shift = e->gw_shift;
     d.plane = e->plane;
     d.plane_mv = e->plane_mv;
     d.plane_gt = e->plane_gt;
@@ -762,7 +864,7 @@ extern "C" int ipp_set_ground_truth(ipp_engine *e, const float *gt, int32_t firs
     int rc = check_range(e, first_env, n_env, "ipp_set_ground_truth");
     if (rc != IPP_OK) return rc;
     if (n_env == 0) return IPP_OK;
-    if (e->cfg.layout == IPP_LAYOUT_TILED) return gt_transfer_tiled(e, const_cast<float *>(gt), first_env, n_env, src_is_device, true);
+    if (e->tiled()) return gt_transfer_tiled(e, const_cast<float *>(gt), first_env, n_env, src_is_device, true);
     CU(e, cudaMemcpyAsync(e->d_gt + (size_t)first_env * e->plane, gt, (size_t)n_env * e->plane * sizeof(float),
                           src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
@@ -774,7 +876,7 @@ extern "C" int ipp_get_ground_truth(ipp_engine *e, float *gt, int32_t first_env,
     int rc = check_range(e, first_env, n_env, "ipp_get_ground_truth");
     if (rc != IPP_OK) return rc;
     if (n_env == 0) return IPP_OK;
-    if (e->cfg.layout == IPP_LAYOUT_TILED) return gt_transfer_tiled(e, gt, first_env, n_env, dst_is_device, false);
+    if (e->tiled()) return gt_transfer_tiled(e, gt, first_env, n_env, dst_is_device, false);
     CU(e, cudaMemcpyAsync(gt, e->d_gt + (size_t)first_env * e->plane, (size_t)n_env * e->plane * sizeof(float),
                           dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
@@ -789,12 +891,12 @@ extern "C" int ipp_synth_ground_truth(ipp_engine *e, uint64_t seed) {
         for (int first = 0; first < e->cfg.batch; first += 65535) {
             const int n = std::min(65535, e->cfg.batch - first);
             dim3 g2(grid.x, (unsigned)n);
-            synth_gt_kernel<<<g2, 256, 0, e->stream>>>(e->d_gt + (size_t)first * e->plane_gt, e->plane, e->plane_gt, e->cfg.x_dim, e->txg, n,
+            synth_gt_kernel<<<g2, 256, 0, e->stream>>>(e->d_gt + (size_t)first * e->plane_gt, e->plane, e->plane_gt, e->cfg.x_dim, e->txg, e->ts_gt, e->gw_shift, n,
                                                        (uint32_t)seed, (uint32_t)(e->cfg.env_id_offset + first));
             e->launches++;
         }
     } else {
-        synth_gt_kernel<<<grid, 256, 0, e->stream>>>(e->d_gt, e->plane, e->plane_gt, e->cfg.x_dim, e->txg, e->cfg.batch, (uint32_t)seed,
+        synth_gt_kernel<<<grid, 256, 0, e->stream>>>(e->d_gt, e->plane, e->plane_gt, e->cfg.x_dim, e->txg, e->ts_gt, e->gw_shift, e->cfg.batch, (uint32_t)seed,
                                                      (uint32_t)e->cfg.env_id_offset);
         e->launches++;
     }
@@ -819,7 +921,7 @@ extern "C" int ipp_get_state(ipp_engine *e, float *mean, float *var, int32_t fir
             dm = mean ? e->d_scratch : nullptr;
             dv = var ? e->d_scratch + n : nullptr;
         }
-        if (e->cfg.layout == IPP_LAYOUT_TILED)
+        if (e->tiled())
             tiled_unpack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(
                 reinterpret_cast<const float2 *>(e->d_mean) + (size_t)first_env * e->plane_mv, dm, dv, tiled_dims(e), n);
         else
@@ -857,7 +959,7 @@ extern "C" int ipp_set_state(ipp_engine *e, const float *mean, const float *var,
                 dv = e->d_scratch + n;
             }
         }
-        if (e->cfg.layout == IPP_LAYOUT_TILED)
+        if (e->tiled())
             tiled_pack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(
                 reinterpret_cast<float2 *>(e->d_mean) + (size_t)first_env * e->plane_mv, dm, dv, tiled_dims(e), n);
         else
@@ -895,6 +997,9 @@ static void fill_params(const ipp_engine *e, StepParams &p) {
     p.plane_gt = e->plane_gt;
     p.txm = e->txm;
     p.txg = e->txg;
+    p.ts_mv = e->ts_mv;
+    p.ts_gt = e->ts_gt;
+    p.gw_shift = e->gw_shift;
     p.X = c.x_dim;
     p.Y = c.y_dim;
     p.batch = c.batch;
@@ -930,6 +1035,8 @@ static void launch_mode(ipp_engine *e, const StepParams &p) {
     const int blocks = (p.n_jobs + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (e->cfg.layout == IPP_LAYOUT_TILED)
         ipp_step_kernel<IPP_LAYOUT_TILED, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
+    else if (e->cfg.layout == IPP_LAYOUT_SUPER)
+        ipp_step_kernel<IPP_LAYOUT_SUPER, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
     else if (e->cfg.layout == IPP_LAYOUT_MV)
         ipp_step_kernel<IPP_LAYOUT_MV, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
     else
@@ -973,7 +1080,7 @@ extern "C" int ipp_step_device(ipp_engine *e, const int32_t *action_ids, const d
     p.flags = flags;
     const int path = (action_ids != nullptr && (flags & (IPP_FLAG_LOGODDS | IPP_FLAG_NO_COMMIT)) == 0) ? effective_path(e) : IPP_PATH_LSU;
     if (path == IPP_PATH_ASYNC)
-        rc = launch_async(e, p);
+        rc = e->bulk_ok ? launch_bulk(e, p, false) : launch_async(e, p);
     else {
         rc = launch_step(e, p, (flags & IPP_FLAG_LOGODDS) ? MODE_LOGODDS : MODE_KALMAN);
         e->path_launches[IPP_PATH_LSU]++;
@@ -1175,7 +1282,12 @@ extern "C" int ipp_predict_device(ipp_engine *e, int32_t n_jobs, const int32_t *
     p.prev_in = prev_poses;
     p.reward = reward;
     p.flags = flags;
-    return launch_step(e, p, MODE_PREDICT);
+    // whole-batch prediction steps on action ids (the rollout loop of the planners) take the persistent path
+    if (!env_index && action_ids && e->bulk_ok && effective_path(e) == IPP_PATH_ASYNC && (flags & IPP_FLAG_LOGODDS) == 0)
+        return launch_bulk(e, p, true);
+    rc = launch_step(e, p, MODE_PREDICT);
+    if (rc == IPP_OK) e->path_launches[IPP_PATH_LSU]++;
+    return rc;
 }
 
 extern "C" int ipp_predict(ipp_engine *e, int32_t n_jobs, const int32_t *env_index, const int32_t *action_ids, const double *poses,
@@ -1226,6 +1338,7 @@ extern "C" int ipp_rollout_device(ipp_engine *e, int32_t n_jobs, int32_t horizon
     rp.tile_floats = cells;
     const size_t smem = (size_t)kRolloutWarps * (horizon - 1) * cells * sizeof(float);
     void (*kern)(const RolloutParams) = e->cfg.layout == IPP_LAYOUT_TILED ? ipp_rollout_kernel<IPP_LAYOUT_TILED>
+                                        : e->cfg.layout == IPP_LAYOUT_SUPER ? ipp_rollout_kernel<IPP_LAYOUT_SUPER>
                                         : e->cfg.layout == IPP_LAYOUT_MV  ? ipp_rollout_kernel<IPP_LAYOUT_MV>
                                                                           : ipp_rollout_kernel<IPP_LAYOUT_PLANES>;
     if (smem > 48 * 1024) {

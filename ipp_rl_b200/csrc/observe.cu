@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kObsThreads) observe_kernel(const __grid_const
     const int j = blockIdx.x, env = op.first_env + j;
     const int X = p.X, Y = p.Y;
     const size_t N = (size_t)X * Y;
-    const bool planes_layout = op.layout == IPP_LAYOUT_PLANES, tiled = op.layout == IPP_LAYOUT_TILED;
+    const bool planes_layout = op.layout == IPP_LAYOUT_PLANES, tiled = op.layout == IPP_LAYOUT_TILED || op.layout == IPP_LAYOUT_SUPER;
     const float *mean_pl = p.mean + (size_t)env * p.plane, *var_pl = p.var + (size_t)env * p.plane;
     const float2 *mv = reinterpret_cast<const float2 *>(p.mean) + (size_t)env * p.plane;
     auto load = [&](size_t i, float &m, float &v) {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kObsThreads) observe_kernel(const __grid_const
             v = var_pl[i];
         } else {
             const int R = (int)(i / X), C = (int)(i - (size_t)R * X);
-            const float2 t = mv[tiled ? (size_t)tiled_mv_index(p.txm, R, C) : i];
+            const float2 t = mv[tiled ? tiled_mv_index_rt(p.txm, p.ts_mv, R, C) : i];
             m = t.x;
             v = t.y;
         }

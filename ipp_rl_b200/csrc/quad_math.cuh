@@ -41,7 +41,9 @@ struct StepParams {
     const float *gt;
     size_t plane;     // cells per env in the belief arrays (y_dim * x_dim; TILED: padded to whole 4x4 tiles)
     size_t plane_gt;  // cells per env in the ground-truth array (TILED: padded to whole 8x4 tiles)
-    int txm, txg;     // TILED: tiles per tile-row of the belief (ceil(X/4)) and of the ground truth (ceil(X/8))
+    int txm, txg;     // TILED / SUPER: tiles per tile-row of the belief (ceil(X/4)) and of the ground truth (ceil(X/8); SUPER: = txm)
+    int ts_mv, ts_gt; // TILED / SUPER: tile stride of the belief [float2] (16 / 24) and of the ground truth [float] (32 / 48)
+    int gw_shift;     // TILED / SUPER: log2 of the ground-truth tile width (3 / 2)
     int X, Y;
     int n_jobs;
     int batch;
@@ -157,6 +159,21 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 //   tiles row-major over the map, cells row-major inside a tile.
 __device__ __forceinline__ int tiled_mv_index(int txm, int R, int C) { return (((R >> 2) * txm + (C >> 2)) << 4) + ((R & 3) << 2) + (C & 3); }
 __device__ __forceinline__ int tiled_gt_index(int txg, int R, int C) { return (((R >> 2) * txg + (C >> 3)) << 5) + ((R & 3) << 3) + (C & 7); }
+// IPP_LAYOUT_SUPER: one 192-byte super-tile per 4 x 4 cells = [16 x float2 {mean,var} | 16 x float gt], super-tiles row-major
+// over the map: the tiles a footprint touches in one tile row are ONE contiguous run of ntx * 192 bytes holding everything the
+// fused step needs (belief and ground truth), i.e. one bulk copy (cp.async.bulk) per tile row and ~1 KB DRAM bursts.
+// The belief index is in float2 units (24 per super-tile), the ground-truth index in floats relative to base + 32 floats
+// (48 per super-tile).
+constexpr int kSuperTileBytes = 192;
+__device__ __forceinline__ int super_mv_index(int tx, int R, int C) { return ((R >> 2) * tx + (C >> 2)) * 24 + ((R & 3) << 2) + (C & 3); }
+__device__ __forceinline__ int super_gt_index(int tx, int R, int C) { return ((R >> 2) * tx + (C >> 2)) * 48 + ((R & 3) << 2) + (C & 3); }
+// run-time forms for the streaming kernels (layout TILED or SUPER; strides from StepParams / TiledDims)
+__device__ __forceinline__ size_t tiled_mv_index_rt(int txm, int ts_mv, int R, int C) {
+    return (size_t)((R >> 2) * txm + (C >> 2)) * ts_mv + ((R & 3) << 2) + (C & 3);
+}
+__device__ __forceinline__ size_t tiled_gt_index_rt(int txg, int ts_gt, int gw_shift, int R, int C) {
+    return (size_t)((R >> 2) * txg + (C >> gw_shift)) * ts_gt + ((R & 3) << gw_shift) + (C & ((1 << gw_shift) - 1));
+}
 
 // ---------------------------------------------------------------------------------------------
 // per-job geometry (footprint, sensor model) — computed redundantly by every lane (SIMT: one
@@ -332,6 +349,12 @@ struct GtTiled {  // global memory, IPP_LAYOUT_TILED; g points at the env's plan
     const float *g;
     int txg, yu, xl;
     __device__ __forceinline__ float at(int r, int c) const { return __ldg(g + tiled_gt_index(txg, yu + r, xl + c)); }
+};
+
+struct GtSuper {  // global memory, IPP_LAYOUT_SUPER; g points at the env's plane (+ 32 floats)
+    const float *g;
+    int tx, yu, xl;
+    __device__ __forceinline__ float at(int r, int c) const { return __ldg(g + super_gt_index(tx, yu + r, xl + c)); }
 };
 
 template <class G>

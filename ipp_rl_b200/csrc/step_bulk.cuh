@@ -1,0 +1,499 @@
+// step_bulk.cuh — the throughput path of the fused step on IPP_LAYOUT_SUPER (sm_100a): a persistent kernel whose warps
+// stage whole footprints in shared memory with bulk asynchronous copies (cp.async.bulk / UBLKCP, the TMA unit's 1-D form)
+// completed through mbarriers.
+//
+// Layout (quad_math.cuh): one 192-byte super-tile per 4 x 4 cells = [16 x {mean,var} | 16 x gt].  The tiles a footprint
+// touches in one tile row are one contiguous run of ntx * 192 bytes, so a 23 x 23 footprint is 6-7 bulk copies of ~1.2 KB
+// (issued by ONE lane, no per-lane address arithmetic, no registers held) where the cp.async kernel (step_async.cuh) issues
+// ~460 16-byte copies from all lanes, and DRAM serves ~1 KB bursts instead of isolated 128-byte lines.  Shared memory keeps
+// the layout of the run, so one tile-local index serves the staged read and the HBM write-back of a quad.
+//
+// Per warp: a byte ring in shared memory holding up to kBulkDepth footprints in flight (small footprints -> deeper
+// prefetch), one mbarrier per in-flight footprint, a ring of 32-byte plans (everything warp-uniform about an env-step is
+// computed once, by one lane, when the warp takes a chunk of tickets: lane i plans ticket base + i).  No block-level
+// synchronisation in the loop.  Work distribution: global ticket counter, guided self-scheduling (as step_async.cuh).
+//
+// INTER_AREA (rf = 2) on unscrambled odd footprints needs no tap tables: output o of n integrates inputs {2o-1, 2o, 2o+1}
+// with weights {o, n, n-1-o} / (2n-1) — the quad's own 2 x 2 cells plus the row above and the column to the left; the
+// weights are formed exactly as make_tap_entry() forms them, so the result is bit-identical to the table path of the
+// general kernel.  Clipped non-square footprints (dsize quirk) take the table path.
+//
+//   grid = #SMs (persistent, 1 CTA / SM), block = up to 16 warps, dynamic smem ~ 227 KB
+//   smem = [warp] byte ring | [warp] plan ring | [warp] tap tables | [warp] mbarriers
+#pragma once
+#include "step_kernel.cuh"
+
+namespace ipp {
+
+#ifndef IPP_BULK_MAX_WARPS
+#define IPP_BULK_MAX_WARPS 16
+#endif
+#ifndef IPP_BULK_DEPTH
+#define IPP_BULK_DEPTH 4  // footprints in flight per warp (power of two)
+#endif
+#ifndef IPP_BULK_CHUNK
+#define IPP_BULK_CHUNK 8
+#endif
+#ifndef IPP_BULK_GUIDE
+#define IPP_BULK_GUIDE 3
+#endif
+#ifndef IPP_BULK_ENDGAME_DEPTH
+#define IPP_BULK_ENDGAME_DEPTH 2  // in-flight footprints per warp once the chunks have shrunk to one ticket
+#endif
+constexpr int kBulkMaxWarps = IPP_BULK_MAX_WARPS;
+constexpr int kBulkDepth = IPP_BULK_DEPTH;
+constexpr int kBulkChunk = IPP_BULK_CHUNK;
+constexpr int kBulkPlanRing = 16;  // live plans per warp: <= kBulkDepth in flight + <= 3 queued + a fresh chunk of <= 8
+constexpr int kBulkTapFloats2 = 2 * kTapCap * 3;
+static_assert((kBulkDepth & (kBulkDepth - 1)) == 0 && kBulkDepth >= 2 && kBulkDepth <= 8, "depth");
+static_assert(kBulkDepth + 3 + kBulkChunk <= kBulkPlanRing, "plan ring too small");
+
+struct BulkParams {
+    StepParams base;
+    unsigned int *tickets;  // [2] ping-pong work counters
+    int parity;             // counter consumed by this launch; the other one is zeroed for the next
+    int warps;              // warps per CTA
+    int ring_bytes;         // per-warp staging ring (multiple of 16, >= the largest footprint)
+};
+
+// Per-env plan (32 B in shared memory), written by the planning lane; ring_off by the lane that starts the copies.
+struct __align__(16) BulkPlan {
+    int job;          // < 0: out of work
+    int geo;          // xl | yu << 16
+    int dims;         // nx | ny << 8 | nqx << 16 | nqy << 24
+    int tiles;        // ntx | ntr << 8 | lvl << 16 | flags << 24   (flags: 1 rf == 2, 2 analytic INTER_AREA taps, 4 unsupported)
+    int magic_x;      // floor(65536 / nqx) + 1
+    float inv_cost1;  // 1 / (cost + 1)
+    int ring_off;     // byte offset of the staged footprint in the warp's ring
+    int outs;         // out_r | out_c << 8
+};
+static_assert(sizeof(BulkPlan) == 32, "BulkPlan layout");
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (src / dst 16-byte aligned, bytes % 16 == 0), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+
+// staged ground truth of a footprint (super-tile runs in shared memory); (r, c) relative to the footprint's top-left cell
+struct GtSuperShared {
+    uint32_t base;  // shared address of the slot
+    int ntx, a, b;  // tiles per staged tile row; xl & 3; yu & 3
+    __device__ __forceinline__ float at(int r, int c) const {
+        const int rr = b + r, cc = a + c;
+        return lds32(base + (uint32_t)(((rr >> 2) * ntx + (cc >> 2)) * kSuperTileBytes + 128 + ((rr & 3) << 4) + ((cc & 3) << 2)));
+    }
+};
+
+// Plan one env-step (one lane).  Also advances the env's stored previous action (when the step commits and KEEP_PREV is
+// off) and raises the status word for footprints the INTER_AREA path cannot serve.
+template <int MODE>
+__device__ __forceinline__ void bulk_plan_env(const StepParams &p, bool quirk, bool write_prev, int job, BulkPlan *out) {
+    if (job < 0) {
+        out->job = -1;
+        return;
+    }
+    const int id = __ldg(p.action_ids + job);
+    double *ps = p.prev_state + 3 * (size_t)job;
+    const double *pv = (MODE == MODE_PREDICT && p.prev_in != nullptr) ? p.prev_in + 3 * (size_t)job : ps;
+    const double q0 = pv[0], q1 = pv[1], q2 = pv[2];
+    int lvl, col, row;
+    decode_id(p, id, lvl, col, row);
+    const AltLevel &L = p.lut[lvl];
+    const int xl = max(col - L.rx, 0), xr = min(col + L.rx, p.X - 1);
+    const int yu = max(row - L.ry, 0), yd = min(row + L.ry, p.Y - 1);
+    const int nx = xr - xl + 1, ny = yd - yu + 1;
+    const int nqx = (nx + 1) >> 1, nqy = (ny + 1) >> 1;
+    const int out_r = quirk ? nqx : nqy, out_c = quirk ? nqy : nqx;
+    const int ntx = (xr >> 2) - (xl >> 2) + 1, ntr = (yd >> 2) - (yu >> 2) + 1;
+    int flags = 0;
+    if (L.rf == 2) {
+        flags |= 1;
+        if (MODE != MODE_PREDICT) {
+            if (out_r > ny || out_c > nx) flags |= 4;
+            // D[pr, pc] = D[qy, qx] and both axes decimate 2n-1 -> n: the quad's own cells + the row above / column to the left
+            if ((nx & 1) && (ny & 1) && out_r == nqy && out_c == nqx) flags |= 2;
+        }
+    }
+    const int magic_x = (int)((uint32_t)(65536.0f * fast_rcp((float)nqx) * 1.00000012f) + 1u);
+    const double px = __dadd_rn(__dmul_rn(p.res, (double)col), __dmul_rn(0.5, p.res));
+    const double py = __dadd_rn(__dmul_rn(p.res, (double)row), __dmul_rn(0.5, p.res));
+    const float cost = job_cost(p, px, py, L.alt, q0, q1, q2);
+    if (write_prev) {
+        ps[0] = px;
+        ps[1] = py;
+        ps[2] = L.alt;
+    }
+    if (flags & 4) *(volatile int *)p.status = 1;  // mapped host word, bit 0 is the only bit
+    int4 *o = reinterpret_cast<int4 *>(out);
+    o[0] = make_int4(job, xl | (yu << 16), nx | (ny << 8) | (nqx << 16) | (nqy << 24), ntx | (ntr << 8) | (lvl << 16) | (flags << 24));
+    o[1] = make_int4(magic_x, __float_as_int(fast_rcp(cost + 1.0f)), 0, out_r | (out_c << 8));
+}
+
+// MODE: MODE_KALMAN (full step) or MODE_PREDICT (covariance only: no ground truth, no noise; the staged run still carries
+// both).  ENTROPY / ADAPTIVE: reward variant and adaptive mask; EXTRAS: host-supplied noise and measurement read-back.
+template <int MODE, bool ENTROPY, bool ADAPTIVE, bool EXTRAS>
+__global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(const __grid_constant__ BulkParams bp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const StepParams &p = bp.base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned char *after = smem_raw + (size_t)bp.warps * bp.ring_bytes;
+    BulkPlan *plans = reinterpret_cast<BulkPlan *>(after) + w * kBulkPlanRing;
+    float2 *taps = reinterpret_cast<float2 *>(after + (size_t)bp.warps * kBulkPlanRing * sizeof(BulkPlan)) + (size_t)w * kBulkTapFloats2;
+    const uint32_t bars = smem_addr(after + (size_t)bp.warps * (kBulkPlanRing * sizeof(BulkPlan) + kBulkTapFloats2 * sizeof(float2))) +
+                          (uint32_t)(w * kBulkDepth * 8);
+    const uint32_t ring = smem_addr(smem_raw) + (uint32_t)(w * bp.ring_bytes);
+    const int cap = bp.ring_bytes;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kBulkDepth; ++k) mbar_init(bars + 8u * k, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    unsigned int *ticket = bp.tickets + bp.parity;
+    if (blockIdx.x == 0 && threadIdx.x == 0) bp.tickets[bp.parity ^ 1] = 0u;  // for the next launch
+
+    const int n_jobs = p.n_jobs;
+    const bool quirk = (p.flags & IPP_FLAG_NO_DSIZE_QUIRK) == 0;
+    const bool commit = (p.flags & IPP_FLAG_NO_COMMIT) == 0;
+    const bool write_prev = commit && (p.flags & IPP_FLAG_KEEP_PREV) == 0;
+    const int txs = p.txm;
+    const unsigned char *plane0 = reinterpret_cast<const unsigned char *>(p.mean);
+    const size_t env_bytes = p.plane * sizeof(float2);
+
+    // ---- plan ring: [c_pos, f_pos) staged (in flight), [f_pos, q_tail) planned, not yet staged ------------------------
+    int c_pos = 0, f_pos = 0, q_tail = 0;
+    int n_if = 0, n_wait = 0;  // staged / planned-not-staged
+    unsigned int fi = 0, ci = 0;  // staged / consumed so far (mbarrier slot and phase)
+    int r_head = 0, r_tail = 0;   // byte ring: oldest staged footprint / next free byte
+    int max_if = kBulkDepth;
+
+    auto plan_chunk = [&](unsigned int base, int cnt) {  // lane i plans ticket base + i
+        if (lane < cnt) {
+            const unsigned int t = base + (unsigned)lane;
+            bulk_plan_env<MODE>(p, quirk, write_prev, t < (unsigned)n_jobs ? (int)t : -1, plans + ((q_tail + lane) & (kBulkPlanRing - 1)));
+        }
+        q_tail = (q_tail + cnt) & (kBulkPlanRing - 1);
+        n_wait += cnt;
+        __syncwarp();
+    };
+
+    // Stage the next planned footprint if the ring has room for it (warp-uniform; lane 0 issues the copies).
+    auto try_fill = [&]() -> bool {
+        if (n_wait == 0 || n_if >= max_if) return false;
+        BulkPlan *pl = plans + f_pos;
+        const int4 a = *reinterpret_cast<const int4 *>(pl);
+        int off = r_tail;
+        if (a.x >= 0) {
+            const int ntx = a.w & 255, ntr = (a.w >> 8) & 255;
+            const int row_bytes = ntx * kSuperTileBytes, bytes = ntr * row_bytes;
+            off = -1;
+            if (n_if == 0)
+                off = 0;
+            else if (r_tail > r_head) {
+                if (r_tail + bytes <= cap)
+                    off = r_tail;
+                else if (bytes <= r_head)
+                    off = 0;
+            } else if (r_tail < r_head) {
+                if (r_tail + bytes <= r_head) off = r_tail;
+            }
+            if (off < 0) return false;
+            if (lane == 0) {
+                const int xl = a.y & 0xffff, yu = a.y >> 16;
+                const uint32_t bar = bars + 8u * (fi & (kBulkDepth - 1));
+                const unsigned char *src = plane0 + (size_t)a.x * env_bytes + (size_t)((yu >> 2) * txs + (xl >> 2)) * kSuperTileBytes;
+                uint32_t dst = ring + (uint32_t)off;
+                mbar_expect_tx(bar, (uint32_t)bytes);
+#pragma unroll 1
+                for (int k = 0; k < ntr; ++k) {
+                    bulk_g2s(dst, src, (uint32_t)row_bytes, bar);
+                    src += (size_t)txs * kSuperTileBytes;
+                    dst += (uint32_t)row_bytes;
+                }
+                pl->ring_off = off;
+            }
+            if (n_if == 0) r_head = off;
+            r_tail = off + bytes;
+        }
+        ++fi;
+        f_pos = (f_pos + 1) & (kBulkPlanRing - 1);
+        ++n_if;
+        --n_wait;
+        return true;
+    };
+
+    // The first pass of the loop finds nothing staged: it only takes the warp's first chunk of tickets, plans and stages it.
+    unsigned int chunk_base = 0;
+    bool exhausted = false;  // no ticket left behind this warp's last chunk
+    const float inv_guide = 1.0f / (float)(max(IPP_BULK_GUIDE, 1) * (int)gridDim.x * bp.warps);
+
+#pragma unroll 1
+    while (true) {
+        // (A) ask for the next chunk of tickets early — the atomic's result is consumed only after this env has been fused
+        const bool request = n_wait <= 2 && !exhausted;
+        unsigned int fresh = 0;
+        int req = kBulkChunk;
+        if (request) {
+            const int left = n_jobs - (int)min(chunk_base, (unsigned)n_jobs);  // as of this warp's previous chunk
+            req = min(kBulkChunk, max(1, (int)((float)left * inv_guide)));
+            if (req == 1) max_if = IPP_BULK_ENDGAME_DEPTH;  // end game: do not hoard work
+            if (lane == 0) fresh = atomicAdd(ticket, (unsigned)req);
+        }
+
+        // (B) fuse the oldest staged env
+        if (n_if == 0) {  // nothing staged, hence nothing planned either: done unless a chunk has just been asked for
+            if (!request) break;
+        } else {
+        const BulkPlan *pl = plans + c_pos;
+        const int4 pa = *reinterpret_cast<const int4 *>(pl);
+        const int job = pa.x;
+        if (job < 0) break;  // warp-uniform: tickets are monotonic, every later plan is empty too
+        const int4 pb = *reinterpret_cast<const int4 *>(&pl->magic_x);
+        mbar_wait(bars + 8u * (ci & (kBulkDepth - 1)), (ci / kBulkDepth) & 1u);
+
+        const int xl = pa.y & 0xffff, yu = pa.y >> 16;
+        const int nx = pa.z & 255, ny = (pa.z >> 8) & 255, nqx = (pa.z >> 16) & 255, nqy = (pa.z >> 24) & 255;
+        const int ntx = pa.w & 255, lvl = (pa.w >> 16) & 255, pflags = (pa.w >> 24) & 255;
+        const int rf = (pflags & 1) ? 2 : 1;
+        const bool analytic = (pflags & 2) != 0, unsupported = (pflags & 4) != 0;
+        const int out_r = pb.w & 255, out_c = (pb.w >> 8) & 255;
+        const uint32_t magic_x = (uint32_t)pb.x;
+        const uint32_t slot = ring + (uint32_t)pb.z;
+        const int a4 = xl & 3, b4 = yu & 3;
+        const int srow = ntx * kSuperTileBytes;                 // staged tile-row stride [bytes]
+        const int grow = txs * kSuperTileBytes;                 // HBM tile-row stride [bytes]
+        const int dts = grow - srow;
+        unsigned char *gbase = const_cast<unsigned char *>(plane0) + (size_t)job * env_bytes + (size_t)((yu >> 2) * txs + (xl >> 2)) * kSuperTileBytes;
+        const int nq = nqx * nqy;
+
+        const AltLevel &L = p.lut[lvl];
+        FuseCtx fc;
+        fc.rf = rf;
+        fc.R = L.R;
+        fc.invR = fast_rcp(L.R);
+        const float s2 = L.s2;
+
+        // INTER_AREA: analytic weights, or this env's tap tables (clipped non-square footprints)
+        TapView tapv;
+        tapv.rows = taps;
+        tapv.cols = taps + 3 * kTapCap;
+        int tap_mode = TAPS_FAST;
+        float inv_nx = 0.f, inv_ny = 0.f, wmid_x = 0.f, wmid_y = 0.f;
+        if (MODE != MODE_PREDICT && rf == 2 && !unsupported) {
+            if (analytic) {
+                inv_nx = __frcp_rn((float)nx);  // == 1.0f / (float)n_in of make_tap_entry
+                inv_ny = __frcp_rn((float)ny);
+                wmid_x = (float)nqx * inv_nx;
+                wmid_y = (float)nqy * inv_ny;
+            } else {
+                tap_mode = build_tap_tables<kTapCap>(taps, lane, ny, nx, out_r, out_c);
+            }
+        }
+        const float inv_outc = (MODE != MODE_PREDICT && rf == 2 && !analytic) ? __frcp_rn((float)out_c) : 0.f;
+        const size_t nrow = (size_t)job * (size_t)p.noise_stride;
+        float acc = 0.0f;
+        float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four iterations
+
+        if (!unsupported) {
+#pragma unroll 1
+            for (int q = lane; q < nq; q += 32) {
+                const int qy = (int)(((uint32_t)q * magic_x) >> 16);
+                const int qx = q - qy * nqx;
+                const int r0 = 2 * qy, c0 = 2 * qx;
+                const bool cok = c0 + 1 < nx, rok = r0 + 1 < ny;
+                const bool ok[4] = {true, cok, rok, cok && rok};
+                // tile-local coordinates: one index for the staged read and the HBM write-back
+                const int rr = b4 + r0, cc = a4 + c0;
+                const int trl = rr >> 2, ir = rr & 3, ic = cc & 3;
+                const int t192 = (trl * ntx + (cc >> 2)) * kSuperTileBytes;
+                const int inner = (ir << 5) | (ic << 3);
+                const uint32_t so = slot + (uint32_t)(t192 + inner);        // {mean,var} of cell (r0, c0), staged
+                unsigned char *go = gbase + (t192 + inner + trl * dts);     // ... and in HBM
+                const bool last_r = ir == 3, last_c = ic == 3;
+                const int dRs = rok ? (last_r ? srow - 96 : 32) : 0;        // to the quad's second row (clamped inside the footprint)
+                const int dRg = last_r ? grow - 96 : 32;
+                const int dC = cok ? (last_c ? 168 : 8) : 0;                // to the quad's second column
+
+                float4 top, bot;
+                if (a4 & 1) {
+                    const float2 t0 = lds64(so), t1 = lds64(so + dC), b0 = lds64(so + dRs), b1 = lds64(so + dRs + dC);
+                    top = make_float4(t0.x, t0.y, t1.x, t1.y);
+                    bot = make_float4(b0.x, b0.y, b1.x, b1.y);
+                } else {  // warp-uniform: (c0, c0 + 1) share a 16-byte chunk
+                    top = lds128(so);
+                    bot = lds128(so + dRs);
+                }
+                const float m[4] = {top.x, cok ? top.z : 0.0f, rok ? bot.x : 0.0f, ok[3] ? bot.z : 0.0f};
+                const float v[4] = {top.y, cok ? top.w : 0.0f, rok ? bot.y : 0.0f, ok[3] ? bot.w : 0.0f};
+
+                // ---- measurement --------------------------------------------------------------------------------
+                float z[4] = {0.f, 0.f, 0.f, 0.f};
+                if (MODE != MODE_PREDICT) {
+                    float eps[4];
+                    if (EXTRAS && p.noise != nullptr) {
+                        if (rf == 1) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) eps[k] = ok[k] ? __ldg(p.noise + nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)) : 0.0f;
+                        } else {
+                            eps[0] = __ldg(p.noise + nrow + q);
+                        }
+                    } else {
+                        draw_normals(p, rf, q, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
+                    }
+                    const uint32_t gs = slot + (uint32_t)(t192 + 128 + (inner >> 1));  // gt of cell (r0, c0), staged
+                    const int dRq = rok ? (last_r ? srow - 48 : 16) : 0;
+                    const int dCq = cok ? (last_c ? 180 : 4) : 0;
+                    if (rf == 1) {
+                        float gv[4];
+                        if (a4 & 1) {
+                            gv[0] = lds32(gs);
+                            gv[1] = lds32(gs + dCq);
+                            gv[2] = lds32(gs + dRq);
+                            gv[3] = lds32(gs + dRq + dCq);
+                        } else {
+                            const float2 g0 = lds64(gs), g1 = lds64(gs + dRq);
+                            gv[0] = g0.x;
+                            gv[1] = g0.y;
+                            gv[2] = g1.x;
+                            gv[3] = g1.y;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) z[k] = ok[k] ? __saturatef(fmaf(s2, eps[k], gv[k])) : 0.0f;
+                    } else if (analytic) {
+                        // rows {r0-1, r0, r0+1} x cols {c0-1, c0, c0+1}; taps with weight 0 are clamped onto the quad's own cells
+                        const int dU = qy > 0 ? ((ir == 0) ? -(srow - 48) : -16) : 0;
+                        const int dL = qx > 0 ? ((ic == 0) ? -180 : -4) : 0;
+                        const float wl = (float)qx * inv_nx, wr_ = (float)(nqx - 1 - qx) * inv_nx;
+                        const float wu = (float)qy * inv_ny, wb = (float)(nqy - 1 - qy) * inv_ny;
+                        float rs[3];
+                        const int dro[3] = {dU, 0, dRq};
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const uint32_t ra = gs + dro[k];
+                            float g0, g1;
+                            if (a4 & 1) {
+                                g0 = lds32(ra);
+                                g1 = lds32(ra + dCq);
+                            } else {
+                                const float2 t = lds64(ra);
+                                g0 = t.x;
+                                g1 = t.y;
+                            }
+                            const float gl = lds32(ra + dL);
+                            rs[k] = fmaf(wr_, g1, fmaf(wmid_x, g0, wl * gl));
+                        }
+                        float d = fmaf(wu, rs[0], 0.0f);
+                        d = fmaf(wmid_y, rs[1], d);
+                        d = fmaf(wb, rs[2], d);
+                        z[0] = __saturatef(fmaf(s2, eps[0], d));
+                    } else {
+                        const int pr = fdiv(q, out_c, inv_outc), pc = q - pr * out_c;
+                        const float d = downsample(tap_mode, GtSuperShared{slot, ntx, a4, b4}, tapv, pr, pc, ny, nx, out_r, out_c);
+                        z[0] = __saturatef(fmaf(s2, eps[0], d));
+                    }
+                    if (EXTRAS && p.z_out != nullptr) {
+                        if (rf == 1) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (ok[k]) p.z_out[nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)] = z[k];
+                        } else {
+                            p.z_out[nrow + q] = z[0];
+                        }
+                    }
+                }
+
+                // ---- fusion + reward, results straight to HBM ------------------------------------------------------
+                float mn[4], vn[4];
+                bool msk[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) msk[k] = ok[k] && (!ADAPTIVE || (fmaf(p.kappa, v[k], m[k]) >= p.thr));
+                acc += kalman_quad<ENTROPY, ADAPTIVE>(fc, cok, rok, m, v, z, msk, mn, vn);
+                if (MODE == MODE_PREDICT) {  // covariance only: the mean goes back as it came
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mn[k] = m[k];
+                }
+                if (MODE != MODE_PREDICT || commit) {
+                    if (a4 & 1) {
+                        const int dCg = last_c ? 168 : 8;
+                        *reinterpret_cast<float2 *>(go) = make_float2(mn[0], vn[0]);
+                        if (cok) *reinterpret_cast<float2 *>(go + dCg) = make_float2(mn[1], vn[1]);
+                        if (rok) *reinterpret_cast<float2 *>(go + dRg) = make_float2(mn[2], vn[2]);
+                        if (ok[3]) *reinterpret_cast<float2 *>(go + dRg + dCg) = make_float2(mn[3], vn[3]);
+                    } else if (cok) {
+                        *reinterpret_cast<float4 *>(go) = make_float4(mn[0], vn[0], mn[1], vn[1]);
+                        if (rok) *reinterpret_cast<float4 *>(go + dRg) = make_float4(mn[2], vn[2], mn[3], vn[3]);
+                    } else {
+                        *reinterpret_cast<float2 *>(go) = make_float2(mn[0], vn[0]);
+                        if (rok) *reinterpret_cast<float2 *>(go + dRg) = make_float2(mn[2], vn[2]);
+                    }
+                }
+            }
+        }
+
+        // per-env information gain: fp32 partials per lane, fp32 tree across the warp; the cost term comes from the plan
+        float accd = acc;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, sft);
+        if (lane == 0 && p.reward != nullptr) p.reward[job] = accd * __int_as_float(pb.y);
+        __syncwarp();  // every lane is done with the staged footprint, the plan and the tap tables
+
+        // (C) release the footprint
+        ++ci;
+        c_pos = (c_pos + 1) & (kBulkPlanRing - 1);
+        --n_if;
+        if (n_if > 0) r_head = plans[c_pos].ring_off;
+        }
+
+        // (D) plan the chunk requested at (A): lane i decodes ticket fresh + i
+        if (request) {
+            chunk_base = __shfl_sync(0xffffffffu, fresh, 0);
+            exhausted = chunk_base + (unsigned)req >= (unsigned)n_jobs;
+            if (chunk_base < (unsigned)n_jobs) plan_chunk(chunk_base, req);
+        }
+        // (E) stage what fits
+        while (try_fill()) {
+        }
+        __syncwarp();  // ring_off of the freshly staged footprints is visible to every lane
+    }
+}
+
+}  // namespace ipp

@@ -23,17 +23,18 @@ constexpr int kTapCap = 16;  // tap-table entries per axis staged in shared memo
 // ---------------------------------------------------------------------------------------------
 // belief accessors for the two HBM layouts
 // ---------------------------------------------------------------------------------------------
-// interleaved {mean,var}; IPP_LAYOUT_MV: row-major map, IPP_LAYOUT_TILED: 4x4-cell tiles (quad_math.cuh)
+// interleaved {mean,var}; IPP_LAYOUT_MV: row-major map, IPP_LAYOUT_TILED: 4x4-cell tiles, IPP_LAYOUT_SUPER: 192-byte
+// super-tiles (quad_math.cuh)
 template <int LAYOUT>
 struct Belief {
-    static_assert(LAYOUT == IPP_LAYOUT_MV || LAYOUT == IPP_LAYOUT_TILED, "unknown layout");
+    static_assert(LAYOUT == IPP_LAYOUT_MV || LAYOUT == IPP_LAYOUT_TILED || LAYOUT == IPP_LAYOUT_SUPER, "unknown layout");
     float2 *mv;
     __device__ __forceinline__ Belief(const StepParams &p, size_t env) : mv(reinterpret_cast<float2 *>(p.mean) + env * p.plane) {}
     static __device__ __forceinline__ int idx(const StepParams &p, int R, int C) {
-        return LAYOUT == IPP_LAYOUT_TILED ? tiled_mv_index(p.txm, R, C) : R * p.X + C;
+        return LAYOUT == IPP_LAYOUT_TILED ? tiled_mv_index(p.txm, R, C) : (LAYOUT == IPP_LAYOUT_SUPER ? super_mv_index(p.txm, R, C) : R * p.X + C);
     }
     static __device__ __forceinline__ int gidx(const StepParams &p, int R, int C) {
-        return LAYOUT == IPP_LAYOUT_TILED ? tiled_gt_index(p.txg, R, C) : R * p.X + C;
+        return LAYOUT == IPP_LAYOUT_TILED ? tiled_gt_index(p.txg, R, C) : (LAYOUT == IPP_LAYOUT_SUPER ? super_gt_index(p.txm, R, C) : R * p.X + C);
     }
     __device__ __forceinline__ void load(int i, float &mean, float &var) const {
         const float2 t = __ldcg(mv + i);
@@ -179,6 +180,8 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
                     float d;
                     if (LAYOUT == IPP_LAYOUT_TILED)
                         d = downsample(tap_mode, GtTiled{gt, p.txg, g.yu, g.xl}, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
+                    else if (LAYOUT == IPP_LAYOUT_SUPER)
+                        d = downsample(tap_mode, GtSuper{gt, p.txm, g.yu, g.xl}, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
                     else
                         d = downsample(tap_mode, GtRowMajor{gt + g.yu * p.X + g.xl, p.X}, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
                     z[0] = __saturatef(fmaf(g.s2, eps[0], d));

@@ -90,7 +90,7 @@ class EngineConfig:
             kw["max_v"], kw["max_a"] = float(uav["max_v"]), float(uav["max_a"])
         backend = params.get("mapping", {}).get("b200", {})
         if "layout" in backend:
-            kw["layout"] = {"planes": capi.LAYOUT_PLANES, "mv": capi.LAYOUT_MV, "tiled": capi.LAYOUT_TILED}[backend["layout"]]
+            kw["layout"] = capi.LAYOUT_NAMES[backend["layout"]]
         kw.update(overrides)
         return cls(**kw)
 

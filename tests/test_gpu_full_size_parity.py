@@ -1,0 +1,209 @@
+"""Value-level parity at BASELINE.json's full per-GPU sizes (the configurations bench.py times).
+
+The oracle comparisons elsewhere run on a few dozen envs — less than one warp per SM — so the persistent kernels' ticket
+scheduling, staging rings and plan queues are never under full occupancy there.  Here the WHOLE batch runs through the
+persistent path and, in the same process, through the general LSU kernel on a row-major layout:
+
+  (a) rewards of every env and the eight evaluation metrics of every env are bit-identical between the two paths, and so
+      are the complete belief maps of 256 sampled envs;
+  (b) the 256 sampled envs are checked cell for cell (<= 1e-5) and reward for reward (rel 1e-5) against the reference-pinned
+      NumPy oracle (oracle.ipp_oracle.full_step with the device Philox stream), both reward modes and the adaptive mask.
+
+Tolerances: cells 1e-5 absolute, rewards 1e-5 relative (BASELINE.json north_star); adaptive steps skip exactly the envs
+with a footprint cell whose mean + kappa*var lies within 1e-5 of the threshold.
+"""
+import numpy as np
+import pytest
+
+from oracle import ipp_oracle as orc
+from oracle import mcts_oracle as morc
+from tests._util import engine_cfg, make_params, oracle_cfg
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-5
+RTOL = 1e-5
+
+SIZES = {  # BASELINE.json configurations at their full per-GPU sizes
+    "C3": (200, 1.0, 8, 20, 6, 65536),
+    "C5": (400, 1.0, 8, 20, 6, 4096),
+    "C2": (50, 4.0, 8, 14, 6, 4096),
+}
+
+
+def _engine(params, batch, **kw):
+    from ipp_rl_b200 import BatchedEngine
+
+    return BatchedEngine(engine_cfg(params, batch, **kw))
+
+
+@pytest.mark.parametrize("size,layout", [("C3", 3), ("C3", 2), ("C5", 3), ("C2", 3), ("C2", 2)])
+def test_full_batch_values_vs_oracle_and_lsu(size, layout):
+    import torch
+
+    G, res, amin, amax, asp, B = SIZES[size]
+    free, _ = torch.cuda.mem_get_info()
+    if 2 * B * G * G * 13 > 0.85 * free:
+        pytest.skip("not enough device memory for two full-size engines")
+    X = Y = G
+    kappa, thr = 0.25, 0.45
+    params = make_params(X, Y, res, amin, amax, asp, kappa=kappa, thr=thr)
+    cfg = oracle_cfg(params)
+    tbl = orc.enumerate_actions(cfg)
+    seed, off = 20260925, 4096
+    rng = np.random.RandomState(11)
+    S = 256
+    sample = np.sort(rng.choice(B, S, replace=False))
+    steps = [(0, False), (1, False), (0, True), (1, True)]  # (reward mode, adaptive)
+    with _engine(params, B, layout=layout, seed=seed, env_id_offset=off) as fast, _engine(params, B, layout=1, seed=seed, env_id_offset=off) as ref:
+        fast.set_step_path("async")
+        ref.set_step_path("lsu")
+        assert fast.step_path == "async" and ref.step_path == "lsu"
+        for eng in (fast, ref):
+            eng.reset(0.5, 1.82)
+            eng.synth_ground_truth(77)
+        gt = np.concatenate([fast.get_ground_truth(int(b), 1) for b in sample]).astype(np.float64)
+        assert np.array_equal(gt, np.concatenate([ref.get_ground_truth(int(b), 1) for b in sample]))
+        # a non-trivial belief first (two un-checked steps), so that means and variances differ per cell
+        for t in range(2):
+            ids = rng.randint(0, fast.num_actions, B).astype(np.int32)
+            assert np.array_equal(fast.step(ids), ref.step(ids))
+        for t, (mode, adaptive) in enumerate(steps):
+            ids = rng.randint(0, fast.num_actions, B).astype(np.int32)
+            if t == 0:  # borders / corners on purpose, inside the sample
+                ids[sample[:6]] = [0, X - 1, X * (Y - 1), X * Y - 1, fast.num_actions - 1, X * Y]
+            pre = [fast.get_state(int(b), 1) for b in sample]
+            prev = fast.get_prev_pose()[sample]
+            l0 = fast.path_launches("async")
+            r_fast = fast.step(ids, reward_mode=mode, adaptive=adaptive).copy()
+            assert fast.path_launches("async") == l0 + 1
+            r_ref = ref.step(ids, reward_mode=mode, adaptive=adaptive).copy()
+            assert np.array_equal(r_fast, r_ref), (t, int(np.sum(r_fast != r_ref)))
+            assert np.all(np.isfinite(r_fast))
+            step_index = 2 + t  # the engines' Philox step counter
+            for j, b in enumerate(sample):
+                b = int(b)
+                m0, v0 = pre[j][0][0].astype(np.float64), pre[j][1][0].astype(np.float64)
+                act = tbl[ids[b]]
+                eps = orc.device_noise_field(cfg, act, seed, off + b, step_index)
+                ro, mo, vo, _ = orc.full_step(cfg, gt[j], m0, v0, prev[j], act, eps, adaptive, mode)
+                m1, v1 = fast.get_state(b, 1)
+                assert np.max(np.abs(m1[0] - mo)) <= ATOL, (t, b, np.max(np.abs(m1[0] - mo)))
+                assert np.max(np.abs(v1[0] - vo)) <= ATOL, (t, b, np.max(np.abs(v1[0] - vo)))
+                near = False
+                if adaptive:
+                    xl, xr, yu, yd = orc.project_field_of_view(cfg, act)
+                    score = (m0 + kappa * v0)[yu : yd + 1, xl : xr + 1]
+                    near = bool(np.any(np.abs(score - thr) <= 1e-5))
+                if not near:
+                    assert abs(r_fast[b] - ro) <= RTOL * max(1.0, abs(ro)), (t, b, r_fast[b], ro)
+        # whole batch: the evaluation metrics (fp64 reductions over every cell of every env) agree bit for bit ...
+        assert np.array_equal(fast.eval(), ref.eval(), equal_nan=True)
+        # ... and so do the complete maps and stored poses of the sampled envs
+        for b in sample:
+            mf, vf = fast.get_state(int(b), 1)
+            mr, vr = ref.get_state(int(b), 1)
+            assert np.array_equal(mf, mr) and np.array_equal(vf, vr)
+        assert np.array_equal(fast.get_prev_pose(), ref.get_prev_pose())
+
+
+@pytest.mark.parametrize("layout", [3, 2])
+def test_full_batch_predict_vs_oracle_and_lsu(layout):
+    """The persistent predict-only path (whole batch, action ids) at C3 size against the LSU kernel (bit-identical) and the
+    oracle's simulate_prediction_step on sampled envs; NO_COMMIT leaves the belief untouched."""
+    G, res, amin, amax, asp, B = SIZES["C3"]
+    X = Y = G
+    kappa, thr = 0.25, 0.45
+    params = make_params(X, Y, res, amin, amax, asp, kappa=kappa, thr=thr)
+    cfg = oracle_cfg(params)
+    tbl = orc.enumerate_actions(cfg)
+    rng = np.random.RandomState(12)
+    S = 128
+    sample = np.sort(rng.choice(B, S, replace=False))
+    with _engine(params, B, layout=layout, seed=3) as fast, _engine(params, B, layout=1, seed=3) as ref:
+        fast.set_step_path("async")
+        ref.set_step_path("lsu")
+        for eng in (fast, ref):
+            eng.reset(0.5, 1.82)
+            eng.synth_ground_truth(5)
+        for t in range(2):
+            ids = rng.randint(0, fast.num_actions, B).astype(np.int32)
+            assert np.array_equal(fast.step(ids), ref.step(ids))
+        for t, (mode, adaptive, commit) in enumerate([(0, False, False), (0, False, True), (1, True, True), (0, True, True)]):
+            ids = rng.randint(0, fast.num_actions, B).astype(np.int32)
+            pre = [fast.get_state(int(b), 1) for b in sample]
+            prev = fast.get_prev_pose()[sample]
+            la = fast.path_launches("async")
+            r_fast = fast.predict(ids, commit=commit, reward_mode=mode, adaptive=adaptive).copy()
+            if layout == 3:
+                assert fast.path_launches("async") == la + 1, "whole-batch prediction steps must take the persistent path"
+            r_ref = ref.predict(ids, commit=commit, reward_mode=mode, adaptive=adaptive).copy()
+            assert np.array_equal(r_fast, r_ref), (t, int(np.sum(r_fast != r_ref)))
+            for j, b in enumerate(sample):
+                b = int(b)
+                m0, v0 = pre[j][0][0].astype(np.float64), pre[j][1][0].astype(np.float64)
+                act = tbl[ids[b]]
+                ro, vo = orc.simulate_prediction_step(cfg, v0, prev[j], act, mean=m0, adaptive=adaptive, reward_mode=mode)
+                m1, v1 = fast.get_state(b, 1)
+                assert np.array_equal(m1[0], pre[j][0][0])
+                if commit:
+                    assert np.max(np.abs(v1[0] - vo)) <= ATOL
+                else:
+                    assert np.array_equal(v1[0], pre[j][1][0])
+                near = False
+                if adaptive:
+                    xl, xr, yu, yd = orc.project_field_of_view(cfg, act)
+                    score = (m0 + kappa * v0)[yu : yd + 1, xl : xr + 1]
+                    near = bool(np.any(np.abs(score - thr) <= 1e-5))
+                if not near:
+                    assert abs(r_fast[b] - ro) <= RTOL * max(1.0, abs(ro)), (t, b, r_fast[b], ro)
+        assert np.array_equal(fast.eval(), ref.eval(), equal_nan=True)
+        assert np.array_equal(fast.get_prev_pose(), ref.get_prev_pose())
+
+
+def test_mcts_full_size_sampled_trees_vs_oracle():
+    """16 384 trees (BASELINE.json C4 per-GPU share) on the 200x200 / 3-altitude workload, uniform priors; 48 sampled trees
+    against oracle.mcts_oracle (root visit counts and Q values)."""
+    from ipp_rl_b200.planning.mcts_zero import BatchedMCTS
+
+    X = Y = 200
+    params = make_params(X, Y, 1.0, 8, 20, 6)
+    cfg = oracle_cfg(params)
+    sims, H = 16, 5
+    hyper = dict(puct_init=15.0, puct_base=10000, num_mcts_simulations=sims, gamma=1.0, dirichlet_alpha=0.3, dirichlet_eps=0.0,
+                 forced_playout_factor=2.0, max_valid_action_distance=11.5)
+    meta = dict(episode_horizon=H, scenario_info=None)
+    T = 16384
+    rng = np.random.RandomState(4)
+    sample = np.sort(rng.choice(T, 48, replace=False))
+    with _engine(params, T, layout=3, seed=3) as eng:
+        eng.reset(0.5, 1.82)
+        eng.synth_ground_truth(5)
+        for _ in range(3):  # a non-trivial belief
+            eng.step(rng.randint(0, eng.num_actions, T).astype(np.int32))
+        prev = eng.get_prev_pose()
+        var0 = {int(b): eng.get_state(int(b), 1)[1][0].astype(np.float64) for b in sample}
+        budgets = rng.uniform(20, 200, T).astype(np.float32)
+        with BatchedMCTS(eng, hyper, meta) as mcts:
+            mcts.begin(budgets, prev)
+            for _ in range(sims):
+                mcts.simulate(lambda lf: (None, None))
+            st = mcts.root_stats()
+        assert np.all(st["Ns"] == sims - 1)
+    exact = 0
+    for b in sample:
+        b = int(b)
+        o = morc.OracleMCTS(cfg, hyper, H, evaluator=None)
+        o.search(var0[b], prev[b], float(budgets[b]), sims)
+        dense_n = np.zeros(o.num_actions)
+        dense_q = np.zeros(o.num_actions)
+        ok = st["action_ids"][b] >= 0
+        dense_n[st["action_ids"][b][ok]] = st["Nsa"][b][ok]
+        dense_q[st["action_ids"][b][ok]] = st["Qsa"][b][ok]
+        assert dense_n.sum() == o.Nsa[()].sum() == st["Ns"][b]
+        if np.array_equal(dense_n, o.Nsa[()]):
+            exact += 1
+            assert np.max(np.abs(dense_q - o.Qsa[()])) <= 2e-4 * max(1.0, np.abs(o.Qsa[()]).max())
+    # uniform priors make every un-visited action tie exactly (lowest id wins on both sides); visited actions are
+    # separated by their Q values, where an fp32-vs-fp64 near-tie may send a simulation elsewhere
+    assert exact >= len(sample) - 2, f"only {exact}/{len(sample)} sampled trees reproduce the oracle's visit counts exactly"

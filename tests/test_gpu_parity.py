@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 ATOL = 1e-5
 RTOL = 1e-5
-LAYOUTS = [0, 1, 2]  # planes, {mean,var} row-major, 128-byte tiles
+LAYOUTS = [0, 1, 2, 3]  # planes, {mean,var} row-major, 128-byte tiles, 192-byte super-tiles
 
 
 def _engine(params, batch, **kw):
@@ -158,6 +158,7 @@ def test_batched_random_vs_oracle_philox(layout, reward_mode, grid):
                 a_orc = np.stack([rng.uniform(0, X * res, B), rng.uniform(0, Y * res, B), rng.uniform(5, 20, B)], axis=1)
                 a_eng = a_orc
             adaptive = t % 3 == 2
+            m_pre, v_pre = st.mean.copy(), st.var.copy()
             r = eng.step(a_eng, reward_mode=reward_mode, adaptive=adaptive)
             # teacher-force the oracle state from the engine's previous fp32 state so that mask
             # decisions are taken on identical numbers
@@ -167,9 +168,16 @@ def test_batched_random_vs_oracle_philox(layout, reward_mode, grid):
             assert _maxerr(var, st.var) <= ATOL, (t, _maxerr(var, st.var))
             if not adaptive:
                 assert np.all(np.abs(r - ro) <= RTOL * np.maximum(1.0, np.abs(ro))), (t, np.max(np.abs(r - ro)))
-            else:  # tolerate threshold flips: compare where no cell is within 1e-5 of the threshold
+            else:  # a mask decision may flip inside fp32 rounding of the threshold: skip exactly the envs with a footprint cell
+                #    whose pre-step  mean + kappa * var  lies within 1e-5 of it, every other env must agree
+                near = np.zeros(B, bool)
+                for b in range(B):
+                    xl, xr, yu, yd = orc.project_field_of_view(cfg, a_orc[b])
+                    score = (m_pre[b] + cfg.interval_factor * v_pre[b])[yu : yd + 1, xl : xr + 1]
+                    near[b] = np.any(np.abs(score - cfg.value_threshold) <= 1e-5)
+                assert near.mean() < 0.2, near.mean()
                 ok = np.abs(r - ro) <= RTOL * np.maximum(1.0, np.abs(ro))
-                assert ok.mean() > 0.9
+                assert np.all(ok[~near]), (t, np.flatnonzero(~ok & ~near))
             st.mean, st.var = mean.astype(np.float64), var.astype(np.float64)
             assert np.allclose(eng.get_prev_pose(), a_orc)
 

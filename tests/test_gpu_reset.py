@@ -14,7 +14,7 @@ def _engine(params, batch, **kw):
     return BatchedEngine(engine_cfg(params, batch, **kw))
 
 
-@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("layout", [0, 1, 2, 3])
 def test_device_grf_matches_reference_fields(layout):
     g = golden("golden_grf.npz")
     for name in g["names"]:
@@ -48,7 +48,7 @@ def test_device_grf_philox_mode_is_shard_invariant_and_smooth():
     assert np.all(corr > 0.9)  # k^-5 spectrum: strongly correlated neighbours (white noise would give ~0)
 
 
-@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("layout", [0, 1, 2, 3])
 def test_observation_planes_match_reference_feature_planes(layout):
     """ipp_observe vs the REAL reference generate_input_feature_planes on a diagonal state (golden_features.npz)."""
     from tests._util import params_from_json
