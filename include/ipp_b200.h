@@ -291,6 +291,14 @@ void *ipp_device_ptr(ipp_engine *e, int32_t which);
 int ipp_set_option(ipp_engine *e, int32_t option, int64_t value);
 int64_t ipp_get_option(const ipp_engine *e, int32_t option);
 
+/* Static Kalman update on a DIAGONAL covariance for a measurement model given as disjoint blocks (CSR rows: the cells of
+ * measurement i are cols[row_ptr[i] .. row_ptr[i+1]), all with weight[i]; noise_var[i] = R_ii).  Replaces the reference's
+ * static Mapping.kalman_filter_update(P, H, R, grid_mean, observation, cov_only) (mapping/mappings.py:155-215) for the H / R
+ * that AltitudeSensorModel builds (sensors/models/sensor_models.py:32-81).  Stateless (no engine handle), host buffers, fp64
+ * on the device.  var[n_cells] is updated in place; mean[n_cells] too when mean and obs are given (cov_only: pass NULL). */
+int ipp_kalman_blocks(int32_t device, int32_t n_cells, int32_t n_meas, const int32_t *row_ptr, const int32_t *cols, const double *weight,
+                      const double *noise_var, const double *obs, double *var, double *mean);
+
 /* Pinned host memory for the host entry points (cudaHostAlloc). */
 int ipp_host_alloc(void **ptr, size_t bytes);
 int ipp_host_free(void *ptr);

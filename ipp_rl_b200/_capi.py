@@ -208,6 +208,7 @@ SIGNATURES = {
     "ipp_get_option": (C.c_int64, [_P, _I32]),
     "ipp_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "ipp_host_free": (C.c_int, [_P]),
+    "ipp_kalman_blocks": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     # include/ipp_mcts.h
     "ipp_mcts_create": (C.c_int, [_P, C.POINTER(ipp_mcts_config), C.POINTER(_P)]),
     "ipp_mcts_destroy": (None, [_P]),

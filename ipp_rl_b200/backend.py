@@ -109,27 +109,34 @@ class SingleEnvBackend:
         m, v = s.get_state()
         return (None if z is None else m[0].astype(np.float64)), v[0].astype(np.float64)
 
+    def set_mask_params(self, value_threshold=None, interval_factor=None) -> None:
+        """The adaptive-mask parameters are engine configuration (ipp_config.value_threshold / interval_factor): rebuild the
+        engines, keeping their state, when a caller asks for different ones (None = keep)."""
+        thr = self.cfg.value_threshold if value_threshold is None else float(value_threshold)
+        kap = self.cfg.interval_factor if interval_factor is None else float(interval_factor)
+        if thr == self.cfg.value_threshold and kap == self.cfg.interval_factor:
+            return
+        self.cfg.value_threshold, self.cfg.interval_factor = thr, kap
+        if self._scratch is not None:
+            self._scratch.close()
+            self._scratch = None
+        if self._real is not None:  # keep both engines on the same configuration
+            m, v = self.read_real()
+            gt = self._real.get_ground_truth()
+            prev = self._real.get_prev_pose()
+            self._real.close()
+            self._real = None
+            self.real.set_ground_truth(gt)
+            self.load_real(m, v)
+            self.real.set_prev_pose(prev)
+
     def rewards_from(self, var: np.ndarray, previous_action, actions: np.ndarray, mean: Optional[np.ndarray] = None,
                      adaptive: bool = False, value_threshold: float = None, interval_factor: float = None) -> np.ndarray:
         """Information-gain rewards of many candidate actions from ONE state in a single launch
         (greedy_search's Pool(4) loop, reference planning/common/optimization.py:82-98)."""
+        if adaptive:
+            self.set_mask_params(value_threshold, interval_factor)
         s = self.scratch
-        if adaptive and (value_threshold != self.cfg.value_threshold or interval_factor != self.cfg.interval_factor):
-            # the mask parameters are engine configuration: rebuild the scratch engine when they differ
-            self.cfg.value_threshold, self.cfg.interval_factor = float(value_threshold), float(interval_factor)
-            if self._scratch is not None:
-                self._scratch.close()
-                self._scratch = None
-            if self._real is not None:  # keep both engines on the same configuration
-                m, v = self.read_real()
-                gt = self._real.get_ground_truth()
-                prev = self._real.get_prev_pose()
-                self._real.close()
-                self._real = None
-                self.real.set_ground_truth(gt)
-                self.load_real(m, v)
-                self.real.set_prev_pose(prev)
-            s = self.scratch
         Y, X = self.cfg.y_dim, self.cfg.x_dim
         s.set_state(None if mean is None else np.asarray(mean, np.float32).reshape(1, Y, X), np.asarray(var, np.float32).reshape(1, Y, X))
         a = np.ascontiguousarray(actions, dtype=np.float64).reshape(-1, 3)

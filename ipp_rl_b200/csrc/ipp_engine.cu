@@ -457,6 +457,7 @@ static int setup_async(ipp_engine *e) {
         gt_cells = std::max(gt_cells, pg * fh);
         // the kernel divides quad indices with a 16-bit magic multiplier: exact while quads * quads-per-row < 2^15
         const int nqx = (fw + 1) / 2, nqy = (fh + 1) / 2;
+        if (nqx > 32) return IPP_OK;  // lane layout: one pass covers whole quad rows
         if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;
     }
     // TILED + IPP_DIRECT_MV: the belief is not staged at all (bulk L2 prefetch + direct loads), a slot holds the ground truth only
@@ -481,7 +482,9 @@ static int setup_async(ipp_engine *e) {
     e->async_gt_tile = gt_tile;
     e->async_smem = per_slot * (warps + double_warps) + per_warp_fixed * warps + per_cta;
     for (int v = 0; v < 16; ++v)
-        if (cudaFuncSetAttribute(async_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->async_smem) != cudaSuccess) {
+        // the attribute is per function, not per engine: always ask for the device maximum, or a second engine with smaller
+        // footprints would lower the limit under the first one
+        if (cudaFuncSetAttribute(async_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem) != cudaSuccess) {
             cudaGetLastError();
             return IPP_OK;
         }
@@ -540,22 +543,25 @@ static int setup_bulk(ipp_engine *e) {
         const int ntx = std::min(e->txm, (fw + 2) / 4 + 1), ntr = std::min(e->tiles_y, (fh + 2) / 4 + 1);
         max_fp = std::max(max_fp, ntx * ntr * kSuperTileBytes);
         const int nqx = (fw + 1) / 2, nqy = (fh + 1) / 2;
+        if (nqx > 32) return IPP_OK;  // lane layout: one pass covers whole quad rows
         if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;  // 16-bit magic division of quad indices
     }
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device) != cudaSuccess) return IPP_OK;
     const size_t per_warp_fixed = kBulkPlanRing * sizeof(BulkPlan) + kBulkTapFloats2 * sizeof(float2) + kBulkDepth * 8;
+    const size_t per_cta = (size_t)kBulkMaxLevels * 2 * sizeof(float4);
+    const size_t avail = (size_t)dev_smem - per_cta;
     int warps = kBulkMaxWarps;
     if (const char *wenv = getenv("IPP_BULK_WARPS")) warps = std::max(1, std::min(kBulkMaxWarps, atoi(wenv)));
-    while (warps > 1 && (size_t)dev_smem / warps < per_warp_fixed + (size_t)max_fp) --warps;
-    if ((size_t)dev_smem / warps < per_warp_fixed + (size_t)max_fp) return IPP_OK;  // footprints too large to stage in shared memory
-    int ring = (int)(((size_t)dev_smem / warps - per_warp_fixed) / 16 * 16);
+    while (warps > 1 && avail / warps < per_warp_fixed + (size_t)max_fp) --warps;
+    if (avail / warps < per_warp_fixed + (size_t)max_fp) return IPP_OK;  // footprints too large to stage in shared memory
+    int ring = (int)((avail / warps - per_warp_fixed) / 16 * 16);
     if (const char *renv = getenv("IPP_BULK_RING")) ring = std::max(max_fp, std::min(ring, atoi(renv) / 16 * 16));
     e->bulk_warps = warps;
     e->bulk_ring = ring;
-    e->bulk_smem = (size_t)warps * ((size_t)ring + per_warp_fixed);
+    e->bulk_smem = (size_t)warps * ((size_t)ring + per_warp_fixed) + per_cta;
     for (int v = 0; v < 12; ++v)
-        if (cudaFuncSetAttribute(bulk_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->bulk_smem) != cudaSuccess) {
+        if (cudaFuncSetAttribute(bulk_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem) != cudaSuccess) {  // per function, not per engine
             cudaGetLastError();
             return IPP_OK;
         }
@@ -1145,8 +1151,11 @@ extern "C" int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *
         if ((rc = ensure(e, &e->d_noise, &e->cap_noise, B * (size_t)noise_stride)) != IPP_OK) return rc;
         CU(e, cudaMemcpyAsync(e->d_noise, noise, B * (size_t)noise_stride * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     }
-    if (measurements)
+    if (measurements) {
         if ((rc = ensure(e, &e->d_z, &e->cap_z, B * (size_t)noise_stride)) != IPP_OK) return rc;
+        // entries past an env's measurement count are unspecified by the kernels: hand back zeros, not stale device memory
+        CU(e, cudaMemsetAsync(e->d_z, 0, B * (size_t)noise_stride * sizeof(float), e->stream));
+    }
     rc = ipp_step_device(e, ids_dev, poses ? e->d_poses : nullptr, noise ? e->d_noise : nullptr, noise_stride,
                          reward_dev ? reward_dev : e->d_reward, measurements ? e->d_z : nullptr, flags);
     if (rc != IPP_OK) return rc;
@@ -1219,6 +1228,7 @@ extern "C" int ipp_measure(ipp_engine *e, const int32_t *action_ids, const doubl
     const size_t B = (size_t)e->cfg.batch;
     if ((rc = ensure_job_buffers(e, B)) != IPP_OK) return rc;
     if ((rc = ensure(e, &e->d_z, &e->cap_z, B * (size_t)stride)) != IPP_OK) return rc;
+    CU(e, cudaMemsetAsync(e->d_z, 0, B * (size_t)stride * sizeof(float), e->stream));
     if (action_ids) CU(e, cudaMemcpyAsync(e->d_actions, action_ids, B * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
     if (poses) CU(e, cudaMemcpyAsync(e->d_poses, poses, 3 * B * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     if (noise) {

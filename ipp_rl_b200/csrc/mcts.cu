@@ -297,29 +297,44 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
         node_pose(p, a, t, node, ccol, crow, lvl, nx, ny, nh);
         float *P = a.P + ((size_t)t * d.M + node) * d.W;
         const bool noisy = node == 0 && root_noise != nullptr && d.dir_eps > 0.0f;
-        // get_next_actions_mask (mcts.py:148-158) and policy * mask (mcts.py:220)
+        // get_next_actions_mask (mcts.py:148-158) and policy * mask (mcts.py:220).  Slot s = (lvl * D + a) * D + b is the cell
+        // (ccol + a - r, crow + b - r) at altitude level lvl: lanes run over b, the warp over (lvl, a), so the column part of
+        // the pose / distance / in-grid test is warp-uniform, the row part a per-lane constant, and no slot index is ever
+        // divided (the s = lane, lane + 32, ... sweep spent ~115 instructions per slot on two integer divisions and three
+        // fp64 poses; this one ~15).  Same arithmetic as slot_pose() / job_dist(): bit-identical priors.
+        // Every reference call site leaves uav_specificaion = None: the mask compares the Euclidean distance with the budget
+        // even when costs are flight times (quirk, reproduced; the budget is decremented by the cost).
         float sum = 0.0f;
         int n_valid = 0;
-        for (int s = lane; s < d.W; s += 32) {
-            const Slot c = slot_cell(d, p, s, ccol, crow);
-            float pr = -1.0f;
-            if (c.in_grid) {
-                double ax, ay, ah;
-                slot_pose(p, c, ax, ay, ah);
-                // every reference call site leaves uav_specificaion = None: the mask compares the Euclidean distance with
-                // the budget even when costs are flight times (quirk, reproduced; the budget is decremented by the cost)
-                const float dist = job_dist(ax, ay, ah, nx, ny, nh);
-                if (dist > 0.0f && dist <= budget && dist < d.max_dist) {
-                    pr = priors_window ? priors_window[(size_t)t * d.W + s]
-                                       : (priors_dense ? priors_dense[(size_t)t * num_actions + c.lvl * (p.X * p.Y) + p.X * c.col + c.row] : 1.0f);
-                    pr = fmaxf(pr, 0.0f);
-                    if (noisy) pr = (1.0f - d.dir_eps) * pr;
-                    sum += pr;
-                    if (noisy) pr += d.dir_eps * root_noise[(size_t)t * d.W + s];
-                    ++n_valid;
+        const double half_res = __dmul_rn(0.5, p.res);
+        const int N = p.X * p.Y;
+        for (int b0 = 0; b0 < d.D; b0 += 32) {
+            const int b = b0 + lane;
+            const int row = crow + b - d.r;
+            const bool row_ok = b < d.D && row >= 0 && row < p.Y;
+            const float dy = (float)(__dadd_rn(__dmul_rn(p.res, (double)row), half_res) - ny);
+            for (int l = 0; l < d.L; ++l) {
+                const float dz = (float)(p.lut[l].alt - nh);
+                const float dyz = fmaf(dy, dy, dz * dz);
+                for (int a_ = 0; a_ < d.D; ++a_) {
+                    const int col = ccol + a_ - d.r;
+                    const bool col_ok = col >= 0 && col < p.X;
+                    const float dx = (float)(__dadd_rn(__dmul_rn(p.res, (double)col), half_res) - nx);
+                    const float dist = fast_sqrt(fmaf(dx, dx, dyz));
+                    const int sl = (l * d.D + a_) * d.D + b;
+                    float pr = -1.0f;
+                    if (row_ok && col_ok && dist > 0.0f && dist <= budget && dist < d.max_dist) {
+                        pr = priors_window ? priors_window[(size_t)t * d.W + sl]
+                                           : (priors_dense ? priors_dense[(size_t)t * num_actions + l * N + p.X * col + row] : 1.0f);
+                        pr = fmaxf(pr, 0.0f);
+                        if (noisy) pr = (1.0f - d.dir_eps) * pr;
+                        sum += pr;
+                        if (noisy) pr += d.dir_eps * root_noise[(size_t)t * d.W + sl];
+                        ++n_valid;
+                    }
+                    if (b < d.D) P[sl] = pr;
                 }
             }
-            P[s] = pr;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

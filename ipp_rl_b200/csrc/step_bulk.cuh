@@ -9,9 +9,14 @@
 // the layout of the run, so one tile-local index serves the staged read and the HBM write-back of a quad.
 //
 // Per warp: a byte ring in shared memory holding up to kBulkDepth footprints in flight (small footprints -> deeper
-// prefetch), one mbarrier per in-flight footprint, a ring of 32-byte plans (everything warp-uniform about an env-step is
+// prefetch), one mbarrier per in-flight footprint, a ring of 48-byte plans (everything warp-uniform about an env-step is
 // computed once, by one lane, when the warp takes a chunk of tickets: lane i plans ticket base + i).  No block-level
 // synchronisation in the loop.  Work distribution: global ticket counter, guided self-scheduling (as step_async.cuh).
+//
+// Lane layout: a footprint's quad grid (nqy x nqx quads of 2 x 2 cells) is swept in passes of RP = 32 / nqx whole quad rows:
+// lane = (qy mod RP) * nqx + qx.  Everything that depends on the quad COLUMN (tile column, in-tile offsets, border clamps,
+// INTER_AREA column weights) is computed once per env and lane; a pass only advances the row part.  The rf = 2 noise stream
+// is defined on the same layout (quad_math.cuh draw_normals): one Philox call serves a lane for four passes.
 //
 // INTER_AREA (rf = 2) on unscrambled odd footprints needs no tap tables: output o of n integrates inputs {2o-1, 2o, 2o+1}
 // with weights {o, n, n-1-o} / (2n-1) — the quad's own 2 x 2 cells plus the row above and the column to the left; the
@@ -37,6 +42,9 @@ namespace ipp {
 #ifndef IPP_BULK_GUIDE
 #define IPP_BULK_GUIDE 3
 #endif
+#ifndef IPP_BULK_TARGET_DEPTH
+#define IPP_BULK_TARGET_DEPTH 3  // after a consumed footprint: stage one, and more while fewer than this many are in flight
+#endif
 #ifndef IPP_BULK_ENDGAME_DEPTH
 #define IPP_BULK_ENDGAME_DEPTH 2  // in-flight footprints per warp once the chunks have shrunk to one ticket
 #endif
@@ -56,18 +64,24 @@ struct BulkParams {
     int ring_bytes;         // per-warp staging ring (multiple of 16, >= the largest footprint)
 };
 
-// Per-env plan (32 B in shared memory), written by the planning lane; ring_off by the lane that starts the copies.
+// Per-env plan (48 B in shared memory), written by the planning lane; ring_off by the lane that starts the copies.
 struct __align__(16) BulkPlan {
-    int job;          // < 0: out of work
-    int geo;          // xl | yu << 16
-    int dims;         // nx | ny << 8 | nqx << 16 | nqy << 24
-    int tiles;        // ntx | ntr << 8 | lvl << 16 | flags << 24   (flags: 1 rf == 2, 2 analytic INTER_AREA taps, 4 unsupported)
-    int magic_x;      // floor(65536 / nqx) + 1
-    float inv_cost1;  // 1 / (cost + 1)
-    int ring_off;     // byte offset of the staged footprint in the warp's ring
-    int outs;         // out_r | out_c << 8
+    int job;           // < 0: out of work
+    int geo;           // xl | yu << 16
+    int dims;          // nx | ny << 8 | nqx << 16 | nqy << 24
+    int tiles;         // ntx | ntr << 8 | lvl << 16 | flags << 24   (flags: 1 rf == 2, 2 analytic INTER_AREA taps, 4 unsupported,
+                       //                                              8 analytic weights = the level's table entry)
+    unsigned src_lo;   // byte offset of the footprint's first super-tile from the start of the belief array (64 bit)
+    unsigned src_hi;
+    int sizes;         // bytes per staged tile row | ntr << 16
+    int ring_off;      // byte offset of the staged footprint in the warp's ring
+    int magic_x;       // floor(65536 / nqx) + 1
+    int rpw;           // RP | (RP * nqx) << 8: quad rows per pass, lanes in use
+    float inv_cost1;   // 1 / (cost + 1)
+    int outs;          // out_r | out_c << 8
 };
-static_assert(sizeof(BulkPlan) == 32, "BulkPlan layout");
+static_assert(sizeof(BulkPlan) == 48, "BulkPlan layout");
+constexpr int kBulkMaxLevels = IPP_MAX_ALTITUDE_LEVELS;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -149,9 +163,11 @@ __device__ __forceinline__ void bulk_plan_env(const StepParams &p, bool quirk, b
             if (out_r > ny || out_c > nx) flags |= 4;
             // D[pr, pc] = D[qy, qx] and both axes decimate 2n-1 -> n: the quad's own cells + the row above / column to the left
             if ((nx & 1) && (ny & 1) && out_r == nqy && out_c == nqx) flags |= 2;
+            if (nx == min(2 * L.rx + 1, p.X) && ny == min(2 * L.ry + 1, p.Y)) flags |= 8;
         }
     }
     const int magic_x = (int)((uint32_t)(65536.0f * fast_rcp((float)nqx) * 1.00000012f) + 1u);
+    const int rp = max(1, (32 * magic_x) >> 16);  // 32 / nqx (the host guarantees nqx <= 32)
     const double px = __dadd_rn(__dmul_rn(p.res, (double)col), __dmul_rn(0.5, p.res));
     const double py = __dadd_rn(__dmul_rn(p.res, (double)row), __dmul_rn(0.5, p.res));
     const float cost = job_cost(p, px, py, L.alt, q0, q1, q2);
@@ -161,9 +177,12 @@ __device__ __forceinline__ void bulk_plan_env(const StepParams &p, bool quirk, b
         ps[2] = L.alt;
     }
     if (flags & 4) *(volatile int *)p.status = 1;  // mapped host word, bit 0 is the only bit
+    const unsigned long long src = (unsigned long long)job * (p.plane * sizeof(float2)) +
+                                   (unsigned long long)((yu >> 2) * p.txm + (xl >> 2)) * kSuperTileBytes;
     int4 *o = reinterpret_cast<int4 *>(out);
     o[0] = make_int4(job, xl | (yu << 16), nx | (ny << 8) | (nqx << 16) | (nqy << 24), ntx | (ntr << 8) | (lvl << 16) | (flags << 24));
-    o[1] = make_int4(magic_x, __float_as_int(fast_rcp(cost + 1.0f)), 0, out_r | (out_c << 8));
+    o[1] = make_int4((int)(unsigned)(src & 0xffffffffull), (int)(unsigned)(src >> 32), (ntx * kSuperTileBytes) | (ntr << 16), 0);
+    o[2] = make_int4(magic_x, rp | ((rp * nqx) << 8), __float_as_int(fast_rcp(cost + 1.0f)), out_r | (out_c << 8));
 }
 
 // MODE: MODE_KALMAN (full step) or MODE_PREDICT (covariance only: no ground truth, no noise; the staged run still carries
@@ -175,9 +194,12 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned char *after = smem_raw + (size_t)bp.warps * bp.ring_bytes;
     BulkPlan *plans = reinterpret_cast<BulkPlan *>(after) + w * kBulkPlanRing;
-    float2 *taps = reinterpret_cast<float2 *>(after + (size_t)bp.warps * kBulkPlanRing * sizeof(BulkPlan)) + (size_t)w * kBulkTapFloats2;
-    const uint32_t bars = smem_addr(after + (size_t)bp.warps * (kBulkPlanRing * sizeof(BulkPlan) + kBulkTapFloats2 * sizeof(float2))) +
-                          (uint32_t)(w * kBulkDepth * 8);
+    after += (size_t)bp.warps * kBulkPlanRing * sizeof(BulkPlan);
+    float2 *taps = reinterpret_cast<float2 *>(after) + (size_t)w * kBulkTapFloats2;
+    after += (size_t)bp.warps * kBulkTapFloats2 * sizeof(float2);
+    float4 *lvl_tab = reinterpret_cast<float4 *>(after);  // [level]{R, 1/R, s2, 0}, {1/nx, nqx/nx, 1/ny, nqy/ny} of the unclipped footprint
+    after += (size_t)kBulkMaxLevels * 2 * sizeof(float4);
+    const uint32_t bars = smem_addr(after) + (uint32_t)(w * kBulkDepth * 8);
     const uint32_t ring = smem_addr(smem_raw) + (uint32_t)(w * bp.ring_bytes);
     const int cap = bp.ring_bytes;
 
@@ -185,6 +207,13 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
 #pragma unroll
         for (int k = 0; k < kBulkDepth; ++k) mbar_init(bars + 8u * k, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((int)threadIdx.x < p.n_levels) {
+        const AltLevel &L = p.lut[threadIdx.x];
+        const int fw = min(2 * L.rx + 1, p.X), fh = min(2 * L.ry + 1, p.Y);
+        const float inx = __frcp_rn((float)fw), iny = __frcp_rn((float)fh);  // == 1.0f / (float)n_in of make_tap_entry
+        lvl_tab[2 * threadIdx.x] = make_float4(L.R, fast_rcp(L.R), L.s2, 0.0f);
+        lvl_tab[2 * threadIdx.x + 1] = make_float4(inx, (float)((fw + 1) >> 1) * inx, iny, (float)((fh + 1) >> 1) * iny);
     }
     __syncthreads();
 
@@ -195,37 +224,25 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
     const bool quirk = (p.flags & IPP_FLAG_NO_DSIZE_QUIRK) == 0;
     const bool commit = (p.flags & IPP_FLAG_NO_COMMIT) == 0;
     const bool write_prev = commit && (p.flags & IPP_FLAG_KEEP_PREV) == 0;
-    const int txs = p.txm;
-    const unsigned char *plane0 = reinterpret_cast<const unsigned char *>(p.mean);
-    const size_t env_bytes = p.plane * sizeof(float2);
+    const int grow = p.txm * kSuperTileBytes;  // HBM tile-row stride [bytes]
+    unsigned char *plane0 = reinterpret_cast<unsigned char *>(p.mean);
 
     // ---- plan ring: [c_pos, f_pos) staged (in flight), [f_pos, q_tail) planned, not yet staged ------------------------
     int c_pos = 0, f_pos = 0, q_tail = 0;
-    int n_if = 0, n_wait = 0;  // staged / planned-not-staged
+    int n_if = 0, n_wait = 0;     // staged / planned-not-staged
     unsigned int fi = 0, ci = 0;  // staged / consumed so far (mbarrier slot and phase)
     int r_head = 0, r_tail = 0;   // byte ring: oldest staged footprint / next free byte
     int max_if = kBulkDepth;
 
-    auto plan_chunk = [&](unsigned int base, int cnt) {  // lane i plans ticket base + i
-        if (lane < cnt) {
-            const unsigned int t = base + (unsigned)lane;
-            bulk_plan_env<MODE>(p, quirk, write_prev, t < (unsigned)n_jobs ? (int)t : -1, plans + ((q_tail + lane) & (kBulkPlanRing - 1)));
-        }
-        q_tail = (q_tail + cnt) & (kBulkPlanRing - 1);
-        n_wait += cnt;
-        __syncwarp();
-    };
-
-    // Stage the next planned footprint if the ring has room for it (warp-uniform; lane 0 issues the copies).
+    // Stage the next planned footprint if the ring has room for it (warp-uniform; one lane per tile row issues its copy).
     auto try_fill = [&]() -> bool {
         if (n_wait == 0 || n_if >= max_if) return false;
         BulkPlan *pl = plans + f_pos;
-        const int4 a = *reinterpret_cast<const int4 *>(pl);
-        int off = r_tail;
-        if (a.x >= 0) {
-            const int ntx = a.w & 255, ntr = (a.w >> 8) & 255;
-            const int row_bytes = ntx * kSuperTileBytes, bytes = ntr * row_bytes;
-            off = -1;
+        if (pl->job >= 0) {
+            const int4 b = *reinterpret_cast<const int4 *>(&pl->src_lo);
+            const int row_bytes = b.z & 0xffff, ntr = b.z >> 16;
+            const int bytes = ntr * row_bytes;
+            int off = -1;
             if (n_if == 0)
                 off = 0;
             else if (r_tail > r_head) {
@@ -237,19 +254,14 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                 if (r_tail + bytes <= r_head) off = r_tail;
             }
             if (off < 0) return false;
+            const uint32_t bar = bars + 8u * (fi & (kBulkDepth - 1));
             if (lane == 0) {
-                const int xl = a.y & 0xffff, yu = a.y >> 16;
-                const uint32_t bar = bars + 8u * (fi & (kBulkDepth - 1));
-                const unsigned char *src = plane0 + (size_t)a.x * env_bytes + (size_t)((yu >> 2) * txs + (xl >> 2)) * kSuperTileBytes;
-                uint32_t dst = ring + (uint32_t)off;
                 mbar_expect_tx(bar, (uint32_t)bytes);
-#pragma unroll 1
-                for (int k = 0; k < ntr; ++k) {
-                    bulk_g2s(dst, src, (uint32_t)row_bytes, bar);
-                    src += (size_t)txs * kSuperTileBytes;
-                    dst += (uint32_t)row_bytes;
-                }
                 pl->ring_off = off;
+            }
+            if (lane < ntr) {
+                const unsigned char *src = plane0 + (((unsigned long long)(unsigned)b.y << 32) | (unsigned)b.x) + (size_t)lane * grow;
+                bulk_g2s(ring + (uint32_t)(off + lane * row_bytes), src, (uint32_t)row_bytes, bar);
             }
             if (n_if == 0) r_head = off;
             r_tail = off + bytes;
@@ -264,7 +276,7 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
     // The first pass of the loop finds nothing staged: it only takes the warp's first chunk of tickets, plans and stages it.
     unsigned int chunk_base = 0;
     bool exhausted = false;  // no ticket left behind this warp's last chunk
-    const float inv_guide = 1.0f / (float)(max(IPP_BULK_GUIDE, 1) * (int)gridDim.x * bp.warps);
+    const float inv_guide = __frcp_rn((float)(max(IPP_BULK_GUIDE, 1) * (int)gridDim.x * bp.warps));
 
 #pragma unroll 1
     while (true) {
@@ -283,91 +295,111 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
         if (n_if == 0) {  // nothing staged, hence nothing planned either: done unless a chunk has just been asked for
             if (!request) break;
         } else {
-        const BulkPlan *pl = plans + c_pos;
-        const int4 pa = *reinterpret_cast<const int4 *>(pl);
-        const int job = pa.x;
-        if (job < 0) break;  // warp-uniform: tickets are monotonic, every later plan is empty too
-        const int4 pb = *reinterpret_cast<const int4 *>(&pl->magic_x);
-        mbar_wait(bars + 8u * (ci & (kBulkDepth - 1)), (ci / kBulkDepth) & 1u);
+            const BulkPlan *pl = plans + c_pos;
+            const int4 pa = *reinterpret_cast<const int4 *>(pl);
+            const int job = pa.x;
+            if (job < 0) break;  // warp-uniform: tickets are monotonic, every later plan is empty too
+            const int4 pb = *reinterpret_cast<const int4 *>(&pl->src_lo);
+            const int4 pc = *reinterpret_cast<const int4 *>(&pl->magic_x);
+            mbar_wait(bars + 8u * (ci & (kBulkDepth - 1)), (ci / kBulkDepth) & 1u);
 
-        const int xl = pa.y & 0xffff, yu = pa.y >> 16;
-        const int nx = pa.z & 255, ny = (pa.z >> 8) & 255, nqx = (pa.z >> 16) & 255, nqy = (pa.z >> 24) & 255;
-        const int ntx = pa.w & 255, lvl = (pa.w >> 16) & 255, pflags = (pa.w >> 24) & 255;
-        const int rf = (pflags & 1) ? 2 : 1;
-        const bool analytic = (pflags & 2) != 0, unsupported = (pflags & 4) != 0;
-        const int out_r = pb.w & 255, out_c = (pb.w >> 8) & 255;
-        const uint32_t magic_x = (uint32_t)pb.x;
-        const uint32_t slot = ring + (uint32_t)pb.z;
-        const int a4 = xl & 3, b4 = yu & 3;
-        const int srow = ntx * kSuperTileBytes;                 // staged tile-row stride [bytes]
-        const int grow = txs * kSuperTileBytes;                 // HBM tile-row stride [bytes]
-        const int dts = grow - srow;
-        unsigned char *gbase = const_cast<unsigned char *>(plane0) + (size_t)job * env_bytes + (size_t)((yu >> 2) * txs + (xl >> 2)) * kSuperTileBytes;
-        const int nq = nqx * nqy;
+            const int xl = pa.y & 0xffff, yu = pa.y >> 16;
+            const int nx = pa.z & 255, ny = (pa.z >> 8) & 255, nqx = (pa.z >> 16) & 255, nqy = (pa.z >> 24) & 255;
+            const int ntx = pa.w & 255, lvl = (pa.w >> 16) & 255, pflags = pa.w >> 24;
+            const int rf = (pflags & 1) ? 2 : 1;
+            const bool analytic = (pflags & 2) != 0, unsupported = (pflags & 4) != 0;
+            const uint32_t slot = ring + (uint32_t)pb.w;
+            const int srow = pb.z & 0xffff;  // staged tile-row stride [bytes]
+            const int a4 = xl & 3, b4 = yu & 3;
+            unsigned char *gbase = plane0 + (((unsigned long long)(unsigned)pb.y << 32) | (unsigned)pb.x);
+            const int RP = pc.y & 255, W = pc.y >> 8;
 
-        const AltLevel &L = p.lut[lvl];
-        FuseCtx fc;
-        fc.rf = rf;
-        fc.R = L.R;
-        fc.invR = fast_rcp(L.R);
-        const float s2 = L.s2;
+            const float4 la = lvl_tab[2 * lvl];
+            FuseCtx fc;
+            fc.rf = rf;
+            fc.R = la.x;
+            fc.invR = la.y;
+            const float s2 = la.z;
 
-        // INTER_AREA: analytic weights, or this env's tap tables (clipped non-square footprints)
-        TapView tapv;
-        tapv.rows = taps;
-        tapv.cols = taps + 3 * kTapCap;
-        int tap_mode = TAPS_FAST;
-        float inv_nx = 0.f, inv_ny = 0.f, wmid_x = 0.f, wmid_y = 0.f;
-        if (MODE != MODE_PREDICT && rf == 2 && !unsupported) {
-            if (analytic) {
-                inv_nx = __frcp_rn((float)nx);  // == 1.0f / (float)n_in of make_tap_entry
-                inv_ny = __frcp_rn((float)ny);
-                wmid_x = (float)nqx * inv_nx;
-                wmid_y = (float)nqy * inv_ny;
-            } else {
-                tap_mode = build_tap_tables<kTapCap>(taps, lane, ny, nx, out_r, out_c);
+            // INTER_AREA: analytic weights, or this env's tap tables (clipped non-square footprints)
+            TapView tapv;
+            tapv.rows = taps;
+            tapv.cols = taps + 3 * kTapCap;
+            int tap_mode = TAPS_FAST;
+            int out_c = 1;
+            float inv_outc = 0.f;
+            float inv_nx = 0.f, inv_ny = 0.f, wmid_x = 0.f, wmid_y = 0.f;
+            if (MODE != MODE_PREDICT && rf == 2 && !unsupported) {
+                if (analytic && (pflags & 8)) {  // the unclipped footprint of this level: weights from the table
+                    const float4 lb = lvl_tab[2 * lvl + 1];
+                    inv_nx = lb.x;
+                    wmid_x = lb.y;
+                    inv_ny = lb.z;
+                    wmid_y = lb.w;
+                } else if (analytic) {
+                    inv_nx = __frcp_rn((float)nx);  // == 1.0f / (float)n_in of make_tap_entry
+                    inv_ny = __frcp_rn((float)ny);
+                    wmid_x = (float)nqx * inv_nx;
+                    wmid_y = (float)nqy * inv_ny;
+                } else {
+                    const int out_r = pc.w & 255;
+                    out_c = (pc.w >> 8) & 255;
+                    inv_outc = __frcp_rn((float)out_c);
+                    tap_mode = build_tap_tables<kTapCap>(taps, lane, ny, nx, out_r, out_c);
+                }
             }
-        }
-        const float inv_outc = (MODE != MODE_PREDICT && rf == 2 && !analytic) ? __frcp_rn((float)out_c) : 0.f;
-        const size_t nrow = (size_t)job * (size_t)p.noise_stride;
-        float acc = 0.0f;
-        float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four iterations
+            const size_t nrow = (size_t)job * (size_t)p.noise_stride;
+            float acc = 0.0f;
+            float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four passes
 
-        if (!unsupported) {
+            // ---- this lane's quad column: everything that does not change from pass to pass ------------------------------
+            const int qy0 = (int)(((uint32_t)lane * (uint32_t)pc.x) >> 16);
+            const int qx = lane - qy0 * nqx;
+            const int c0 = 2 * qx;
+            const bool cok = c0 + 1 < nx;
+            const int cc = a4 + c0, ic = cc & 3;
+            const bool last_c = ic == 3;
+            const int col_s = (cc >> 2) * kSuperTileBytes + (ic << 3);        // {mean,var} of column c0 inside a tile row [bytes]
+            const int col_q = (cc >> 2) * kSuperTileBytes + 128 + (ic << 2);  // ground truth of column c0
+            const int dCg = last_c ? 168 : 8;                                 // to column c0 + 1 ({mean,var})
+            const int dC = cok ? dCg : 0;                                     // ... clamped inside the footprint
+            const int dCq = cok ? (last_c ? 180 : 4) : 0;                     // ... ground truth
+            const int dL = qx > 0 ? ((ic == 0) ? -180 : -4) : 0;              // to column c0 - 1 (ground truth), clamped
+            const float wl = (float)qx * inv_nx, wr_ = (float)(nqx - 1 - qx) * inv_nx;
+            const int nqy_l = (lane < W && !unsupported) ? nqy : 0;
+            const bool odd = (a4 & 1) != 0;  // warp-uniform: (c0, c0 + 1) do not share a 16-byte chunk
+
+            int it = 0;
 #pragma unroll 1
-            for (int q = lane; q < nq; q += 32) {
-                const int qy = (int)(((uint32_t)q * magic_x) >> 16);
-                const int qx = q - qy * nqx;
-                const int r0 = 2 * qy, c0 = 2 * qx;
-                const bool cok = c0 + 1 < nx, rok = r0 + 1 < ny;
-                const bool ok[4] = {true, cok, rok, cok && rok};
-                // tile-local coordinates: one index for the staged read and the HBM write-back
-                const int rr = b4 + r0, cc = a4 + c0;
-                const int trl = rr >> 2, ir = rr & 3, ic = cc & 3;
-                const int t192 = (trl * ntx + (cc >> 2)) * kSuperTileBytes;
-                const int inner = (ir << 5) | (ic << 3);
-                const uint32_t so = slot + (uint32_t)(t192 + inner);        // {mean,var} of cell (r0, c0), staged
-                unsigned char *go = gbase + (t192 + inner + trl * dts);     // ... and in HBM
-                const bool last_r = ir == 3, last_c = ic == 3;
-                const int dRs = rok ? (last_r ? srow - 96 : 32) : 0;        // to the quad's second row (clamped inside the footprint)
+            for (int qy = qy0; qy < nqy_l; qy += RP, ++it) {
+                const int r0 = 2 * qy;
+                const bool rok = r0 + 1 < ny;
+                const bool ok3 = cok && rok;
+                const int rr = b4 + r0, trl = rr >> 2, ir = rr & 3;
+                const bool last_r = ir == 3;
+                const int row_s = trl * srow;
+                const uint32_t so = slot + (uint32_t)(row_s + (ir << 5) + col_s);  // {mean,var} of cell (r0, c0), staged
+                unsigned char *go = gbase + (trl * grow + (ir << 5) + col_s);      // ... and in HBM
+                const int dRs = rok ? (last_r ? srow - 96 : 32) : 0;               // to the quad's second row (clamped inside the footprint)
                 const int dRg = last_r ? grow - 96 : 32;
-                const int dC = cok ? (last_c ? 168 : 8) : 0;                // to the quad's second column
 
                 float4 top, bot;
-                if (a4 & 1) {
+                if (odd) {
                     const float2 t0 = lds64(so), t1 = lds64(so + dC), b0 = lds64(so + dRs), b1 = lds64(so + dRs + dC);
                     top = make_float4(t0.x, t0.y, t1.x, t1.y);
                     bot = make_float4(b0.x, b0.y, b1.x, b1.y);
-                } else {  // warp-uniform: (c0, c0 + 1) share a 16-byte chunk
+                } else {
                     top = lds128(so);
                     bot = lds128(so + dRs);
                 }
-                const float m[4] = {top.x, cok ? top.z : 0.0f, rok ? bot.x : 0.0f, ok[3] ? bot.z : 0.0f};
-                const float v[4] = {top.y, cok ? top.w : 0.0f, rok ? bot.y : 0.0f, ok[3] ? bot.w : 0.0f};
+                const float m[4] = {top.x, cok ? top.z : 0.0f, rok ? bot.x : 0.0f, ok3 ? bot.z : 0.0f};
+                const float v[4] = {top.y, cok ? top.w : 0.0f, rok ? bot.y : 0.0f, ok3 ? bot.w : 0.0f};
+                const bool ok[4] = {true, cok, rok, ok3};
 
                 // ---- measurement --------------------------------------------------------------------------------
                 float z[4] = {0.f, 0.f, 0.f, 0.f};
                 if (MODE != MODE_PREDICT) {
+                    const int q = qy * nqx + qx;
                     float eps[4];
                     if (EXTRAS && p.noise != nullptr) {
                         if (rf == 1) {
@@ -377,14 +409,13 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                             eps[0] = __ldg(p.noise + nrow + q);
                         }
                     } else {
-                        draw_normals(p, rf, q, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
+                        draw_normals_strip(p, rf, q, lane, it, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
                     }
-                    const uint32_t gs = slot + (uint32_t)(t192 + 128 + (inner >> 1));  // gt of cell (r0, c0), staged
+                    const uint32_t gs = slot + (uint32_t)(row_s + (ir << 4) + col_q);  // gt of cell (r0, c0), staged
                     const int dRq = rok ? (last_r ? srow - 48 : 16) : 0;
-                    const int dCq = cok ? (last_c ? 180 : 4) : 0;
                     if (rf == 1) {
                         float gv[4];
-                        if (a4 & 1) {
+                        if (odd) {
                             gv[0] = lds32(gs);
                             gv[1] = lds32(gs + dCq);
                             gv[2] = lds32(gs + dRq);
@@ -401,8 +432,6 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                     } else if (analytic) {
                         // rows {r0-1, r0, r0+1} x cols {c0-1, c0, c0+1}; taps with weight 0 are clamped onto the quad's own cells
                         const int dU = qy > 0 ? ((ir == 0) ? -(srow - 48) : -16) : 0;
-                        const int dL = qx > 0 ? ((ic == 0) ? -180 : -4) : 0;
-                        const float wl = (float)qx * inv_nx, wr_ = (float)(nqx - 1 - qx) * inv_nx;
                         const float wu = (float)qy * inv_ny, wb = (float)(nqy - 1 - qy) * inv_ny;
                         float rs[3];
                         const int dro[3] = {dU, 0, dRq};
@@ -410,7 +439,7 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                         for (int k = 0; k < 3; ++k) {
                             const uint32_t ra = gs + dro[k];
                             float g0, g1;
-                            if (a4 & 1) {
+                            if (odd) {
                                 g0 = lds32(ra);
                                 g1 = lds32(ra + dCq);
                             } else {
@@ -426,8 +455,8 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                         d = fmaf(wb, rs[2], d);
                         z[0] = __saturatef(fmaf(s2, eps[0], d));
                     } else {
-                        const int pr = fdiv(q, out_c, inv_outc), pc = q - pr * out_c;
-                        const float d = downsample(tap_mode, GtSuperShared{slot, ntx, a4, b4}, tapv, pr, pc, ny, nx, out_r, out_c);
+                        const int pr = fdiv(q, out_c, inv_outc), pcc = q - pr * out_c;
+                        const float d = downsample(tap_mode, GtSuperShared{slot, ntx, a4, b4}, tapv, pr, pcc, ny, nx, pc.w & 255, out_c);
                         z[0] = __saturatef(fmaf(s2, eps[0], d));
                     }
                     if (EXTRAS && p.z_out != nullptr) {
@@ -452,12 +481,11 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                     for (int k = 0; k < 4; ++k) mn[k] = m[k];
                 }
                 if (MODE != MODE_PREDICT || commit) {
-                    if (a4 & 1) {
-                        const int dCg = last_c ? 168 : 8;
+                    if (odd) {
                         *reinterpret_cast<float2 *>(go) = make_float2(mn[0], vn[0]);
                         if (cok) *reinterpret_cast<float2 *>(go + dCg) = make_float2(mn[1], vn[1]);
                         if (rok) *reinterpret_cast<float2 *>(go + dRg) = make_float2(mn[2], vn[2]);
-                        if (ok[3]) *reinterpret_cast<float2 *>(go + dRg + dCg) = make_float2(mn[3], vn[3]);
+                        if (ok3) *reinterpret_cast<float2 *>(go + dRg + dCg) = make_float2(mn[3], vn[3]);
                     } else if (cok) {
                         *reinterpret_cast<float4 *>(go) = make_float4(mn[0], vn[0], mn[1], vn[1]);
                         if (rok) *reinterpret_cast<float4 *>(go + dRg) = make_float4(mn[2], vn[2], mn[3], vn[3]);
@@ -467,30 +495,39 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                     }
                 }
             }
-        }
 
-        // per-env information gain: fp32 partials per lane, fp32 tree across the warp; the cost term comes from the plan
-        float accd = acc;
+            // per-env information gain: fp32 partials per lane, fp32 tree across the warp; the cost term comes from the plan
+            float accd = acc;
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, sft);
-        if (lane == 0 && p.reward != nullptr) p.reward[job] = accd * __int_as_float(pb.y);
-        __syncwarp();  // every lane is done with the staged footprint, the plan and the tap tables
+            for (int sft = 16; sft > 0; sft >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, sft);
+            if (lane == 0 && p.reward != nullptr) p.reward[job] = accd * __int_as_float(pc.z);
+            __syncwarp();  // every lane is done with the staged footprint, the plan and the tap tables
 
-        // (C) release the footprint
-        ++ci;
-        c_pos = (c_pos + 1) & (kBulkPlanRing - 1);
-        --n_if;
-        if (n_if > 0) r_head = plans[c_pos].ring_off;
+            // (C) release the footprint
+            ++ci;
+            c_pos = (c_pos + 1) & (kBulkPlanRing - 1);
+            --n_if;
+            if (n_if > 0) r_head = plans[c_pos].ring_off;
         }
 
         // (D) plan the chunk requested at (A): lane i decodes ticket fresh + i
         if (request) {
             chunk_base = __shfl_sync(0xffffffffu, fresh, 0);
             exhausted = chunk_base + (unsigned)req >= (unsigned)n_jobs;
-            if (chunk_base < (unsigned)n_jobs) plan_chunk(chunk_base, req);
+            if (chunk_base < (unsigned)n_jobs) {
+                if (lane < req) {
+                    const unsigned int t = chunk_base + (unsigned)lane;
+                    bulk_plan_env<MODE>(p, quirk, write_prev, t < (unsigned)n_jobs ? (int)t : -1, plans + ((q_tail + lane) & (kBulkPlanRing - 1)));
+                }
+                q_tail = (q_tail + req) & (kBulkPlanRing - 1);
+                n_wait += req;
+                __syncwarp();
+            }
         }
-        // (E) stage what fits
-        while (try_fill()) {
+        // (E) stage what fits: one footprint per consumed one, more while the pipeline is shallow
+        if (try_fill()) {
+            while (n_if < IPP_BULK_TARGET_DEPTH && try_fill()) {
+            }
         }
         __syncwarp();  // ring_off of the freshly staged footprints is visible to every lane
     }

@@ -81,6 +81,48 @@ def gather_experience(local: dict, total_envs: int, group=None) -> dict:
     return {k: gather_rows(v, total_envs, group) for k, v in local.items()}
 
 
+def gather_rows_to(local, total_envs: int, dst: int = 0, group=None):
+    """Gather per-env rows to ONE rank (the learner): what the trainer's experience buffer needs without
+    making every rank receive every other rank's rows.  Returns the (total_envs, ...) tensor on ``dst``, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    counts = all_shard_counts(total_envs, world)
+    if local.shape[0] != counts[rank]:
+        raise ValueError(f"local rows: {local.shape[0]}, this rank owns {counts[rank]} envs")
+    tail = tuple(local.shape[1:])
+    width = max(counts)
+    src = local.contiguous()
+    if counts[rank] != width:
+        src = torch.zeros((width,) + tail, dtype=local.dtype, device=local.device)
+        src[: counts[rank]] = local
+    if rank == dst:
+        parts = [torch.empty((width,) + tail, dtype=local.dtype, device=local.device) for _ in range(world)]
+        dist.gather(src, parts, dst=dst, group=group)
+        return torch.cat([p[:c] for p, c in zip(parts, counts)])
+    dist.gather(src, None, dst=dst, group=group)
+    return None
+
+
+def all_reduce_policy(policy: np.ndarray, group=None) -> np.ndarray:
+    """Root-parallel MCTS: sum of the visit-count policies of every rank's trees (the reference sums the policies of its
+    worker processes, planning/mcts_zero/mcts_zero_mission.py:516-521).  Identity when torch.distributed is not
+    initialised; NCCL (through a device tensor) or gloo otherwise."""
+    try:
+        import torch
+        import torch.distributed as dist
+    except Exception:  # pragma: no cover
+        return policy
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return policy
+    t = torch.from_numpy(np.ascontiguousarray(policy, dtype=np.float64))
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
 class ShardedEngine:
     """This rank's slice of a ``total_envs`` batch.  ``step`` takes / returns LOCAL arrays; ``global_slice``
     tells which rows of a global action array belong here."""

@@ -88,6 +88,8 @@ class EngineConfig:
         uav = exp.get("uav")
         if uav is not None:
             kw["max_v"], kw["max_a"] = float(uav["max_v"]), float(uav["max_a"])
+        else:  # uav_specifications=None in the reference: costs are Euclidean distances (planning/common/actions.py:8-16)
+            kw["max_v"] = kw["max_a"] = None
         backend = params.get("mapping", {}).get("b200", {})
         if "layout" in backend:
             kw["layout"] = capi.LAYOUT_NAMES[backend["layout"]]

@@ -50,12 +50,27 @@ class DiagonalCovariance:
         return self.var.size
 
 
-def covariance_diagonal(cov) -> np.ndarray:
-    """Diagonal of a covariance given as DiagonalCovariance, dense (N, N) array or (N,) / (Y, X) variances."""
+class VarianceMap(np.ndarray):
+    """(y_dim, x_dim) per-cell variances — what ``GridMap.var`` returns.  The type tells ``covariance_diagonal`` that a
+    SQUARE map is a variance map and not a dense (N, N) covariance (the two are indistinguishable by shape)."""
+
+    def __new__(cls, a):
+        return np.asarray(a, dtype=np.float64).view(cls)
+
+
+def covariance_diagonal(cov, num_cells: int = None) -> np.ndarray:
+    """Diagonal of a covariance given as DiagonalCovariance, dense (N, N) array, VarianceMap, or (N,) variances.
+
+    A plain square 2-D array is a dense covariance, as in the reference, unless ``num_cells`` says its SIZE is the number
+    of grid cells (then it is a (Y, X) variance map); non-square 2-D arrays are variance maps."""
     if isinstance(cov, DiagonalCovariance):
         return cov.var
+    if isinstance(cov, VarianceMap):
+        return np.asarray(cov).ravel()
     a = np.asarray(cov, dtype=np.float64)
     if a.ndim == 2 and a.shape[0] == a.shape[1] and a.shape[0] > 1:
+        if num_cells is not None and a.size == num_cells and a.shape[0] != num_cells:
+            return a.ravel()
         return np.ascontiguousarray(np.diag(a))
     return a.ravel()
 
@@ -88,7 +103,7 @@ class GridMap:
     @property
     def var(self) -> np.ndarray:
         """(y_dim, x_dim) view of the covariance diagonal — the quantity the engine stores."""
-        return covariance_diagonal(self.cov_matrix).reshape(self.y_dim, self.x_dim)
+        return VarianceMap(covariance_diagonal(self.cov_matrix, self.num_grid_cells).reshape(self.y_dim, self.x_dim))
 
     # CUDA handles do not survive pickling / fork: drop the device backend, the child re-creates it lazily
     def __getstate__(self):

@@ -79,7 +79,7 @@ class Mapping:
         backend = get_backend(self.grid_map)
         g = self.grid_map
         if predict_only:
-            var = covariance_diagonal(g.cov_matrix if current_cov_matrix is None else current_cov_matrix)
+            var = covariance_diagonal(g.cov_matrix if current_cov_matrix is None else current_cov_matrix, g.num_grid_cells)
             if cov_only:
                 _, var_n = backend.predict_from(var, measurement_position)
                 return None, DiagonalCovariance(var_n)
@@ -87,7 +87,7 @@ class Mapping:
             return mean_n, DiagonalCovariance(var_n)
         # committing update of the real belief; honour state the caller assigned to the grid map directly
         if current_cov_matrix is not None:
-            g.cov_matrix = DiagonalCovariance(covariance_diagonal(current_cov_matrix))
+            g.cov_matrix = DiagonalCovariance(covariance_diagonal(current_cov_matrix, g.num_grid_cells))
         self._push()
         if cov_only:
             _, var_n = backend.predict_from(g.var, measurement_position)
@@ -99,8 +99,55 @@ class Mapping:
         return None
 
     @staticmethod
-    def kalman_filter_update(*args, **kwargs):
-        raise NotImplementedError(
-            "The dense Kalman update (reference mapping/mappings.py:155-215) is fused into the CUDA step kernel in its "
-            "per-cell form; use Mapping.update_grid_map / BatchedEngine.step instead."
-        )
+    def kalman_filter_update(P, H, R, grid_mean=None, observation=None, cov_only: bool = False, device: int = 0):
+        """Static Kalman update (reference :155-215) for a DIAGONAL covariance and a measurement model whose rows have
+        disjoint supports and one weight per row — what ``sensor_model.measurement_model_matrix`` /
+        ``measurement_variance_matrix`` build.  Runs on the device (``ipp_kalman_blocks``, fp64): per block
+        ``S = w^2 sum v + R``, ``v' = v - (w v)^2 / S``, ``x' = x + (w v / S)(z - w sum x)``; the off-diagonals the dense update
+        would create inside a block are dropped.  Returns ``(x' flattened | None, DiagonalCovariance)``
+        like the reference returns ``(x, P)``.  A dense, non-diagonal ``P`` or overlapping rows of ``H`` raise ValueError."""
+        import ctypes as C
+
+        from .. import _capi as capi
+
+        H = np.asarray(H, dtype=np.float64)
+        if H.ndim != 2:
+            raise ValueError("H must be (num_measurements, num_grid_cells)")
+        m, n = H.shape
+        if not isinstance(P, DiagonalCovariance):
+            dense = np.asarray(P, dtype=np.float64)
+            if dense.shape == (n, n) and np.count_nonzero(dense - np.diag(np.diag(dense))):
+                logger.error("kalman_filter_update: dense covariances with off-diagonal entries are not supported by the per-cell engine")
+                raise ValueError("covariance must be diagonal")
+        var = np.array(covariance_diagonal(P, num_cells=n), dtype=np.float64, copy=True)
+        if var.size != n:
+            raise ValueError(f"covariance has {var.size} diagonal entries, H has {n} columns")
+        Rm = np.asarray(R, dtype=np.float64)
+        r_diag = np.ascontiguousarray(np.diag(Rm) if Rm.ndim == 2 else np.broadcast_to(Rm, (m,)))
+        rows, cols = np.nonzero(H)
+        if rows.size and np.bincount(cols, minlength=n).max() > 1:
+            raise ValueError("rows of H overlap: not a block measurement model")
+        counts = np.bincount(rows, minlength=m)
+        row_ptr = np.zeros(m + 1, np.int32)
+        np.cumsum(counts, out=row_ptr[1:])
+        weight = np.zeros(m)
+        if rows.size:
+            vals = H[rows, cols]
+            first = np.minimum(row_ptr[:-1], max(rows.size - 1, 0))
+            weight = np.where(counts > 0, vals[first], 0.0)
+            if np.any(vals != weight[rows]):
+                raise ValueError("rows of H must carry one weight each")
+        cols32 = np.ascontiguousarray(cols, dtype=np.int32)
+        weight = np.ascontiguousarray(weight, dtype=np.float64)
+        x = z = None
+        if not cov_only:
+            x = np.array(np.asarray(grid_mean, dtype=np.float64).flatten(order="C"), copy=True)
+            z = np.ascontiguousarray(np.asarray(observation, dtype=np.float64).flatten(order="C"))
+            if x.size != n or z.size != m:
+                raise ValueError("grid_mean / observation do not match H")
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        lib = capi.load_library()
+        rc = lib.ipp_kalman_blocks(int(device), n, m, ptr(row_ptr), ptr(cols32), ptr(weight), ptr(r_diag), ptr(z), ptr(var), ptr(x))
+        if rc != capi.IPP_OK:
+            raise capi.IppError(rc, "ipp_kalman_blocks failed")
+        return x, DiagonalCovariance(var)

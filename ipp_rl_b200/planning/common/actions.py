@@ -71,7 +71,9 @@ def get_actions(previous_action, remaining_budget, grid_map, min_altitude, max_a
     """All (cell centre, altitude level) poses reachable with 0 < cost <= budget, in the reference's order
     (row-major cells, altitude innermost; :44-66)."""
     res, X, Y = grid_map.resolution, grid_map.x_dim, grid_map.y_dim
-    lv = altitude_levels(min_altitude, max_altitude, altitude_spacing)
+    # the reference's candidate set steps by the spacing (:53-60), its id table uses linspace (:74): they differ whenever
+    # (max - min) is not a multiple of the spacing
+    lv = min_altitude + altitude_spacing * np.arange(int((max_altitude - min_altitude) / altitude_spacing) + 1)
     rows, cols, ks = np.meshgrid(np.arange(Y), np.arange(X), np.arange(len(lv)), indexing="ij")
     poses = np.stack([res * cols.ravel() + 0.5 * res, res * rows.ravel() + 0.5 * res, lv[ks.ravel()]], axis=1)
     prev = np.asarray(previous_action, float)

@@ -31,7 +31,7 @@ def greedy_search(previous_action, remaining_budget, current_state, episode_hori
     if (uav_specifications is None) != (backend.cfg.max_v is None):
         raise ValueError("uav_specifications must match the experiment.uav section the engine was configured with")
     waypoints = []
-    var = covariance_diagonal(current_state)
+    var = covariance_diagonal(current_state, mapping.grid_map.num_grid_cells)
     for _ in range(episode_horizon):
         candidates = get_actions(previous_action, remaining_budget, mapping.grid_map, min_altitude, max_altitude, altitude_spacing,
                                  uav_specifications)

@@ -9,7 +9,7 @@ from .actions import action_costs
 
 def compute_adaptive_msk(grid_mean: np.array, grid_covariance, value_threshold: float, interval_factor: float):
     """cells whose upper confidence value mean + k * variance reaches the threshold (variance, as in the reference)"""
-    return np.asarray(grid_mean).flatten(order="C") + interval_factor * covariance_diagonal(grid_covariance) >= value_threshold
+    return np.asarray(grid_mean).flatten(order="C") + interval_factor * covariance_diagonal(grid_covariance, int(np.size(grid_mean))) >= value_threshold
 
 
 def compute_reward(current_state, next_state, previous_action, action, uav_specifications: Dict = None, adaptive_msk=None) -> float:

@@ -35,7 +35,7 @@ def weighted_root_mean_squared_error(ground_truth_map, estimated_map) -> float:
 
 
 def _log_loss(ground_truth_map, estimated_map, cov):
-    p = covariance_diagonal(cov).reshape(np.shape(estimated_map))
+    p = covariance_diagonal(cov, int(np.size(estimated_map))).reshape(np.shape(estimated_map))
     return 0.5 * np.log(2 * np.pi * p) + np.square(ground_truth_map - estimated_map) / 2 * p  # "* p" as in the reference (:44)
 
 
