@@ -143,6 +143,22 @@ int ipp_reset(ipp_engine *e, float prior_mean, float prior_var, const float *pri
 int ipp_set_ground_truth(ipp_engine *e, const float *gt, int32_t first_env, int32_t n_env,
                          int32_t src_is_device);
 
+/* Piecewise-constant ground truths generated ON THE DEVICE for envs [first_env, first_env + n_env): replaces
+ * HotspotRandomField / SplitRandomField.create_ground_truth_map (simulations/simulations.py:57-92, :102-125).  Every env
+ * takes the reference's sequence of decisions (values, centres / cut, rejection of overlapping hot spots) with uniforms
+ * from Philox4x32-10 keyed by (seed; global env id, draw index) instead of NumPy's global MT19937: statistical parity,
+ * independent of how the batch is sharded. */
+#define IPP_FIELD_HOTSPOT 1
+#define IPP_FIELD_SPLIT 2
+int ipp_generate_field(ipp_engine *e, int32_t kind, int32_t cluster_radius, uint64_t seed, int32_t first_env, int32_t n_env);
+
+/* ipp_reset with the per-env prior of Mapping.init_priors(shuffle_prior_cov=True) (mapping/mappings.py:219-240), drawn on
+ * the device (Philox keyed by (seed; global env id)): gp_mode != 0: variance = U(0.8, 1.2) * signal_variance per env (the
+ * diagonal of the shuffled Matern prior; p0 = signal_variance); gp_mode == 0: prior_cov_mean ~ U(0.1, p0 = prior_cov_mean),
+ * prior_cov_std = prior_cov_mean, per-cell variance = the diagonal of A A^T / ||A||_F in its large-N normal limit
+ * (level sqrt(2) mu, relative spread sqrt(6 / N) / 2 per cell).  Statistical parity. */
+int ipp_reset_shuffled(ipp_engine *e, float prior_mean, int32_t gp_mode, float p0, uint64_t seed, const double *init_pose);
+
 /* Synthetic ground truth generated on the device for benchmarking (smooth random harmonic field in
  * [0,1] per env, a stand-in for simulations/ground_truths.py:14-33; not a parity item). */
 int ipp_synth_ground_truth(ipp_engine *e, uint64_t seed);

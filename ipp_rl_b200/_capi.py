@@ -33,6 +33,7 @@ LAYOUT_MV = 1
 LAYOUT_TILED = 2
 LAYOUT_SUPER = 3
 LAYOUT_NAMES = {"planes": LAYOUT_PLANES, "mv": LAYOUT_MV, "tiled": LAYOUT_TILED, "super": LAYOUT_SUPER}
+FIELD_HOTSPOT, FIELD_SPLIT = 1, 2
 COST_DISTANCE = 0
 COST_FLIGHT_TIME = 1
 MAX_ALTITUDE_LEVELS = 32
@@ -185,6 +186,8 @@ SIGNATURES = {
     "ipp_set_ground_truth": (C.c_int, [_P, _P, _I32, _I32, _I32]),
     "ipp_get_ground_truth": (C.c_int, [_P, _P, _I32, _I32, _I32]),
     "ipp_synth_ground_truth": (C.c_int, [_P, C.c_uint64]),
+    "ipp_generate_field": (C.c_int, [_P, _I32, _I32, C.c_uint64, _I32, _I32]),
+    "ipp_reset_shuffled": (C.c_int, [_P, _F32, _I32, _F32, C.c_uint64, _P]),
     "ipp_generate_ground_truth": (C.c_int, [_P, C.c_double, C.c_uint64, _P, _I32, _I32]),
     "ipp_get_state": (C.c_int, [_P, _P, _P, _I32, _I32, _I32]),
     "ipp_set_state": (C.c_int, [_P, _P, _P, _I32, _I32, _I32]),

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libipp_b200.so")
-SOURCES = ["ipp_engine.cu", "mcts.cu", "grf.cu", "observe.cu", "experience.cu", "kalman_blocks.cu"]
+SOURCES = ["ipp_engine.cu", "mcts.cu", "grf.cu", "observe.cu", "experience.cu", "kalman_blocks.cu", "fields.cu"]
 HEADERS = ["step_kernel.cuh", "step_async.cuh", "step_bulk.cuh", "quad_math.cuh", "rollout_kernel.cuh", "engine_internal.h", os.path.join("..", "..", "include", "ipp_mcts.h"), os.path.join("..", "..", "include", "ipp_b200.h"),
            os.path.join("..", "..", "include", "ipp_experience.h")]
 NVCC_FLAGS = [

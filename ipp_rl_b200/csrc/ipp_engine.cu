@@ -457,7 +457,6 @@ static int setup_async(ipp_engine *e) {
         gt_cells = std::max(gt_cells, pg * fh);
         // the kernel divides quad indices with a 16-bit magic multiplier: exact while quads * quads-per-row < 2^15
         const int nqx = (fw + 1) / 2, nqy = (fh + 1) / 2;
-        if (nqx > 32) return IPP_OK;  // lane layout: one pass covers whole quad rows
         if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;
     }
     // TILED + IPP_DIRECT_MV: the belief is not staged at all (bulk L2 prefetch + direct loads), a slot holds the ground truth only
@@ -543,7 +542,6 @@ static int setup_bulk(ipp_engine *e) {
         const int ntx = std::min(e->txm, (fw + 2) / 4 + 1), ntr = std::min(e->tiles_y, (fh + 2) / 4 + 1);
         max_fp = std::max(max_fp, ntx * ntr * kSuperTileBytes);
         const int nqx = (fw + 1) / 2, nqy = (fh + 1) / 2;
-        if (nqx > 32) return IPP_OK;  // lane layout: one pass covers whole quad rows
         if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;  // 16-bit magic division of quad indices
     }
     int dev_smem = 0;
@@ -831,6 +829,52 @@ extern "C" int ipp_reset(ipp_engine *e, float prior_mean, float prior_var, const
     }
     reset_kernel<<<grid_for(e->plane_mv * (size_t)B, 256, e->sm_count), 256, 0, e->stream>>>(e->d_mean, e->d_var, e->cfg.layout, e->plane_mv, B,
                                                                                              prior_mean, prior_var, d_pv);
+    const double dflt[3] = {2.0, 2.0, 14.0};  // planning/missions.py:69
+    const double *ip = init_pose ? init_pose : dflt;
+    fill_prev_kernel<<<(B + 255) / 256, 256, 0, e->stream>>>(e->d_prev, B, ip[0], ip[1], ip[2]);
+    e->launches += 2;
+    e->steps = 0;
+    CU(e, cudaGetLastError());
+    CU(e, cudaStreamSynchronize(e->stream));
+    return IPP_OK;
+}
+
+// prior fill with a per-env {level, relative spread}: cell variance = level * (1 + spread * N(0, 1)) (Philox per cell)
+__global__ void reset_shuffled_kernel(float *mean, float *var, int layout, size_t plane, int batch, float prior_mean, const float *scale,
+                                      uint32_t seed_lo, uint32_t seed_hi, uint32_t env0) {
+    const size_t total = plane * (size_t)batch;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        if (layout == IPP_LAYOUT_SUPER && (i % 24) >= 16) continue;
+        const size_t env = i / plane;
+        const float level = scale[2 * env], spread = scale[2 * env + 1];
+        float pv = level;
+        if (spread > 0.0f) {
+            const uint32_t cell = (uint32_t)(i - env * plane);
+            uint32_t r[4];
+            philox4x32_10(cell >> 1, env0 + (uint32_t)env, 11u, 0x5eedu, seed_lo, seed_hi, r);
+            float n0, n1;
+            box_muller(r[0], r[1], n0, n1);
+            pv = fmaxf(level * (1.0f + spread * ((cell & 1) ? n1 : n0)), 1.0e-6f);
+        }
+        if (layout != IPP_LAYOUT_PLANES) {
+            reinterpret_cast<float2 *>(mean)[i] = make_float2(prior_mean, pv);
+        } else {
+            mean[i] = prior_mean;
+            var[i] = pv;
+        }
+    }
+}
+
+extern "C" int ipp_reset_shuffled(ipp_engine *e, float prior_mean, int32_t gp_mode, float p0, uint64_t seed, const double *init_pose) {
+    if (!e) return IPP_ERR_INVALID;
+    if (!(p0 > 0) || (!gp_mode && !(p0 > 0.1f))) return fail(e, IPP_ERR_INVALID, "ipp_reset_shuffled: signal_variance must be > 0 / prior_cov_mean > 0.1");
+    const int B = e->cfg.batch;
+    int rc = ensure_job_buffers(e, 2 * (size_t)B);  // borrow the reward staging as a [B][2] float buffer
+    if (rc != IPP_OK) return rc;
+    if ((rc = ipp_internal_shuffled_prior(e, e->d_reward, B, gp_mode, p0, p0, seed)) != IPP_OK) return fail(e, rc, "ipp_reset_shuffled: launch failed");
+    reset_shuffled_kernel<<<grid_for(e->plane_mv * (size_t)B, 256, e->sm_count), 256, 0, e->stream>>>(
+        e->d_mean, e->d_var, e->cfg.layout, e->plane_mv, B, prior_mean, e->d_reward, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32),
+        (uint32_t)e->cfg.env_id_offset);
     const double dflt[3] = {2.0, 2.0, 14.0};  // planning/missions.py:69
     const double *ip = init_pose ? init_pose : dflt;
     fill_prev_kernel<<<(B + 255) / 256, 256, 0, e->stream>>>(e->d_prev, B, ip[0], ip[1], ip[2]);

@@ -119,45 +119,27 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, fl
 }
 
 // The engine's noise stream (mirrored by oracle device_noise_field).  A footprint is tiled by 2x2-cell quads anchored at
-// its top-left cell, quad q = qy * nqx + qx (nqx = ceil(nx / 2) quads per row); Philox group g draws
-// philox4x32_10(counter = (g, env, step), key = seed) -> four normals.
+// its top-left cell, quad q = qy * nqx + qx (nqx = ceil(nx / 2) quads per row); every step kernel sweeps the quads as
+// q = lane + 32 * pass.  Philox group g draws philox4x32_10(counter = (g, env, step), key = seed) -> four normals.
 //   rf = 1: quad q draws group q; its four cells use the group's four normals.
-//   rf = 2: measurement i = block q.  The quad grid is swept in passes of RP = 32 / nqx whole quad rows (the persistent
-//           kernel's lane layout, step_bulk.cuh): pass t = qy / RP, lane s = (qy mod RP) * nqx + qx.  The block uses normal
-//           (t & 3) of group s + 32 * (t >> 2): a lane keeps the four normals of ONE Philox call for four consecutive passes —
-//           one call per four measurement blocks, no cross-lane traffic.  (nqx > 32: group q, normal 0.)
+//   rf = 2: measurement i = block q uses normal (pass & 3) of group lane + 32 * (pass >> 2), i.e. normal (i >> 5) & 3 of group
+//           (i & 31) + 32 * (i >> 7): a lane keeps the four normals of ONE Philox call for four consecutive passes — one
+//           call per four measurement blocks instead of one each, no cross-lane traffic.
 __device__ __forceinline__ void philox_normals(const StepParams &p, uint32_t group, uint32_t env_id, float (&n)[4]) {
     uint32_t rnd[4];
     philox4x32_10(group, env_id, p.step_lo, p.step_hi, p.seed_lo, p.seed_hi, rnd);
     box_muller(rnd[0], rnd[1], n[0], n[1]);
     box_muller(rnd[2], rnd[3], n[2], n[3]);
 }
-// persistent-kernel form: the caller IS lane s in pass `it`; `cache` must persist across the passes of one env
-__device__ __forceinline__ void draw_normals_strip(const StepParams &p, int rf, int q, int lane, int it, uint32_t env_id, float (&cache)[4],
-                                                   float (&eps)[4]) {
+// the caller holds quad q = lane + 32 * pass; `cache` must persist across the passes of one env
+__device__ __forceinline__ void draw_normals(const StepParams &p, int rf, int q, int lane, int pass, uint32_t env_id, float (&cache)[4],
+                                             float (&eps)[4]) {
     if (rf == 1) {
         philox_normals(p, (uint32_t)q, env_id, eps);
     } else {
-        const int t = it & 3;
-        if (t == 0) philox_normals(p, (uint32_t)(lane + 32 * (it >> 2)), env_id, cache);  // warp-uniform: every lane is in the same pass
+        const int t = pass & 3;
+        if (t == 0) philox_normals(p, (uint32_t)(lane + 32 * (pass >> 2)), env_id, cache);  // warp-uniform: every lane is in the same pass
         eps[0] = t == 0 ? cache[0] : (t == 1 ? cache[1] : (t == 2 ? cache[2] : cache[3]));
-    }
-}
-// general form (any lane may hold any quad): one Philox call per quad
-__device__ __forceinline__ void draw_normals(const StepParams &p, int rf, int q, int qy, int qx, int nqx, uint32_t env_id, float (&eps)[4]) {
-    if (rf == 1) {
-        philox_normals(p, (uint32_t)q, env_id, eps);
-    } else {
-        float n[4];
-        int g = q, t = 0;
-        if (nqx <= 32) {
-            const int rp = 32 / nqx;
-            t = qy / rp;
-            g = (qy - t * rp) * nqx + qx + 32 * (t >> 2);
-            t &= 3;
-        }
-        philox_normals(p, (uint32_t)g, env_id, n);
-        eps[0] = t == 0 ? n[0] : (t == 1 ? n[1] : (t == 2 ? n[2] : n[3]));
     }
 }
 

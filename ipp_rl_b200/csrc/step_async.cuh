@@ -471,14 +471,11 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
         float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four passes
 
         if (!unsupported) {
-            // lane layout shared by all step kernels (step_kernel.cuh): passes of RP = 32 / nqx whole quad rows
-            const int rp = 32 / nqx;  // the host routes footprints wider than 64 cells to the general kernel
-            const int qy_first = (int)(((uint32_t)lane * magic_x) >> 16);
-            const int qx = lane - qy_first * nqx;
             int it = 0;
             IPP_UNROLL(IPP_QUAD_UNROLL)
-            for (int qy = qy_first < rp ? qy_first : nqy; qy < nqy; qy += rp, ++it) {
-                const int q = qy * nqx + qx;
+            for (int q = lane; q < nq; q += 32, ++it) {
+                const int qy = (int)(((uint32_t)q * magic_x) >> 16);
+                const int qx = q - qy * nqx;
                 const int r0 = 2 * qy, c0 = 2 * qx;
                 const bool cok = c0 + 1 < nx, rok = r0 + 1 < ny;
                 const bool ok[4] = {true, cok, rok, cok && rok};
@@ -523,7 +520,7 @@ __global__ void __launch_bounds__(kAsyncMaxWarps * 32, 1) ipp_step_async_kernel(
                         eps[0] = __ldg(p.noise + nrow + q);
                     }
                 } else {
-                    draw_normals_strip(p, rf, q, lane, it, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
+                    draw_normals(p, rf, q, lane, it, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
                 }
                 if (rf == 1) {
                     const float gv[4] = {gt_t[r0 * pg + c0], gt_t[r0 * pg + c0 + 1], gt_t[r1 * pg + c0], gt_t[r1 * pg + c0 + 1]};

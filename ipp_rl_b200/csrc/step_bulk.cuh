@@ -13,11 +13,6 @@
 // computed once, by one lane, when the warp takes a chunk of tickets: lane i plans ticket base + i).  No block-level
 // synchronisation in the loop.  Work distribution: global ticket counter, guided self-scheduling (as step_async.cuh).
 //
-// Lane layout: a footprint's quad grid (nqy x nqx quads of 2 x 2 cells) is swept in passes of RP = 32 / nqx whole quad rows:
-// lane = (qy mod RP) * nqx + qx.  Everything that depends on the quad COLUMN (tile column, in-tile offsets, border clamps,
-// INTER_AREA column weights) is computed once per env and lane; a pass only advances the row part.  The rf = 2 noise stream
-// is defined on the same layout (quad_math.cuh draw_normals): one Philox call serves a lane for four passes.
-//
 // INTER_AREA (rf = 2) on unscrambled odd footprints needs no tap tables: output o of n integrates inputs {2o-1, 2o, 2o+1}
 // with weights {o, n, n-1-o} / (2n-1) — the quad's own 2 x 2 cells plus the row above and the column to the left; the
 // weights are formed exactly as make_tap_entry() forms them, so the result is bit-identical to the table path of the
@@ -76,7 +71,7 @@ struct __align__(16) BulkPlan {
     int sizes;         // bytes per staged tile row | ntr << 16
     int ring_off;      // byte offset of the staged footprint in the warp's ring
     int magic_x;       // floor(65536 / nqx) + 1
-    int rpw;           // RP | (RP * nqx) << 8: quad rows per pass, lanes in use
+    int spare;
     float inv_cost1;   // 1 / (cost + 1)
     int outs;          // out_r | out_c << 8
 };
@@ -167,7 +162,6 @@ __device__ __forceinline__ void bulk_plan_env(const StepParams &p, bool quirk, b
         }
     }
     const int magic_x = (int)((uint32_t)(65536.0f * fast_rcp((float)nqx) * 1.00000012f) + 1u);
-    const int rp = max(1, (32 * magic_x) >> 16);  // 32 / nqx (the host guarantees nqx <= 32)
     const double px = __dadd_rn(__dmul_rn(p.res, (double)col), __dmul_rn(0.5, p.res));
     const double py = __dadd_rn(__dmul_rn(p.res, (double)row), __dmul_rn(0.5, p.res));
     const float cost = job_cost(p, px, py, L.alt, q0, q1, q2);
@@ -182,7 +176,7 @@ __device__ __forceinline__ void bulk_plan_env(const StepParams &p, bool quirk, b
     int4 *o = reinterpret_cast<int4 *>(out);
     o[0] = make_int4(job, xl | (yu << 16), nx | (ny << 8) | (nqx << 16) | (nqy << 24), ntx | (ntr << 8) | (lvl << 16) | (flags << 24));
     o[1] = make_int4((int)(unsigned)(src & 0xffffffffull), (int)(unsigned)(src >> 32), (ntx * kSuperTileBytes) | (ntr << 16), 0);
-    o[2] = make_int4(magic_x, rp | ((rp * nqx) << 8), __float_as_int(fast_rcp(cost + 1.0f)), out_r | (out_c << 8));
+    o[2] = make_int4(magic_x, 0, __float_as_int(fast_rcp(cost + 1.0f)), out_r | (out_c << 8));
 }
 
 // MODE: MODE_KALMAN (full step) or MODE_PREDICT (covariance only: no ground truth, no noise; the staged run still carries
@@ -312,7 +306,6 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
             const int srow = pb.z & 0xffff;  // staged tile-row stride [bytes]
             const int a4 = xl & 3, b4 = yu & 3;
             unsigned char *gbase = plane0 + (((unsigned long long)(unsigned)pb.y << 32) | (unsigned)pb.x);
-            const int RP = pc.y & 255, W = pc.y >> 8;
 
             const float4 la = lvl_tab[2 * lvl];
             FuseCtx fc;
@@ -352,26 +345,25 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
             float acc = 0.0f;
             float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four passes
 
-            // ---- this lane's quad column: everything that does not change from pass to pass ------------------------------
-            const int qy0 = (int)(((uint32_t)lane * (uint32_t)pc.x) >> 16);
-            const int qx = lane - qy0 * nqx;
-            const int c0 = 2 * qx;
-            const bool cok = c0 + 1 < nx;
-            const int cc = a4 + c0, ic = cc & 3;
-            const bool last_c = ic == 3;
-            const int col_s = (cc >> 2) * kSuperTileBytes + (ic << 3);        // {mean,var} of column c0 inside a tile row [bytes]
-            const int col_q = (cc >> 2) * kSuperTileBytes + 128 + (ic << 2);  // ground truth of column c0
-            const int dCg = last_c ? 168 : 8;                                 // to column c0 + 1 ({mean,var})
-            const int dC = cok ? dCg : 0;                                     // ... clamped inside the footprint
-            const int dCq = cok ? (last_c ? 180 : 4) : 0;                     // ... ground truth
-            const int dL = qx > 0 ? ((ic == 0) ? -180 : -4) : 0;              // to column c0 - 1 (ground truth), clamped
-            const float wl = (float)qx * inv_nx, wr_ = (float)(nqx - 1 - qx) * inv_nx;
-            const int nqy_l = (lane < W && !unsupported) ? nqy : 0;
+            const uint32_t magic_x = (uint32_t)pc.x;
             const bool odd = (a4 & 1) != 0;  // warp-uniform: (c0, c0 + 1) do not share a 16-byte chunk
-
+            const int nq = unsupported ? 0 : nqx * nqy;
             int it = 0;
 #pragma unroll 1
-            for (int qy = qy0; qy < nqy_l; qy += RP, ++it) {
+            for (int q = lane; q < nq; q += 32, ++it) {
+                const int qy = (int)(((uint32_t)q * magic_x) >> 16);
+                const int qx = q - qy * nqx;
+                // column part
+                const int c0 = 2 * qx;
+                const bool cok = c0 + 1 < nx;
+                const int cc = a4 + c0, ic = cc & 3;
+                const bool last_c = ic == 3;
+                const int col_s = (cc >> 2) * kSuperTileBytes + (ic << 3);        // {mean,var} of column c0 inside a tile row [bytes]
+                const int col_q = (cc >> 2) * kSuperTileBytes + 128 + (ic << 2);  // ground truth of column c0
+                const int dCg = last_c ? 168 : 8;                                 // to column c0 + 1 ({mean,var})
+                const int dC = cok ? dCg : 0;                                     // ... clamped inside the footprint
+                const int dCq = cok ? (last_c ? 180 : 4) : 0;                     // ... ground truth
+                // row part
                 const int r0 = 2 * qy;
                 const bool rok = r0 + 1 < ny;
                 const bool ok3 = cok && rok;
@@ -399,7 +391,6 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                 // ---- measurement --------------------------------------------------------------------------------
                 float z[4] = {0.f, 0.f, 0.f, 0.f};
                 if (MODE != MODE_PREDICT) {
-                    const int q = qy * nqx + qx;
                     float eps[4];
                     if (EXTRAS && p.noise != nullptr) {
                         if (rf == 1) {
@@ -409,7 +400,7 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                             eps[0] = __ldg(p.noise + nrow + q);
                         }
                     } else {
-                        draw_normals_strip(p, rf, q, lane, it, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
+                        draw_normals(p, rf, q, lane, it, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
                     }
                     const uint32_t gs = slot + (uint32_t)(row_s + (ir << 4) + col_q);  // gt of cell (r0, c0), staged
                     const int dRq = rok ? (last_r ? srow - 48 : 16) : 0;
@@ -432,6 +423,8 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                     } else if (analytic) {
                         // rows {r0-1, r0, r0+1} x cols {c0-1, c0, c0+1}; taps with weight 0 are clamped onto the quad's own cells
                         const int dU = qy > 0 ? ((ir == 0) ? -(srow - 48) : -16) : 0;
+                        const int dL = qx > 0 ? ((ic == 0) ? -180 : -4) : 0;  // to column c0 - 1 (ground truth), clamped
+                        const float wl = (float)qx * inv_nx, wr_ = (float)(nqx - 1 - qx) * inv_nx;
                         const float wu = (float)qy * inv_ny, wb = (float)(nqy - 1 - qy) * inv_ny;
                         float rs[3];
                         const int dro[3] = {dU, 0, dRq};

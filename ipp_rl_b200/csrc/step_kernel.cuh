@@ -118,19 +118,9 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
 
     float acc = 0.0f;  // per-lane partial (<= a few dozen quads); fp64 tree across the warp
     float nrm_cache[4] = {0.f, 0.f, 0.f, 0.f};  // rf = 2: one Philox call serves four passes
-    // Lane layout (shared with the persistent kernels, so that per-lane partial sums — and with them the rewards — agree bit
-    // for bit): passes of RP = 32 / nqx whole quad rows, lane = (qy mod RP) * nqx + qx; footprints wider than 64 cells fall
-    // back to q = lane, lane + 32, ...
-    const bool strip = nqx <= 32;
-    const int rp = strip ? 32 / nqx : 0;
-    const int qy_first = strip ? fdiv(lane, nqx, inv_nqx) : 0;
-    const int qx_strip = lane - qy_first * nqx;
-    const int n_pass = strip ? (qy_first < rp ? (nqy - qy_first + rp - 1) / rp : 0) : (nq - lane + 31) / 32;
-    for (int it = 0; it < n_pass; ++it) {
-        const int q_lin = lane + 32 * it;
-        const int qy = strip ? qy_first + it * rp : fdiv(q_lin, nqx, inv_nqx);
-        const int qx = strip ? qx_strip : q_lin - qy * nqx;
-        const int q = qy * nqx + qx;
+    int it = 0;  // pass: lane holds quad q = lane + 32 * it (the layout the noise stream is defined on, quad_math.cuh)
+    for (int q = lane; q < nq; q += 32, ++it) {
+        const int qy = fdiv(q, nqx, inv_nqx), qx = q - qy * nqx;
         const int r0 = 2 * qy, c0 = 2 * qx;
         const bool cok = c0 + 1 < g.nx, rok = r0 + 1 < g.ny;
         const bool ok[4] = {true, cok, rok, cok && rok};
@@ -178,10 +168,7 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
                         eps[0] = __ldg(p.noise + nrow + q);
                     }
                 } else {
-                    if (strip)
-                        draw_normals_strip(p, g.rf, q, lane, it, (uint32_t)env + p.env_id_offset, nrm_cache, eps);
-                    else
-                        draw_normals(p, g.rf, q, qy, qx, nqx, (uint32_t)env + p.env_id_offset, eps);
+                    draw_normals(p, g.rf, q, lane, it, (uint32_t)env + p.env_id_offset, nrm_cache, eps);
                 }
                 if (g.rf == 1) {
 #pragma unroll

@@ -268,6 +268,21 @@ class BatchedEngine:
                 raise ValueError(f"white_noise must hold {n} maps")
         self._ck(self._lib.ipp_generate_ground_truth(self._h, float(cluster_radius), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(wn), first_env, n))
 
+    FIELDS = {"hotspot_random_field": capi.FIELD_HOTSPOT, "split_random_field": capi.FIELD_SPLIT}
+
+    def generate_field(self, kind: str, cluster_radius: int, seed: int = 0, first_env: int = 0, n_env: Optional[int] = None) -> None:
+        """Piecewise-constant ground truths generated on the device (HotspotRandomField / SplitRandomField,
+        simulations/simulations.py:51-123); ``kind`` is the reference's simulation type string."""
+        n = self.batch - first_env if n_env is None else n_env
+        self._ck(self._lib.ipp_generate_field(self._h, self.FIELDS[kind], int(cluster_radius), int(seed) & 0xFFFFFFFFFFFFFFFF, first_env, n))
+
+    def reset_shuffled(self, prior_mean: float = 0.5, fit_gaussian_process: bool = True, scale: float = 1.82, seed: int = 0, init_pose=None) -> None:
+        """``Mapping.init_priors(shuffle_prior_cov=True)`` for every env, drawn on the device (mapping/mappings.py:219-240):
+        ``scale`` = signal_variance (GP mode) or prior_cov_mean."""
+        ip = None if init_pose is None else np.ascontiguousarray(init_pose, dtype=np.float64).reshape(3)
+        self._ck(self._lib.ipp_reset_shuffled(self._h, prior_mean, 1 if fit_gaussian_process else 0, float(scale), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                              _ptr(ip)))
+
     def get_ground_truth(self, first_env: int = 0, n_env: Optional[int] = None) -> np.ndarray:
         n = self.batch - first_env if n_env is None else n_env
         out = np.empty((n, self.y_dim, self.x_dim), np.float32)

@@ -212,17 +212,10 @@ int orc_step(const orc_cfg *c, int B, const double *gt, double *mean, double *va
                             z[r * nx + cc] += s2 * n4[2 * (r % 2) + (cc % 2)];
                         }
                 } else {
-                    /* measurement i = block (qy, qx) of the block grid; passes of RP = 32 / nqx block rows (quad_math.cuh) */
                     for (int i = 0; i < nz; ++i) {
                         double n4[4];
-                        int g = i, comp = 0;
-                        if (nqx <= 32) {
-                            const int qy = i / nqx, qx = i % nqx, rp = 32 / nqx, t = qy / rp;
-                            g = (qy - t * rp) * nqx + qx + 32 * (t >> 2);
-                            comp = t & 3;
-                        }
-                        device_normals(seed, (uint32_t)(env_offset + b), step, (uint32_t)g, n4);
-                        z[i] += s2 * n4[comp];
+                        device_normals(seed, (uint32_t)(env_offset + b), step, (uint32_t)((i & 31) + 32 * (i >> 7)), n4);
+                        z[i] += s2 * n4[(i >> 5) & 3];
                     }
                 }
             }

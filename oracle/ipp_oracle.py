@@ -575,10 +575,8 @@ def device_noise_field(cfg: OracleConfig, position, seed: int, env: int, step: i
     """The eps array (measurement shape, C order) the engine's Philox mode applies for this
     (env, step).  The footprint is tiled by 2x2 cell quads anchored at (yu, xl), quad index
     ``g = qy * ceil(nx/2) + qx``.  rf=1: cell (2qy+dy, 2qx+dx) uses normal ``[g, 2*dy+dx]``.
-    rf=2: measurement i = block (qy, qx) = divmod(i, nqx) of the block grid.  The grid is swept in passes of
-    ``RP = 32 // nqx`` whole block rows (the persistent kernel's lane layout): pass ``t = qy // RP``, lane
-    ``s = (qy % RP) * nqx + qx``; the block uses normal ``[s + 32 * (t >> 2), t & 3]`` — a lane keeps the four normals of one
-    Philox call for four consecutive passes (quad_math.cuh draw_normals).  ``nqx > 32``: normal ``[i, 0]``."""
+    rf=2: measurement i (flat index into z) uses normal ``[(i & 31) + 32 * (i >> 7), (i >> 5) & 3]`` — four
+    consecutive 32-blocks of measurements share one Philox call per lane position (quad_math.cuh draw_normals)."""
     xl, xr, yu, yd = project_field_of_view(cfg, position)
     nx, ny = xr - xl + 1, yd - yu + 1
     rf = resolution_factor(cfg, position)
@@ -593,14 +591,7 @@ def device_noise_field(cfg: OracleConfig, position, seed: int, env: int, step: i
     shape = measurement_shape(cfg, position)
     m = shape[0] * shape[1]
     i = np.arange(m)
-    qy, qx = i // nqx, i % nqx  # measurement i is block i of the footprint's block grid (nqy x nqx), whatever the dsize quirk does to the shape
-    if nqx <= 32:
-        rp = 32 // nqx
-        t = qy // rp
-        groups = (qy - t * rp) * nqx + qx + 32 * (t >> 2)
-        comp = t & 3
-    else:
-        groups, comp = i, np.zeros_like(i)
+    groups, comp = (i & 31) + 32 * (i >> 7), (i >> 5) & 3
     nrm = device_normals(seed, env, step, int(groups.max()) + 1)
     return nrm[groups, comp].reshape(shape)
 
