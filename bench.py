@@ -52,7 +52,7 @@ class ClockSampler:
     """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -79,7 +79,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, load, mx, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) < 7:
@@ -89,11 +89,17 @@ class ClockSampler:
                 mx.append(float(r[1]))
             except ValueError:
                 continue
+            try:
+                if len(r) > 7 and float(r[7]) >= 10.0:
+                    load.append(sm[-1])
+            except ValueError:
+                pass
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        use = load if load else sm  # median over the samples that saw the GPU busy (the legs alternate with host-side set-up)
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "samples_under_load": len(load), "reasons": sorted(reasons)}
 
 
 def footprint_cells(ids, X, Y, radii):
@@ -115,13 +121,14 @@ def run_reference(args, rank, world):
         return
     from oracle import cpu_baseline
 
-    res = cpu_baseline.run(WORKLOAD, steps=args.steps, warmup=args.warmup, envs=args.cpu_envs, reward_mode=1)
+    res = cpu_baseline.run(WORKLOAD, steps=args.steps, warmup=args.warmup, envs=args.cpu_envs, reward_mode=0)
     line = {
         "metric": "env_steps_per_sec", "value": res["steps_per_sec"], "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "C3: batch 65536 envs/GPU, 200x200 grid, 3-altitude action set {8,14,20} m, Kalman fusion, "
-                               "entropy-reduction reward (Gaussian-entropy extension; trace-reduction timed alongside)",
+        "config": {"workload": "C3: batch 65536 envs/GPU, 200x200 grid, 3-altitude action set {8,14,20} m, Kalman fusion, information-gain reward: "
+                               "trace (variance) reduction = the reference's reward, parity-pinned [headline]",
+                   "reward_mode": "trace_reduction",
                    "batch_per_step_sample": res["envs"], "grid": [200, 200], "noise": "Philox4x32-10 (same stream definition)",
                    "note": "CPU port of the reference algorithm (oracle/ipp_oracle.c, fp64, OpenMP over envs); each step = one pass over a "
                            "bounded env sample of the same workload"},
@@ -134,6 +141,77 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+class SharedRewards:
+    """One pinned host segment shared by all ranks of the node (POSIX shared memory + cudaHostRegister): every rank's step
+    kernel writes the rewards of its env slice straight into it (4 B per env over its own PCIe link) and bumps its step
+    counter; the learner (rank 0) sees the whole batch's rewards without any collective on the step path.  Two slots, so a
+    rank may run one step ahead of the learner."""
+
+    SLOTS = 2
+
+    def __init__(self, rank, world, per_rank, tag):
+        from multiprocessing import shared_memory
+
+        import torch
+
+        self.rank, self.world, self.n = rank, world, per_rank
+        self.bytes = self.SLOTS * world * per_rank * 4 + 4096
+        name = f"ipp_b200_rewards_{tag}"
+        if rank == 0:
+            try:
+                shared_memory.SharedMemory(name=name).unlink()
+            except Exception:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=self.bytes)
+            self.shm.buf[: self.bytes] = bytes(self.bytes)
+        import torch.distributed as dist
+
+        dist.barrier()
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+        arr = np.ndarray((self.bytes,), dtype=np.uint8, buffer=self.shm.buf)
+        self.rewards = arr[: self.SLOTS * world * per_rank * 4].view(np.float32).reshape(self.SLOTS, world, per_rank)
+        self.flags = arr[self.SLOTS * world * per_rank * 4 :].view(np.int64)[: 64]  # flags[r] = steps rank r has completed, flags[32] = consumed by the learner
+        rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, self.bytes, 1 | 2)  # portable | mapped
+        self.registered = (getattr(rc, "value", rc) == 0) or ("success" in str(rc).lower())
+        self._ptr = arr.ctypes.data
+        dist.barrier()
+
+    def my_slice(self, step):
+        return self.rewards[step % self.SLOTS, self.rank]
+
+    def publish(self, step):
+        self.flags[self.rank] = step + 1
+
+    def learner_collect(self, step):
+        """rank 0: wait until every rank has published `step`, return the (world * per_rank,) view."""
+        while int(self.flags[: self.world].min()) < step + 1:
+            pass
+        out = self.rewards[step % self.SLOTS].reshape(-1)
+        self.flags[32] = step + 1
+        return out
+
+    def wait_for_slot(self, step):
+        """any rank: the slot of `step` was last used by step - SLOTS; the learner must have consumed that one."""
+        while int(self.flags[32]) < step + 1 - self.SLOTS:
+            pass
+
+    def close(self):
+        import torch
+
+        try:
+            torch.cuda.cudart().cudaHostUnregister(self._ptr)
+        except Exception:
+            pass
+        self.rewards = self.flags = None
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
@@ -142,6 +220,7 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    nvtx = torch.cuda.nvtx
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -169,148 +248,159 @@ def run_ours(args, rank, world, local_rank):
     ids_e2e = rng.randint(0, eng.num_actions, size=(POOL, B)).astype(np.int32)
     cells_pool = footprint_cells(ids_host.astype(np.int64), X, Y, radii).sum(axis=1)  # (POOL,)
     cells_timed_total = float(sum(cells_pool[t % POOL] for t in range(W, W + K)))
-    alg_bytes_per_launch = (20.0 * cells_timed_total + 16.0 * B * K) / K
+    alg_bytes_per_launch = (20.0 * cells_timed_total + 16.0 * B * K) / K          # full step: 20 B per covered cell + 16 B per env
+    alg_bytes_predict = (8.0 * cells_timed_total + 16.0 * B * K) / K              # covariance-only step: read + write the variance
 
-    reward_modes = {"entropy": capi.REWARD_GAUSS_ENTROPY, "trace": capi.REWARD_TRACE}
+    # headline = the reference-pinned reward (trace reduction, planning/common/rewards.py:15-31); the Gaussian-entropy
+    # extension (BASELINE.json's "entropy-reduction" wording, parity unpinned) is timed and reported beside it
+    reward_modes = {"trace_reduction": capi.REWARD_TRACE, "gauss_entropy": capi.REWARD_GAUSS_ENTROPY}
+    HEAD = "trace_reduction"
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
     with torch.cuda.stream(stream):
         ids_dev = torch.from_numpy(ids_host).cuda(non_blocking=False)
         reward_dev = torch.empty(B, dtype=torch.float32, device="cuda")
-        gathered = torch.empty(world * B, dtype=torch.float32, device="cuda") if dist is not None else None
         torch.cuda.synchronize()
 
-        def device_loop(mode, lo, hi):
-            for t in range(lo, hi):
-                eng.step_device(action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=mode)
-
-        results = {}
-        clocks = None
-        for name, mode in reward_modes.items():
+        def timed_device_loop(fn, tag):
+            """W warm-up launches, then K launches between two CUDA events on the engine's stream; max over ranks."""
             eng.reset(PRIOR_MEAN, PRIOR_VAR)
-            device_loop(mode, 0, W)
+            for t in range(W):
+                fn(t)
             barrier()
-            sampler = ClockSampler(local_rank) if (name == "entropy" and rank == 0) else None
-            if sampler:
-                sampler.start()
             launches0 = eng.launches
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nvtx.range_push(tag)
             e0.record(stream)
-            device_loop(mode, W, W + K)
+            for t in range(W, W + K):
+                fn(t)
             e1.record(stream)
             barrier()
-            ms = e0.elapsed_time(e1)
-            if sampler:
-                clocks = sampler.stop()
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            if dist is not None:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            results[name] = dict(ms_total=float(t.item()), launches=eng.launches - launches0)
+            nvtx.range_pop()
+            ms = max_over_ranks(e0.elapsed_time(e1))
             eng.sync()
+            return dict(ms_total=ms, launches=eng.launches - launches0)
 
-        # ---- e2e: host buffers through the public step call, H2D + kernel + (gather) + D2H per step
+        results = {}
+        for name, mode in reward_modes.items():
+            results[name] = timed_device_loop(
+                lambda t, mode=mode: eng.step_device(action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=mode),
+                f"step[{name}]")
+        # predict-only leg: the covariance-only step the planners' rollouts run (simulate_prediction_step,
+        # planning/common/optimization.py:14-30), whole batch, committing — the persistent kernel's MODE_PREDICT
+        pl0 = eng.path_launches("async")
+        results["predict"] = timed_device_loop(
+            lambda t: eng.predict_device(B, action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), commit=True,
+                                         reward_mode=capi.REWARD_TRACE),
+            "predict")
+        predict_persistent = eng.path_launches("async") - pl0 >= K
+
+        # ---- e2e: host buffers through the public step call, H2D + kernel + rewards back on the host, every step -----------
         ids_pinned = torch.from_numpy(ids_e2e).pin_memory()
-        out_pinned = torch.empty(world * B if dist is not None else B, dtype=torch.float32).pin_memory()
-        ids_np, out_np = ids_pinned.numpy(), out_pinned.numpy()
+        ids_np = ids_pinned.numpy()
         id_rows = [ids_np[k] for k in range(POOL)]  # stable array objects (the engine caches their ctypes pointers)
+        shared = None
+        if dist is None:
+            out_np = torch.empty(B, dtype=torch.float32).pin_memory().numpy()
+        else:
+            shared = SharedRewards(rank, world, B, tag=os.environ.get("MASTER_PORT", "0"))
         eng.reset(PRIOR_MEAN, PRIOR_VAR)
         if args.zero_copy is not None:
             eng.set_zero_copy(rewards="r" in args.zero_copy, ids="i" in args.zero_copy)
         zc0 = eng.zero_copy_steps
+        e2e_mode = reward_modes[HEAD]
+        checksum = [0.0]
 
-        def e2e_step(t):
-            if dist is None:
-                eng.step(id_rows[t % POOL], reward_mode=capi.REWARD_GAUSS_ENTROPY, out=out_np)
-            else:
-                staged = ids_pinned[t % POOL].cuda(non_blocking=True)
-                eng.step_device(action_ids_ptr=staged.data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=capi.REWARD_GAUSS_ENTROPY)
-                dist.all_gather_into_tensor(gathered, reward_dev)
-                out_pinned.copy_(gathered, non_blocking=True)
-                stream.synchronize()
+        def e2e_step(t, base):
+            if shared is None:
+                eng.step(id_rows[t % POOL], reward_mode=e2e_mode, out=out_np)
+            else:  # every rank: ids up, kernel, rewards straight into the node's shared pinned segment; the learner reads them all
+                s = base + t
+                shared.wait_for_slot(s)
+                eng.step(id_rows[t % POOL], reward_mode=e2e_mode, out=shared.my_slice(s))
+                shared.publish(s)
+                if rank == 0:
+                    checksum[0] = float(shared.learner_collect(s)[:: 4096].sum())
 
         KE = min(K, args.e2e_steps)  # the e2e leg is host-latency bound; keep the default run short
         for t in range(W):
-            e2e_step(t)
+            e2e_step(t, 0)
         barrier()
         launches_e2e0 = eng.launches
+        nvtx.range_push("e2e[sync]")
         t0 = time.perf_counter()
         for t in range(W, W + KE):
-            e2e_step(t)
+            e2e_step(t, 0)
         barrier()
-        e2e_s = time.perf_counter() - t0
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        nvtx.range_pop()
         launches_e2e = eng.launches - launches_e2e0
         zero_copy_steps = eng.zero_copy_steps - zc0
-        assert np.isfinite(out_np).all()
-
-        # ---- e2e, pipelined (N = 1): the same per-step transfers through ipp_step_submit / ipp_step_wait, two slots — the host
-        #      uploads step t+1 while step t computes and waits for step t-1 before reusing its buffers (reported beside e2e.value)
-        pipe_s = None
-        if dist is None:
-            outs2 = [torch.empty(B, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
-
-            def pipe_loop(lo, hi):
-                for t in range(lo, hi):
-                    sl = t & 1
-                    eng.step_wait(sl)
-                    eng.step_submit(sl, id_rows[t % POOL], outs2[sl], reward_mode=capi.REWARD_GAUSS_ENTROPY)
-                eng.step_wait(0)
-                eng.step_wait(1)
-
-            pipe_loop(0, W)
-            barrier()
-            t0 = time.perf_counter()
-            pipe_loop(W, W + KE)
-            barrier()
-            pipe_s = time.perf_counter() - t0
-            assert np.isfinite(outs2[0]).all() and np.isfinite(outs2[1]).all()
+        if shared is None:
+            assert np.isfinite(out_np).all()
         else:
-            # N > 1: same idea with the exchange in the pipeline — the rewards all-gather (NCCL) and the D2H of the gathered vector
-            # of step t run on a side stream under the kernel of step t+1; the host waits for step t-1 before reusing its buffers
-            comm = torch.cuda.Stream()
-            ids_dev2 = [torch.empty(B, dtype=torch.int32, device="cuda") for _ in range(2)]
-            rew_dev2 = [torch.empty(B, dtype=torch.float32, device="cuda") for _ in range(2)]
-            gath2 = [torch.empty(world * B, dtype=torch.float32, device="cuda") for _ in range(2)]
-            outs2 = [torch.empty(world * B, dtype=torch.float32).pin_memory() for _ in range(2)]
-            ev_k = [torch.cuda.Event() for _ in range(2)]
-            ev_d = [torch.cuda.Event() for _ in range(2)]
-            used = [False, False]
+            assert np.isfinite(shared.rewards).all()
 
-            def pipe_loop(lo, hi):
-                for t in range(lo, hi):
-                    sl = t & 1
-                    if used[sl]:
-                        ev_d[sl].synchronize()
-                    ids_dev2[sl].copy_(ids_pinned[t % POOL], non_blocking=True)
-                    eng.step_device(action_ids_ptr=ids_dev2[sl].data_ptr(), reward_ptr=rew_dev2[sl].data_ptr(), reward_mode=capi.REWARD_GAUSS_ENTROPY)
-                    ev_k[sl].record(stream)
-                    with torch.cuda.stream(comm):
-                        comm.wait_event(ev_k[sl])
-                        dist.all_gather_into_tensor(gath2[sl], rew_dev2[sl])
-                        outs2[sl].copy_(gath2[sl], non_blocking=True)
-                        ev_d[sl].record(comm)
-                    used[sl] = True
-                for sl in (0, 1):
-                    if used[sl]:
-                        ev_d[sl].synchronize()
+        # ---- e2e, pipelined: the same per-step transfers through ipp_step_submit / ipp_step_wait, two slots — the host uploads
+        #      step t+1 while step t computes and waits for step t-1 before reusing its buffers (reported beside e2e.value)
+        if shared is None:
+            outs2 = [torch.empty(B, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+            slot_out = lambda s: outs2[s & 1]  # noqa: E731
+        else:
+            slot_out = lambda s: shared.my_slice(s)  # noqa: E731
+        base2 = W + KE  # continues the shared segment's step numbering
 
-            pipe_loop(0, W)
+        def pipe_loop(lo, hi):
+            for t in range(lo, hi):
+                sl = t & 1
+                eng.step_wait(sl)
+                if shared is not None:
+                    s = base2 + t
+                    if t - 2 >= lo:  # step t-2 (same slot) is complete: publish it, the learner collects
+                        shared.publish(s - 2)
+                        if rank == 0:
+                            checksum[0] = float(shared.learner_collect(s - 2)[:: 4096].sum())
+                    shared.wait_for_slot(s)
+                eng.step_submit(sl, id_rows[t % POOL], slot_out(base2 + t), reward_mode=e2e_mode)
+            eng.step_wait(0)
+            eng.step_wait(1)
+            if shared is not None:
+                for s in range(max(lo, hi - 2), hi):
+                    shared.publish(base2 + s)
+                    if rank == 0:
+                        checksum[0] = float(shared.learner_collect(base2 + s)[:: 4096].sum())
+
+        if shared is not None:  # restart the segment's counters at a common point
             barrier()
-            t0 = time.perf_counter()
-            pipe_loop(W, W + KE)
+            shared.flags[rank] = base2
+            if rank == 0:
+                shared.flags[32] = base2
             barrier()
-            pipe_s = time.perf_counter() - t0
-            tp = torch.tensor([pipe_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-            pipe_s = float(tp.item())
-            assert np.isfinite(outs2[0].numpy()).all() and np.isfinite(outs2[1].numpy()).all()
+        pipe_loop(0, W)
+        base2 += W if shared is not None else 0
+        barrier()
+        nvtx.range_push("e2e[pipelined]")
+        t0 = time.perf_counter()
+        pipe_loop(0, KE) if shared is not None else pipe_loop(W, W + KE)
+        barrier()
+        pipe_s = max_over_ranks(time.perf_counter() - t0)
+        nvtx.range_pop()
+        if shared is not None:
+            shared.close()
 
     # ---- secondary leg (BASELINE.json configs[3], "C4"): mcts_zero rollouts on the same beliefs.  Lock-step search over
     #      `--mcts-trees` envs, `--mcts-sims` simulations, episode_horizon 5, max_valid_action_distance 11.5 m, uniform
@@ -326,38 +416,42 @@ def run_ours(args, rank, world, local_rank):
         budgets = np.full(Tm, 150.0, np.float32)
         with torch.cuda.stream(stream):
             with BatchedMCTS(eng, hyper, meta, n_trees=Tm) as mcts:
-                # pass 1 (untimed, host-synchronous): count the prediction steps of the search (it is deterministic)
+                # pass 1 (untimed, host-synchronous): count the prediction steps / expansions of the search (it is deterministic)
                 mcts.begin(budgets)
-                edges = 0
-                cells_by_level = np.array([(2 * r + 1) ** 2 for r in radii], np.float64)
-                cells = 0.0
+                edges, expansions, path_cells = 0, 0, 0.0
+                cells_by_level = np.array([float((2 * r + 1) ** 2) for r in radii])
                 for i in range(Sm):
                     leaf = mcts.simulate(lambda lf: (None, None))
                     edges += int(leaf.path_len.sum())
-                path_ids = None
+                    expansions += int(leaf.needs_eval.sum())
                 # pass 2 (timed): device-only loop, CUDA events on the engine stream
                 mcts.begin(budgets)
                 l0 = mcts.launches
                 barrier()
                 m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nvtx.range_push("mcts")
                 m0.record(stream)
                 for i in range(Sm):
                     mcts.simulate(None)
                 m1.record(stream)
                 barrier()
-                ms_m = m0.elapsed_time(m1)
-                tm = torch.tensor([ms_m], dtype=torch.float64, device="cuda")
-                if dist is not None:
-                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-                ms_m = float(tm.item())
+                nvtx.range_pop()
+                ms_m = max_over_ranks(m0.elapsed_time(m1))
                 st = mcts.root_stats()
                 assert np.all(st["Ns"] == Sm - 1)
+                # algorithmic bytes of the search: 4 B per footprint cell of every prediction step (the variance it reads; mean
+                # footprint of the 3-altitude set, unclipped), one window row of priors written per expansion, 32 B per path edge
+                mean_cells = float(cells_by_level.mean())
+                alg_mcts = 4.0 * mean_cells * edges + 4.0 * mcts.window_slots * expansions + 32.0 * edges
                 mcts_res = {"trees_per_gpu": Tm, "simulations": Sm, "episode_horizon": 5, "window_slots": mcts.window_slots,
                             "tree_simulations_per_sec": world * Tm * Sm / (ms_m * 1e-3),
-                            "prediction_steps_per_sec": world * edges / (ms_m * 1e-3), "prediction_steps": edges,
+                            "prediction_steps_per_sec": world * edges / (ms_m * 1e-3), "prediction_steps": edges, "expansions": expansions,
                             "ms_per_lockstep_simulation": ms_m / Sm, "gpu_launches": int(mcts.launches - l0),
+                            "algorithmic_bytes": alg_mcts, "achieved_gbs": alg_mcts / (ms_m * 1e-3) / 1e9,
                             "tree_bytes_per_gpu": int(mcts.info.device_bytes),
                             "evaluator": "uniform priors, zero values (network outside this library)"}
+
+    clocks = sampler.stop() if sampler else None
 
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
     cpu = None
@@ -365,56 +459,78 @@ def run_ours(args, rank, world, local_rank):
         try:
             from oracle import cpu_baseline
 
-            r = cpu_baseline.run(WORKLOAD, steps=3, warmup=1, envs=args.cpu_envs, reward_mode=1, min_seconds=1.0)
+            r = cpu_baseline.run(WORKLOAD, steps=3, warmup=1, envs=args.cpu_envs, reward_mode=0, min_seconds=1.0)
             cpu = {"value": r["steps_per_sec"], "unit": "env-steps/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            tiers = os.path.join(ROOT, "profiles", "r02_reference_cpu_tiers.json")
+            if os.path.exists(tiers):  # the reference's OWN code (pure Python, cannot travel): timed in the build container
+                cpu["reference_tiers_build_container"] = json.load(open(tiers))
         except Exception as exc:  # report, never hide
             cpu = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "port", "sample": f"failed: {exc!r}"}
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        ms = results["entropy"]["ms_total"]
-        per_launch_ms = ms / K
-        achieved = alg_bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
-        ms_tr = results["trace"]["ms_total"]
-        traffic = None
+
+        def mode_block(name, alg):
+            ms = results[name]["ms_total"]
+            ach = alg / (ms / K * 1e-3) / 1e9
+            return {"value": world * B * K / (ms * 1e-3), "ms_per_launch": ms / K, "achieved": ach, "frac": ach / peak,
+                    "algorithmic_bytes_per_launch": alg}
+
+        modes = {n: mode_block(n, alg_bytes_per_launch) for n in reward_modes}
+        head = modes[HEAD]
+        kernel = {"super": "ipp_step_bulk_kernel", "tiled": "ipp_step_async_kernel", "mv": "ipp_step_async_kernel"}.get(args.layout, "ipp_step_kernel") \
+            if eng.step_path == "async" else "ipp_step_kernel"
+        traffic, traffic_note = None, "no ncu capture committed for this kernel"
         tp = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(f"{args.layout}_bytes_per_launch")
+                tj = json.load(open(tp))
+                ent = tj.get("kernels", {}).get(kernel + ":" + args.layout)
+                if ent:
+                    traffic = ent["bytes_per_launch"]
+                    traffic_note = f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, captured at commit {ent.get('commit', '?')} ({ent.get('how', '')})"
             except Exception:
-                traffic = None
+                pass
+        pred = mode_block("predict", alg_bytes_predict)
+        pred.update({"unit": "predict-steps/s", "kernel": "ipp_step_bulk_kernel<MODE_PREDICT>" if predict_persistent else "ipp_step_kernel<MODE_PREDICT>",
+                     "bytes_per_cell": 8, "note": "covariance-only step on the interleaved {mean,var} layout: the staged run and the written "
+                                                 "sectors carry the mean (and, in the super-tile layout, the ground truth) too, so ~27 B per "
+                                                 "cell move where 8 B are algorithmic (DESIGN.md 3.1)"})
         line = {
-            "metric": "env_steps_per_sec", "value": world * B * K / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "env_steps_per_sec", "value": head["value"], "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": head["ms_per_launch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3: batch 65536 envs/GPU, 200x200 grid, 3-altitude action set {8,14,20} m, Kalman fusion, "
-                                   "entropy-reduction reward (Gaussian-entropy extension; trace-reduction timed alongside)",
+            "config": {"workload": "C3: batch 65536 envs/GPU, 200x200 grid, 3-altitude action set {8,14,20} m, Kalman fusion, information-gain reward: "
+                                   "trace (variance) reduction = the reference's reward, parity-pinned [headline]; Gaussian-entropy reduction = "
+                                   "extension, parity unpinned [roofline.modes / e2e in the same mode as the headline]",
                        "batch_per_gpu": B, "grid": [Y, X], "layout": args.layout, "noise": "device Philox4x32-10",
+                       "reward_mode": HEAD,
                        "cache": "working set 31.5 GB/GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "parallelism": f"env-batch sharded x{world}"},
-            "value_trace_reduction": world * B * K / (ms_tr * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "achieved": head["achieved"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
+                         "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                         "mean_cells_per_env_step": cells_timed_total / (B * K), "kernel": "ipp_step_async_kernel" if eng.step_path == "async" else "ipp_step_kernel<MV, KALMAN>", "step_path": eng.step_path},
-            "e2e": {"value": world * B * KE / e2e_s, "steps": KE, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * B * world,
-                    "d2h_bytes_per_step": 4 * B * world * (world if dist is not None else 1),
-                    "pipelined_value": (world * B * KE / pipe_s) if pipe_s else None,
-                    "pipelined_path": ("ipp_step_submit / ipp_step_wait, 2 slots: same per-step H2D ids + rewards to pinned host memory, upload of "
-                                       "step t+1 under the kernel of step t") if dist is None else
-                                      ("2 slots: H2D ids -> ipp_step_device; NCCL all_gather(rewards) + D2H of step t on a side stream under the "
-                                       "kernel of step t+1"),
+                         "mean_cells_per_env_step": cells_timed_total / (B * K), "kernel": kernel, "step_path": eng.step_path,
+                         "modes": modes, "predict": pred},
+            "e2e": {"value": world * B * KE / e2e_s, "steps": KE, "unit": "env-steps/s", "reward_mode": HEAD,
+                    "us_per_step": 1e6 * e2e_s / KE, "h2d_bytes_per_step": 4 * B * world, "d2h_bytes_per_step": 4 * B * world,
+                    "pipelined_value": world * B * KE / pipe_s,
+                    "pipelined_path": "ipp_step_submit / ipp_step_wait, 2 slots: same per-step H2D ids + rewards to pinned host memory, upload of "
+                                      "step t+1 under the kernel of step t",
                     "path": ("BatchedEngine.step (ipp_step: pinned host ids -> H2D -> fused kernel -> "
                              + ("rewards written by the kernel into the caller's pinned buffer [zero-copy D2H, 4 B/env over PCIe])"
-                                if zero_copy_steps > 0 else "D2H rewards)")) if dist is None else
-                            "pinned host ids -> H2D -> ipp_step_device -> NCCL all_gather(rewards) -> D2H"},
-            "gpu_launches": int(results["entropy"]["launches"]),
+                                if zero_copy_steps > 0 else "D2H rewards)"))
+                            + ("" if dist is None else "; every rank writes its slice of ONE pinned segment shared by the node's ranks "
+                               "(POSIX shm + cudaHostRegister), the learner rank reads the whole batch's rewards there: no collective on the step path")},
+            "gpu_launches": int(results[HEAD]["launches"]),
             "gpu_launches_e2e": int(launches_e2e),
             "clocks": clocks,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if mcts_res is not None:
+            mcts_res["frac_of_hbm_peak"] = mcts_res["achieved_gbs"] / peak / world
+            line["roofline"]["mcts"] = mcts_res
             line["mcts_rollouts"] = mcts_res
         print(json.dumps(line))
     eng.close()
@@ -429,7 +545,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="envs per GPU")
-    ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "tiled"), choices=["planes", "mv", "tiled", "super"])
+    ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "super"), choices=["planes", "mv", "tiled", "super"])
     ap.add_argument("--cpu-envs", type=int, default=4096, help="env sample of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=500, help="steps of the host-buffer (e2e) leg (<= --steps)")

@@ -86,6 +86,22 @@ __device__ __forceinline__ void node_pose(const StepParams &p, const TreeArrays 
     }
 }
 
+// order-preserving map float -> unsigned (for the hardware warp reductions, REDUX): a < b  <=>  fkey(a) < fkey(b)
+__device__ __forceinline__ unsigned fkey(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+// arg max over the warp of (value, lowest slot among equal values): returns the winning lane (every lane takes part)
+__device__ __forceinline__ int warp_argmax_lowest_slot(float value, int slot, float &best, int &best_slot) {
+    const unsigned k = fkey(value);
+    const unsigned kmax = __reduce_max_sync(0xffffffffu, k);
+    const int cand = k == kmax ? slot : 0x7fffffff;
+    best_slot = __reduce_min_sync(0xffffffffu, cand);
+    best = fkey_inv(kmax);
+    return __ffs(__ballot_sync(0xffffffffu, k == kmax && slot == best_slot)) - 1;
+}
+
 struct Slot {
     int lvl, col, row;
     bool in_grid;
@@ -144,11 +160,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             qmin = fminf(qmin, q);
             qmax = fmaxf(qmax, q);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            qmin = fminf(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
-            qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
-        }
+        qmin = fkey_inv(__reduce_min_sync(0xffffffffu, fkey(qmin)));
+        qmax = fkey_inv(__reduce_max_sync(0xffffffffu, fkey(qmax)));
         const float qscale = qmax > qmin ? 1.0f / (qmax - qmin) : 0.0f;  // all zero -> values unchanged (= 0)
         // compute_uct (mcts.py:280-296): the node's edges, then its best unvisited action (Q = N = 0)
         const float prior_c = d.c_init + logf(((float)Ns + d.c_base + 1.0f) / d.c_base);
@@ -177,16 +190,9 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
                 best_e = -1;
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int os = __shfl_xor_sync(0xffffffffu, best_s, o);
-            const int oe = __shfl_xor_sync(0xffffffffu, best_e, o);
-            if (ob > best || (ob == best && os < best_s)) {
-                best = ob;
-                best_s = os;
-                best_e = oe;
-            }
+        {
+            const int win = warp_argmax_lowest_slot(best, best_s, best, best_s);
+            best_e = __shfl_sync(0xffffffffu, best_e, win);
         }
         int child = kNoNode;
         if (best_e < 0) {
@@ -210,15 +216,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
                     bs = s;
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float op = __shfl_xor_sync(0xffffffffu, bp, o);
-                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-                if (op > bp || (op == bp && os < bs)) {
-                    bp = op;
-                    bs = os;
-                }
-            }
+            warp_argmax_lowest_slot(bp, bs, bp, bs);
             if (lane == 0) a.bu[(size_t)t * d.M + node] = make_int2(bp >= 0.0f ? bs : -1, __float_as_int(bp));
         } else {
             child = edges[best_e].child;
@@ -360,15 +358,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
                     bs = s;
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float op = __shfl_xor_sync(0xffffffffu, bp, o);
-                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-                if (op > bp || (op == bp && os < bs)) {
-                    bp = op;
-                    bs = os;
-                }
-            }
+            warp_argmax_lowest_slot(bp, bs, bp, bs);
             if (lane == 0) {
                 hdr[node] = make_int4(h.x, h.y, 0, (h.w & 0xFF) | (1 << 8));
                 a.bu[(size_t)t * d.M + node] = make_int2(bs, __float_as_int(bp));

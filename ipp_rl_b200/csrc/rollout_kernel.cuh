@@ -29,7 +29,7 @@ struct RolloutParams {
 template <int LAYOUT>
 __global__ void __launch_bounds__(kRolloutWarps * 32) ipp_rollout_kernel(const __grid_constant__ RolloutParams rp) {
     extern __shared__ float s_tiles[];  // [warp][horizon - 1][tile_floats]
-    __shared__ int s_rect[kRolloutWarps][kMaxHorizon][4];  // xl, yu, nx, ny of the earlier steps
+    __shared__ int4 s_rect[kRolloutWarps][kMaxHorizon];  // {xl, yu, nx, ny} of the earlier steps
 
     const StepParams &p = rp.base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -65,25 +65,68 @@ __global__ void __launch_bounds__(kRolloutWarps * 32) ipp_rollout_kernel(const _
             const int r0 = 2 * qyy, c0 = 2 * qxx;
             const bool cok = c0 + 1 < g.nx, rok = r0 + 1 < g.ny;
             const bool ok[4] = {true, cok, rok, cok && rok};
-            float m[4], v[4];
+            float m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
+            const int R0 = g.yu + r0, C0 = g.xl + c0;
+            // Where does the quad's variance come from?  The latest earlier step of this path whose footprint covers it, else the
+            // env's belief in HBM.  Classify the whole quad against each earlier rectangle (one 16-byte shared load per step):
+            // fully inside -> its overlay tile, disjoint from all -> HBM, straddling a border -> cell by cell.
+            int src = -1;        // >= 0: overlay tile of that step; -1: HBM; -2: mixed
+            int4 rc = make_int4(0, 0, 0, 0);
+            for (int s = k - 1; s >= 0; --s) {
+                rc = s_rect[wib][s];
+                const int dx0 = C0 - rc.x, dy0 = R0 - rc.y, dx1 = dx0 + (cok ? 1 : 0), dy1 = dy0 + (rok ? 1 : 0);
+                const bool in_x0 = (unsigned)dx0 < (unsigned)rc.z, in_x1 = (unsigned)dx1 < (unsigned)rc.z;
+                const bool in_y0 = (unsigned)dy0 < (unsigned)rc.w, in_y1 = (unsigned)dy1 < (unsigned)rc.w;
+                if (in_x0 && in_x1 && in_y0 && in_y1) {
+                    src = s;
+                    break;
+                }
+                if ((in_x0 || in_x1) && (in_y0 || in_y1)) {
+                    src = -2;
+                    break;
+                }
+            }
+            if (src >= 0) {
+                const float *t = tiles + (size_t)src * rp.tile_floats + (R0 - rc.y) * rc.z + (C0 - rc.x);
+                v[0] = t[0];
+                if (cok) v[1] = t[1];
+                if (rok) v[2] = t[rc.z];
+                if (cok && rok) v[3] = t[rc.z + 1];
+                if (adaptive) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                m[c] = 0.0f;
-                v[c] = 0.0f;
-                if (!ok[c]) continue;
-                const int R = g.yu + r0 + (c >> 1), C = g.xl + c0 + (c & 1);
-                // latest earlier step of this path that covered the cell, else the env's variance in HBM
-                bool found = false;
-                for (int s = k - 1; s >= 0 && !found; --s) {
-                    const int dx = C - s_rect[wib][s][0], dy = R - s_rect[wib][s][1];
-                    if ((unsigned)dx < (unsigned)s_rect[wib][s][2] && (unsigned)dy < (unsigned)s_rect[wib][s][3]) {
-                        v[c] = tiles[(size_t)s * rp.tile_floats + dy * s_rect[wib][s][2] + dx];
-                        found = true;
+                    for (int c = 0; c < 4; ++c)
+                        if (ok[c]) m[c] = bel.load_mean(Belief<LAYOUT>::idx(p, R0 + (c >> 1), C0 + (c & 1)));
+                }
+            } else if (src == -1) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (!ok[c]) continue;
+                    const int off = Belief<LAYOUT>::idx(p, R0 + (c >> 1), C0 + (c & 1));
+                    if (LAYOUT == IPP_LAYOUT_PLANES || !adaptive) {
+                        v[c] = bel.load_var(off);
+                        if (adaptive) m[c] = bel.load_mean(off);
+                    } else {
+                        bel.load(off, m[c], v[c]);  // one 8-byte load for {mean, var}
                     }
                 }
-                const int off = Belief<LAYOUT>::idx(p, R, C);
-                if (!found) v[c] = bel.load_var(off);
-                if (adaptive) m[c] = bel.load_mean(off);  // the mean never changes in a prediction step
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (!ok[c]) continue;
+                    const int R = R0 + (c >> 1), C = C0 + (c & 1);
+                    bool found = false;
+                    for (int s = k - 1; s >= 0 && !found; --s) {
+                        const int4 r4 = s_rect[wib][s];
+                        const int dx = C - r4.x, dy = R - r4.y;
+                        if ((unsigned)dx < (unsigned)r4.z && (unsigned)dy < (unsigned)r4.w) {
+                            v[c] = tiles[(size_t)s * rp.tile_floats + dy * r4.z + dx];
+                            found = true;
+                        }
+                    }
+                    const int off = Belief<LAYOUT>::idx(p, R, C);
+                    if (!found) v[c] = bel.load_var(off);
+                    if (adaptive) m[c] = bel.load_mean(off);  // the mean never changes in a prediction step
+                }
             }
             const float z[4] = {0.f, 0.f, 0.f, 0.f};
             float mn[4], vn[4];
@@ -103,10 +146,7 @@ __global__ void __launch_bounds__(kRolloutWarps * 32) ipp_rollout_kernel(const _
         if (lane == 0) {
             const float cost = job_cost(p, g.px, g.py, g.ph, qx, qy, qh);
             rp.rewards[(size_t)job * H + k] = accd * fast_rcp(cost + 1.0f);
-            s_rect[wib][k][0] = g.xl;
-            s_rect[wib][k][1] = g.yu;
-            s_rect[wib][k][2] = g.nx;
-            s_rect[wib][k][3] = g.ny;
+            s_rect[wib][k] = make_int4(g.xl, g.yu, g.nx, g.ny);
         }
         qx = g.px;
         qy = g.py;

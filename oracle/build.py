@@ -13,15 +13,22 @@ OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libipp_oracle.so")
 
 
-def build_oracle(force: bool = False) -> str:
+LIB_NATIVE = os.path.join(OUT_DIR, "libipp_oracle_native.so")
+
+
+def build_oracle(force: bool = False, native: bool = False) -> str:
+    """``native``: -O3 -march=native for the machine this runs on (the CPU-baseline leg of bench.py builds it on the box
+    whose cores it times; the portable -O2 build is the one that ships with the snapshot and checks parity)."""
     os.makedirs(OUT_DIR, exist_ok=True)
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
-        return LIB
-    cmd = ["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-o", LIB, SRC, "-lm"]
+    lib = LIB_NATIVE if native else LIB
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= os.path.getmtime(SRC):
+        return lib
+    opt = ["-O3", "-march=native"] if native else ["-O2"]
+    cmd = ["gcc"] + opt + ["-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-o", lib, SRC, "-lm"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"gcc failed:\n{res.stdout}\n{res.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

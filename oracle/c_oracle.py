@@ -21,10 +21,28 @@ class orc_cfg(C.Structure):
 _lib = None
 
 
+_native = False
+
+
+def use_native_build() -> str:
+    """Switch to a -O3 -march=native build made on THIS machine (CPU-baseline timing only; call before the first use).
+    Falls back to the portable build when gcc is missing."""
+    global _lib, _native
+    try:
+        path = _build.build_oracle(force=True, native=True)
+        _lib, _native = None, True
+        return f"-O3 -march=native, built on this host ({os.path.basename(path)})"
+    except Exception as exc:
+        return f"-O2 portable build (native build failed: {exc!r})"
+
+
 def lib():
     global _lib
     if _lib is None:
-        path = _build.LIB if os.path.exists(_build.LIB) and os.path.getmtime(_build.LIB) >= os.path.getmtime(_build.SRC) else _build.build_oracle()
+        if _native:
+            path = _build.LIB_NATIVE
+        else:
+            path = _build.LIB if os.path.exists(_build.LIB) and os.path.getmtime(_build.LIB) >= os.path.getmtime(_build.SRC) else _build.build_oracle()
         _lib = C.CDLL(path)
         _lib.orc_step.restype = C.c_int
         _lib.orc_step.argtypes = [C.POINTER(orc_cfg), C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_uint64, C.c_int64, C.c_uint64, C.c_int,

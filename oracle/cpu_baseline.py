@@ -28,6 +28,7 @@ def run(workload: dict, steps: int = 3, warmup: int = 1, envs: int = 4096, rewar
     X, Y, res = workload["x_dim"], workload["y_dim"], workload["resolution"]
     cfg = c_oracle.make_cfg(X, Y, res, workload.get("angle_x", 60.0), workload.get("angle_y", 60.0), workload.get("coeff_a", 0.05),
                             workload.get("coeff_b", 0.2), 10.0, workload.get("max_v", 2.0), workload.get("max_a", 2.0))
+    build_note = c_oracle.use_native_build()
     c_oracle.use_all_cores()
     rng = np.random.RandomState(4242)
     base = _synthetic_gt(rng, 32, Y, X)
@@ -62,5 +63,5 @@ def run(workload: dict, steps: int = 3, warmup: int = 1, envs: int = 4096, rewar
         "kind": "port",
         "envs": envs,
         "sample": f"{done} steps x {envs} envs of the same 200x200 / 3-altitude workload, fp64 C port (oracle/ipp_oracle.c), OpenMP "
-                  f"over envs, Philox noise; {dt:.2f} s wall",
+                  f"over envs, Philox noise, {build_note}; {dt:.2f} s wall",
     }

@@ -74,3 +74,93 @@ def test_observation_planes_match_reference_feature_planes(layout):
             cost = g[f"{tag}_cost_by_action"]  # indexed by action id X*col + row (planning/common/actions.py:94-96)
             cols, rows = np.meshgrid(np.arange(X), np.arange(Y))
             assert np.max(np.abs(obs[0, 5] - cost[X * cols + rows])) <= 1e-6
+
+
+@pytest.mark.parametrize("layout", [1, 3])
+def test_device_hotspot_and_split_fields(layout):
+    """ipp_generate_field: the reference's construction (simulations/simulations.py:57-125) per env on the device — two-valued
+    maps with the reference's value ranges and geometry, keyed by the global env id (sharding invariance), and the same
+    statistics as the host twins that are pinned bit for bit against the reference (tests/test_missions_host.py)."""
+    X, Y, r, B = 40, 30, 5, 512
+    params = make_params(X, Y, 1.0, 8, 14, 6)
+    with _engine(params, B, layout=layout, seed=1) as eng:
+        eng.generate_field("hotspot_random_field", r, seed=11)
+        hot = eng.get_ground_truth()
+        eng.generate_field("split_random_field", r, seed=12)
+        split = eng.get_ground_truth()
+    with _engine(params, 64, layout=1, seed=1, env_id_offset=100) as eng:
+        eng.generate_field("hotspot_random_field", r, seed=11)
+        assert np.array_equal(eng.get_ground_truth(), hot[100:164])  # keyed by the GLOBAL env id
+        eng.generate_field("split_random_field", r, seed=12, first_env=10, n_env=20)
+        assert np.array_equal(eng.get_ground_truth(10, 20), split[110:130])
+    areas = []
+    for b in range(B):
+        vals = np.unique(hot[b])
+        assert len(vals) == 2 and 0.0 <= vals[0] <= 0.3 and 0.7 <= vals[1] <= 1.0
+        m = hot[b] == vals[1]
+        rows, cols = np.flatnonzero(m.any(1)), np.flatnonzero(m.any(0))
+        # two axis-aligned squares of side <= 2r whose centres are more than r apart in BOTH axes: their row ranges may touch, never nest
+        assert m.sum() <= 2 * (2 * r) ** 2 and m.sum() >= r * r
+        areas.append(m.sum())
+        lab_rows = np.split(rows, np.flatnonzero(np.diff(rows) > 1) + 1)
+        assert len(lab_rows) <= 2 and len(np.split(cols, np.flatnonzero(np.diff(cols) > 1) + 1)) <= 2
+        vs = np.unique(split[b])
+        assert len(vs) == 2 and 0.0 <= vs[0] <= 0.35 and 0.65 <= vs[1] <= 1.0
+        first = split[b][0, 0]
+        by_rows = np.all(split[b] == split[b][:, :1])  # constant along x -> split along y
+        if by_rows:
+            cut = int(np.argmax(split[b][:, 0] != first))
+            assert int(np.ceil(Y * 0.33)) <= cut <= int(np.ceil(Y * 0.66)) and np.all(split[b][:cut] == first) and np.all(split[b][cut:] != first)
+        else:
+            assert np.all(split[b] == split[b][:1, :])
+            cut = int(np.argmax(split[b][0] != first))
+            assert int(np.floor(X * 0.33)) <= cut <= int(np.ceil(X * 0.66)) and np.all(split[b][:, :cut] == first)
+    # statistics against the (reference-pinned) host twins under NumPy's RNG
+    from ipp_rl_b200.mapping.grid_maps import GridMap
+    from ipp_rl_b200.sensors.models.sensor_model_factories import SensorModelFactory
+    from ipp_rl_b200.sensors.sensor_factories import SensorFactory
+    from ipp_rl_b200.simulations.simulations import HotspotRandomField, SplitRandomField
+
+    gm = GridMap(params)
+    sensor = SensorFactory(params, SensorModelFactory(params).create_sensor_model(), gm).create_sensor()
+    np.random.seed(0)
+    host_hot = np.stack([HotspotRandomField(sensor, r).ground_truth_map for _ in range(B)])
+    host_split = np.stack([SplitRandomField(sensor, r).ground_truth_map for _ in range(B)])
+    assert abs(hot.mean() - host_hot.mean()) < 0.03 and abs(split.mean() - host_split.mean()) < 0.05
+    assert abs(np.mean(areas) - np.mean([(h == h.max()).sum() for h in host_hot])) < 12
+    by_rows_dev = np.mean([np.all(s == s[:, :1]) for s in split])
+    assert 0.4 < by_rows_dev < 0.6
+
+
+@pytest.mark.parametrize("layout", [0, 3])
+def test_device_shuffled_priors(layout):
+    """ipp_reset_shuffled: Mapping.init_priors(shuffle_prior_cov=True) per env (mapping/mappings.py:219-240)."""
+    X = Y = 20
+    B = 1024
+    params = make_params(X, Y, 1.0, 8, 14, 6)
+    with _engine(params, B, layout=layout, seed=1) as eng:
+        eng.reset_shuffled(0.5, fit_gaussian_process=True, scale=1.82, seed=5)
+        m, v = eng.get_state()
+        assert np.all(m == 0.5)
+        lv = v.reshape(B, -1)
+        assert np.all(lv == lv[:, :1])  # GP mode: the Matern prior's diagonal is one signal variance per env
+        assert lv[:, 0].min() >= 0.8 * 1.82 - 1e-6 and lv[:, 0].max() <= 1.2 * 1.82 + 1e-6
+        assert abs(lv[:, 0].mean() - 1.82) < 0.02 and abs(lv[:, 0].std() - 0.4 * 1.82 / np.sqrt(12)) < 0.02
+        assert np.allclose(eng.get_prev_pose(), [2.0, 2.0, 14.0])
+        eng.reset_shuffled(0.5, fit_gaussian_process=False, scale=0.5, seed=6)
+        _, v2 = eng.get_state()
+    with _engine(params, 32, layout=1, seed=1, env_id_offset=64) as eng:
+        eng.reset_shuffled(0.5, fit_gaussian_process=True, scale=1.82, seed=5)
+        assert np.array_equal(eng.get_state()[1], v[64:96])
+    # non-GP: diag(A A^T) / ||A||_F with A ~ N(mu, mu), mu ~ U(0.1, 0.5): level sqrt(2) mu, a small per-cell spread
+    lv2 = v2.reshape(B, -1)
+    level = lv2.mean(1)
+    assert level.min() >= np.sqrt(2) * 0.1 * 0.97 and level.max() <= np.sqrt(2) * 0.5 * 1.03
+    assert abs(level.mean() - np.sqrt(2) * 0.3) < 0.02
+    rel = lv2.std(1) / level
+    assert np.all(rel > 0) and abs(rel.mean() - np.sqrt(6.0 / (X * Y)) / 2) < 0.01
+    # the same statistic from the reference's construction (host, NumPy)
+    rng = np.random.RandomState(0)
+    a = rng.normal(0.3, 0.3, (X * Y, X * Y))
+    d = np.einsum("ij,ij->i", a, a) / np.linalg.norm(a)
+    assert abs(d.mean() - np.sqrt(2) * 0.3) < 0.01 and abs(d.std() / d.mean() - np.sqrt(6.0 / (X * Y)) / 2) < 0.01
