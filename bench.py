@@ -169,6 +169,12 @@ class SharedRewards:
         dist.barrier()
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name)
+            try:  # attached, not owned: keep Python's resource tracker from unlinking (and warning about) the creator's segment
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         arr = np.ndarray((self.bytes,), dtype=np.uint8, buffer=self.shm.buf)
         self.rewards = arr[: self.SLOTS * world * per_rank * 4].view(np.float32).reshape(self.SLOTS, world, per_rank)
         self.flags = arr[self.SLOTS * world * per_rank * 4 :].view(np.int64)[: 64]  # flags[r] = steps rank r has completed, flags[32] = consumed by the learner
@@ -308,6 +314,15 @@ def run_ours(args, rank, world, local_rank):
                                          reward_mode=capi.REWARD_TRACE),
             "predict")
         predict_persistent = eng.path_launches("async") - pl0 >= K
+        # ... and the evaluate-only form (IPP_FLAG_NO_COMMIT: rewards of candidate actions, nothing written — what greedy_search
+        # and the tree search ask for): the same staged reads without the write-back
+        results["predict_eval"] = timed_device_loop(
+            lambda t: eng.predict_device(B, action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), commit=False,
+                                         reward_mode=capi.REWARD_TRACE),
+            "predict[no commit]")
+
+        # the clock sampler polls nvidia-smi, which takes driver locks for ~1 ms at a time: stop it before the latency-bound legs
+        clocks = sampler.stop() if sampler else None
 
         # ---- e2e: host buffers through the public step call, H2D + kernel + rewards back on the host, every step -----------
         ids_pinned = torch.from_numpy(ids_e2e).pin_memory()
@@ -336,7 +351,10 @@ def run_ours(args, rank, world, local_rank):
                 if rank == 0:
                     checksum[0] = float(shared.learner_collect(s)[:: 4096].sum())
 
-        KE = min(K, args.e2e_steps)  # the e2e leg is host-latency bound; keep the default run short
+        # The e2e legs are host-latency bound (~25 us of copy / launch / wake-up around a ~120 us kernel) and any other process that
+        # polls the driver (nvidia-smi, ~1 ms per poll) shows up in them: time a few hundred steps whatever K is, so that one such
+        # stall is not a third of the measurement.
+        KE = args.e2e_steps
         for t in range(W):
             e2e_step(t, 0)
         barrier()
@@ -414,8 +432,21 @@ def run_ours(args, rank, world, local_rank):
                      forced_playout_factor=2.0, max_valid_action_distance=11.5)
         meta = dict(episode_horizon=5, scenario_info=None)
         budgets = np.full(Tm, 150.0, np.float32)
+        # The search only READS the variance (4 B per footprint cell): it runs on its own engine in the layout that drags the
+        # fewest other bytes through the 128-byte lines DRAM serves (--mcts-layout; the step engine's super-tiles interleave
+        # mean, variance and ground truth for the full step).  A few executed steps first, so that the beliefs are not uniform.
+        meng = eng
+        if args.mcts_layout != args.layout:
+            mcfg = EngineConfig(batch=Tm, layout=capi.LAYOUT_NAMES[args.mcts_layout], device=local_rank, seed=20260925, env_id_offset=rank * B,
+                                stream=stream.cuda_stream, **WORKLOAD)
+            meng = BatchedEngine(mcfg)
+            meng.reset(PRIOR_MEAN, PRIOR_VAR)
+            meng.synth_ground_truth(seed=1000)
+            with torch.cuda.stream(stream):
+                for t in range(4):
+                    meng.step(np.ascontiguousarray(ids_host[t % POOL][:Tm]), reward_mode=capi.REWARD_TRACE)
         with torch.cuda.stream(stream):
-            with BatchedMCTS(eng, hyper, meta, n_trees=Tm) as mcts:
+            with BatchedMCTS(meng, hyper, meta, n_trees=Tm) as mcts:
                 # pass 1 (untimed, host-synchronous): count the prediction steps / expansions of the search (it is deterministic)
                 mcts.begin(budgets)
                 edges, expansions, path_cells = 0, 0, 0.0
@@ -449,9 +480,10 @@ def run_ours(args, rank, world, local_rank):
                             "ms_per_lockstep_simulation": ms_m / Sm, "gpu_launches": int(mcts.launches - l0),
                             "algorithmic_bytes": alg_mcts, "achieved_gbs": alg_mcts / (ms_m * 1e-3) / 1e9,
                             "tree_bytes_per_gpu": int(mcts.info.device_bytes),
+                            "layout": args.mcts_layout,
                             "evaluator": "uniform priors, zero values (network outside this library)"}
-
-    clocks = sampler.stop() if sampler else None
+        if meng is not eng:
+            meng.close()
 
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
     cpu = None
@@ -496,6 +528,9 @@ def run_ours(args, rank, world, local_rank):
                      "bytes_per_cell": 8, "note": "covariance-only step on the interleaved {mean,var} layout: the staged run and the written "
                                                  "sectors carry the mean (and, in the super-tile layout, the ground truth) too, so ~27 B per "
                                                  "cell move where 8 B are algorithmic (DESIGN.md 3.1)"})
+        pe = mode_block("predict_eval", (4.0 * cells_timed_total + 16.0 * B * K) / K)
+        pred["evaluate_only"] = {"value": pe["value"], "ms_per_launch": pe["ms_per_launch"], "achieved": pe["achieved"], "frac": pe["frac"],
+                                 "bytes_per_cell": 4, "note": "IPP_FLAG_NO_COMMIT: the variance is read, nothing is written"}
         line = {
             "metric": "env_steps_per_sec", "value": head["value"], "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": head["ms_per_launch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -548,11 +583,12 @@ def main():
     ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "super"), choices=["planes", "mv", "tiled", "super"])
     ap.add_argument("--cpu-envs", type=int, default=4096, help="env sample of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=500, help="steps of the host-buffer (e2e) leg (<= --steps)")
+    ap.add_argument("--e2e-steps", type=int, default=300, help="steps of the host-buffer (e2e) legs (independent of --steps)")
     ap.add_argument("--zero-copy", default=None, choices=["", "r", "i", "ri"],
                     help="e2e leg: host buffers the kernel accesses in place (r = rewards, i = action ids); default = the engine's (r)")
     ap.add_argument("--mcts-trees", type=int, default=16384, help="trees of the secondary mcts_zero rollout leg = BASELINE.json C4 per-GPU share (0 = skip)")
     ap.add_argument("--mcts-sims", type=int, default=32)
+    ap.add_argument("--mcts-layout", default="planes", choices=["planes", "mv", "tiled", "super"], help="belief layout of the search leg's engine")
     ap.add_argument("--max-altitude", type=float, default=None, help="experiments only: override the top altitude of the action set")
     args = ap.parse_args()
     if args.warmup < 3:

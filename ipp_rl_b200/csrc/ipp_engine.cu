@@ -791,16 +791,21 @@ static TiledDims tiled_dims(const ipp_engine *e) {
     return d;
 }
 
+// the kernels' status word (mapped host memory): bit 0 unsupported footprint, bit 1 invalid action id
+static int status_error(ipp_engine *e) {
+    const int st = *(volatile int *)e->h_status;
+    if (st == 0) return IPP_OK;
+    *(volatile int *)e->h_status = 0;
+    if (st & 2)
+        return fail(e, IPP_ERR_INVALID, "action id outside the action table (planning/common/actions.py:73-91: level * N + x_dim * col + row); the step ran on the clamped id");
+    return fail(e, IPP_ERR_UNSUPPORTED, "footprint needs cv2 INTER_AREA with an up-sampling axis (non-square FoV/grid corner case); not supported");
+}
+
 static int check_status(ipp_engine *e) {
     // the status word lives in mapped host memory: visible here once the stream has drained
     CU(e, cudaStreamSynchronize(e->stream));
     for (int k = 0; k < IPP_STEP_SLOTS; ++k) e->slot_busy[k] = false;  // submitted steps run on this stream: drained too
-    if (*(volatile int *)e->h_status & 1) {
-        *(volatile int *)e->h_status = 0;
-        return fail(e, IPP_ERR_UNSUPPORTED,
-                    "footprint needs cv2 INTER_AREA with an up-sampling axis (non-square FoV/grid corner case); not supported");
-    }
-    return IPP_OK;
+    return status_error(e);
 }
 
 extern "C" int ipp_sync(ipp_engine *e) {
@@ -1252,12 +1257,7 @@ extern "C" int ipp_step_wait(ipp_engine *e, int32_t slot) {
     if (!e->slot_busy[slot]) return IPP_OK;
     CU(e, cudaEventSynchronize(e->ev_done[slot]));
     e->slot_busy[slot] = false;
-    if (*(volatile int *)e->h_status & 1) {
-        *(volatile int *)e->h_status = 0;
-        return fail(e, IPP_ERR_UNSUPPORTED,
-                    "footprint needs cv2 INTER_AREA with an up-sampling axis (non-square FoV/grid corner case); not supported");
-    }
-    return IPP_OK;
+    return status_error(e);
 }
 
 // Measurement only (Sensor.take_measurement, sensors/cameras.py:108-116) and update with a

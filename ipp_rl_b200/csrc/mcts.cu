@@ -497,6 +497,8 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
     if (!(cfg->max_valid_action_distance > 0) || !(cfg->puct_base > 0))
         return mfail(nullptr, IPP_ERR_INVALID, "ipp_mcts_create: max_valid_action_distance and puct_base must be > 0");
     if (info.x_dim > 4095 || info.y_dim > 4095) return mfail(nullptr, IPP_ERR_UNSUPPORTED, "ipp_mcts_create: grids beyond 4095 cells per side");
+    if (info.x_dim != info.y_dim)  // level * N + x_dim * col + row is a bijection on square grids only (the dense prior is indexed by it)
+        return mfail(nullptr, IPP_ERR_UNSUPPORTED, "ipp_mcts_create: the reference's action ids are ambiguous on non-square grids (%d x %d)", info.x_dim, info.y_dim);
 
     ipp_mcts *m = new (std::nothrow) ipp_mcts();
     if (!m) return mfail(nullptr, IPP_ERR_NOMEM, "ipp_mcts_create: out of host memory");

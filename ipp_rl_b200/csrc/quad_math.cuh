@@ -187,6 +187,9 @@ struct Geom {
 };
 
 // planning/common/actions.py:73-91: id = level*N + x_dim*col + row
+// Ids outside [0, levels * N) are clamped (memory safety) and reported through the status word (bit 1 -> IPP_ERR_INVALID).
+// On non-square grids the reference's formula is not a bijection (col or row can leave the map for ids < levels * N): those
+// are clamped onto the border cell, as the host-side action table drops them.
 __device__ __forceinline__ void decode_id(const StepParams &p, int id_raw, int &lvl, int &col, int &row) {
     const int N = p.X * p.Y;
     const int id = clampi(id_raw, 0, p.n_levels * N - 1);
@@ -194,6 +197,7 @@ __device__ __forceinline__ void decode_id(const StepParams &p, int id_raw, int &
     const int i = id - lvl * N;
     col = fdiv(i, p.X, p.inv_X);
     row = i - col * p.X;
+    if (id != id_raw) *(volatile int *)p.status = 2;
     col = min(col, p.X - 1);
     row = min(row, p.Y - 1);
 }

@@ -437,3 +437,32 @@ def test_edge_grids_and_batches(layout, G, B):
             st.mean, st.var = mean.astype(np.float64), var.astype(np.float64)
         jobs = eng.predict(np.zeros(0, np.int32), env_index=np.zeros(0, np.int32), commit=False)  # empty job list
         assert jobs.shape == (0,)
+
+
+def test_invalid_action_ids_are_reported():
+    """Ids outside the action table raise instead of silently stepping a clamped action; the tree search refuses
+    non-square grids, where the reference's id formula is not a bijection."""
+    from ipp_rl_b200._capi import IPP_ERR_INVALID, IppError
+
+    params = make_params(24, 24, 1.0, 8, 20, 6)
+    for layout in (1, 3):
+        with _engine(params, 8, layout=layout) as eng:
+            eng.reset(0.5, 1.82)
+            ids = np.arange(8, dtype=np.int32)
+            eng.step(ids)
+            bad = ids.copy()
+            bad[3] = eng.num_actions
+            with pytest.raises(IppError) as ei:
+                eng.step(bad)
+            assert ei.value.code == IPP_ERR_INVALID
+            bad[3] = -1
+            with pytest.raises(IppError):
+                eng.step(bad)
+            eng.step(ids)  # the engine stays usable
+    params = make_params(30, 20, 2.0, 8, 26, 9)
+    from ipp_rl_b200.planning.mcts_zero import BatchedMCTS
+
+    with _engine(params, 4, layout=1) as eng:
+        with pytest.raises(IppError):
+            BatchedMCTS(eng, dict(puct_init=1.0, puct_base=100, num_mcts_simulations=4, gamma=1.0, forced_playout_factor=2.0,
+                                  max_valid_action_distance=7.5), dict(episode_horizon=2, scenario_info=None))

@@ -1,0 +1,21 @@
+#!/bin/bash
+# round 2 evidence: full GPU test suite, sanitizer, launch list, full ncu capture + DRAM traffic of the step kernel, MCTS kernels, bench lines
+O=gpurun_out; mkdir -p $O
+T=${1:-r02}
+timeout 1500 python -m pytest tests -m gpu -x -q > $O/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 $O/${T}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${T}_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 $O/${T}_smoke.log
+timeout 900 compute-sanitizer --tool memcheck --log-file $O/${T}_sanitizer_memcheck.log python tools/sanitize_small.py > $O/${T}_sanitizer_memcheck.out 2>&1; echo "memcheck rc=$?"; tail -2 $O/${T}_sanitizer_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck --log-file $O/${T}_sanitizer_racecheck.log python tools/sanitize_small.py 1 3 > $O/${T}_sanitizer_racecheck.out 2>&1; echo "racecheck rc=$?"; tail -2 $O/${T}_sanitizer_racecheck.log
+timeout 900 compute-sanitizer --tool synccheck --log-file $O/${T}_sanitizer_synccheck.log python tools/sanitize_small.py 3 > $O/${T}_sanitizer_synccheck.out 2>&1; echo "synccheck rc=$?"; tail -2 $O/${T}_sanitizer_synccheck.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/${T}_launches.csv \
+  python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 4 --mcts-sims 8 > $O/${T}_launches_bench.log 2>&1
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:ipp_step_bulk -s 4 -c 6 --csv \
+  --log-file $O/${T}_traffic_super.csv python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 2 --mcts-trees 0 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ipp_step_bulk -s 6 -c 1 -f -o $O/${T}_bulk_step \
+  python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 2 --mcts-trees 0 > $O/${T}_ncu_bench.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct --clock-control none -k regex:"mcts_|rollout" -c 120 --csv --log-file $O/${T}_mcts_launches.csv \
+   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 2 --mcts-sims 24 > /dev/null 2>&1
+python bench.py --impl reference --steps 5 --warmup 3 > $O/${T}_bench_ref.json 2>/dev/null; cut -c1-200 $O/${T}_bench_ref.json
+python bench.py --steps 20 --warmup 5 > $O/${T}_bench_k20.json 2> $O/${T}_bench_k20.err; cut -c1-200 $O/${T}_bench_k20.json
+python bench.py > $O/${T}_bench.json 2> $O/${T}_bench.err; cut -c1-300 $O/${T}_bench.json
+ls -la $O | tail -20

@@ -1,7 +1,7 @@
 """Small, fast exercise of every hand-written kernel for compute-sanitizer (memcheck / racecheck / synccheck runs are 10-100x
 slower than native, so the sizes are tiny but cover: all four layouts, the three step kernels (bulk / cp.async / LSU), both
 reward modes, the adaptive mask, host noise + measurement read-back, clipped / corner footprints, predict (persistent and
-job-list), path rollouts, the lock-step MCTS kernels, eval, observe, GRF reset and the experience ring).
+job-list), path rollouts, the lock-step MCTS kernels, eval, observe, GRF / field / prior reset).
 
     compute-sanitizer --tool racecheck python tools/sanitize_small.py
 """
@@ -46,6 +46,17 @@ def main():
             eng.eval()
             eng.observe(0, 4)
             eng.generate_ground_truth(3.0, seed=1, first_env=0, n_env=8)
+            eng.generate_field("hotspot_random_field", 5, seed=3)
+            eng.generate_field("split_random_field", 5, seed=4, first_env=3, n_env=50)
+            eng.reset_shuffled(0.5, fit_gaussian_process=True, scale=1.82, seed=2)
+            eng.reset_shuffled(0.5, fit_gaussian_process=False, scale=0.5, seed=2)
+        # the tree search needs a square grid (the reference's action ids are a bijection only there)
+        cfg = EngineConfig(batch=96, x_dim=40, y_dim=40, resolution=1.0, min_altitude=8.0, max_altitude=20.0, altitude_spacing=6.0,
+                           layout=layout, seed=7, interval_factor=0.25, value_threshold=0.45)
+        with BatchedEngine(cfg) as eng:
+            eng.reset(0.5, 1.82)
+            eng.set_ground_truth(gt[:96, :40, :40].copy())
+            eng.step(rng.randint(0, eng.num_actions, 96).astype(np.int32))
             hyper = dict(puct_init=6.0, puct_base=10000, num_mcts_simulations=6, gamma=0.95, dirichlet_alpha=0.3, dirichlet_eps=0.25,
                          forced_playout_factor=2.0, max_valid_action_distance=7.5)
             with BatchedMCTS(eng, hyper, dict(episode_horizon=3, scenario_info=None), n_trees=64) as mcts:
