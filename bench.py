@@ -189,18 +189,24 @@ class SharedRewards:
     def publish(self, step):
         self.flags[self.rank] = step + 1
 
+    def _spin(self, cond, what):
+        t0 = time.perf_counter()
+        n = 0
+        while not cond():
+            n += 1
+            if (n & 0xFFFF) == 0 and time.perf_counter() - t0 > 120.0:  # a rank died: fail instead of hanging the node
+                raise RuntimeError(f"SharedRewards: timed out waiting for {what} (flags {self.flags[: self.world].tolist()}, consumed {int(self.flags[32])})")
+
     def learner_collect(self, step):
         """rank 0: wait until every rank has published `step`, return the (world * per_rank,) view."""
-        while int(self.flags[: self.world].min()) < step + 1:
-            pass
+        self._spin(lambda: int(self.flags[: self.world].min()) >= step + 1, f"step {step} of every rank")
         out = self.rewards[step % self.SLOTS].reshape(-1)
         self.flags[32] = step + 1
         return out
 
     def wait_for_slot(self, step):
         """any rank: the slot of `step` was last used by step - SLOTS; the learner must have consumed that one."""
-        while int(self.flags[32]) < step + 1 - self.SLOTS:
-            pass
+        self._spin(lambda: int(self.flags[32]) >= step + 1 - self.SLOTS, f"the learner to consume step {step - self.SLOTS}")
 
     def close(self):
         import torch

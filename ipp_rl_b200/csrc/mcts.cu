@@ -221,6 +221,17 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
         } else {
             child = edges[best_e].child;
         }
+        if (child != kNoNode) {
+            // a visited edge whose child exists: its action id was cached when the child was created, the child's header has the
+            // rest — no slot decode, no poses, no cost on the way down
+            if (lane == 0) {
+                a.path_edge[(size_t)t * d.max_path + len] = best_e;
+                a.path_action[(size_t)t * d.max_path + len] = edges[best_e].pad[0];
+            }
+            ++len;
+            node = child;
+            continue;
+        }
         // the chosen edge
         const Slot c = slot_cell(d, p, best_s, ccol, crow);
         double nx, ny, nh, ax, ay, ah;
@@ -233,7 +244,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             a.path_action[(size_t)t * d.max_path + len] = c.lvl * (p.X * p.Y) + p.X * c.col + c.row;
         }
         ++len;
-        if (child == kNoNode) {
+        {
             const int n_nodes = a.n_nodes[t];
             if (depth + 1 > d.H || !(child_budget > 0.0f) || n_nodes >= d.M) {
                 kind = IPP_MCTS_LEAF_TERMINAL;  // simulate() returns 0 before any node exists (mcts.py:175-176)
@@ -247,6 +258,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
                 hdr[n_nodes] = make_int4(pack_pos(c.col, c.row, c.lvl), __float_as_int(child_budget), 0, depth + 1);
                 a.bu[(size_t)t * d.M + n_nodes] = make_int2(-1, 0);
                 edges[best_e].child = n_nodes;
+                edges[best_e].pad[0] = c.lvl * (p.X * p.Y) + p.X * c.col + c.row;
                 a.n_nodes[t] = n_nodes + 1;
             }
             __syncwarp();
@@ -257,7 +269,6 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             kind = IPP_MCTS_LEAF_EVAL;
             break;
         }
-        node = child;
     }
     if (lane == 0) {
         for (int k = len; k < d.max_path; ++k) a.path_action[(size_t)t * d.max_path + k] = -1;

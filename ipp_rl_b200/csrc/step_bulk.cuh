@@ -99,10 +99,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 // 1-D bulk copy global -> shared (src / dst 16-byte aligned, bytes % 16 == 0), completion on an mbarrier
+// IPP_BULK_LDHINT (experiment switch): L2 eviction priority of the staged lines: 0 none, 1 evict_first, 2 evict_last.
+#ifndef IPP_BULK_LDHINT
+#define IPP_BULK_LDHINT 0
+#endif
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+#if IPP_BULK_LDHINT == 0
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
                  "r"(bar)
                  : "memory");
+#else
+    uint64_t pol;
+#if IPP_BULK_LDHINT == 1
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#else
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+#endif
 }
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
@@ -118,6 +134,34 @@ __device__ __forceinline__ float lds32(uint32_t a) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
+}
+
+// Write-back of a quad row.  IPP_BULK_ST selects the cache operator (experiment switch): 0 default (write-back), 1 .cs (streaming /
+// evict-first), 2 .wt (write-through), 3 .cg.  Measured at C3: see DESIGN.md 3.5.
+#ifndef IPP_BULK_ST
+#define IPP_BULK_ST 0
+#endif
+__device__ __forceinline__ void st_row4(unsigned char *p, float a, float b, float c, float d) {
+#if IPP_BULK_ST == 1
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(a, b, c, d));
+#elif IPP_BULK_ST == 2
+    __stwt(reinterpret_cast<float4 *>(p), make_float4(a, b, c, d));
+#elif IPP_BULK_ST == 3
+    __stcg(reinterpret_cast<float4 *>(p), make_float4(a, b, c, d));
+#else
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+#endif
+}
+__device__ __forceinline__ void st_row2(unsigned char *p, float a, float b) {
+#if IPP_BULK_ST == 1
+    __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b));
+#elif IPP_BULK_ST == 2
+    __stwt(reinterpret_cast<float2 *>(p), make_float2(a, b));
+#elif IPP_BULK_ST == 3
+    __stcg(reinterpret_cast<float2 *>(p), make_float2(a, b));
+#else
+    *reinterpret_cast<float2 *>(p) = make_float2(a, b);
+#endif
 }
 
 // staged ground truth of a footprint (super-tile runs in shared memory); (r, c) relative to the footprint's top-left cell
@@ -475,16 +519,16 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                 }
                 if (MODE != MODE_PREDICT || commit) {
                     if (odd) {
-                        *reinterpret_cast<float2 *>(go) = make_float2(mn[0], vn[0]);
-                        if (cok) *reinterpret_cast<float2 *>(go + dCg) = make_float2(mn[1], vn[1]);
-                        if (rok) *reinterpret_cast<float2 *>(go + dRg) = make_float2(mn[2], vn[2]);
-                        if (ok3) *reinterpret_cast<float2 *>(go + dRg + dCg) = make_float2(mn[3], vn[3]);
+                        st_row2(go, mn[0], vn[0]);
+                        if (cok) st_row2(go + dCg, mn[1], vn[1]);
+                        if (rok) st_row2(go + dRg, mn[2], vn[2]);
+                        if (ok3) st_row2(go + dRg + dCg, mn[3], vn[3]);
                     } else if (cok) {
-                        *reinterpret_cast<float4 *>(go) = make_float4(mn[0], vn[0], mn[1], vn[1]);
-                        if (rok) *reinterpret_cast<float4 *>(go + dRg) = make_float4(mn[2], vn[2], mn[3], vn[3]);
+                        st_row4(go, mn[0], vn[0], mn[1], vn[1]);
+                        if (rok) st_row4(go + dRg, mn[2], vn[2], mn[3], vn[3]);
                     } else {
-                        *reinterpret_cast<float2 *>(go) = make_float2(mn[0], vn[0]);
-                        if (rok) *reinterpret_cast<float2 *>(go + dRg) = make_float2(mn[2], vn[2]);
+                        st_row2(go, mn[0], vn[0]);
+                        if (rok) st_row2(go + dRg, mn[2], vn[2]);
                     }
                 }
             }

@@ -186,9 +186,10 @@ def test_batched_search_matches_oracle_on_a_deeper_problem():
         if np.array_equal(dense_n, o.Nsa[()]):
             exact += 1
             assert np.max(np.abs(dense_q - o.Qsa[()])) <= 2e-4 * max(1.0, np.abs(o.Qsa[()]).max())
-        else:  # an fp32-vs-fp64 near-tie may send a few simulations elsewhere; the bulk of the visits must agree
-            assert np.abs(dense_n - o.Nsa[()]).sum() <= 0.25 * dense_n.sum(), (t, np.abs(dense_n - o.Nsa[()]).sum())
-    assert exact >= T - 3, f"only {exact}/{T} trees reproduce the oracle's visit counts exactly"
+        else:  # an fp32-vs-fp64 near-tie may send ONE simulation elsewhere (sum |dN| = 2); anything more is a bug
+            assert np.abs(dense_n - o.Nsa[()]).sum() <= 2, (t, np.abs(dense_n - o.Nsa[()]).sum())
+    # measured on B200 (tools/mcts_gap_probe.py, three seeds, 60 trees): every tree reproduces the oracle's visit counts exactly
+    assert exact >= T - 1, f"only {exact}/{T} trees reproduce the oracle's visit counts exactly"
 
 
 def test_search_properties_at_scale():

@@ -28,7 +28,7 @@ K, W, POOL = 300, 10, 16
 stream = torch.cuda.Stream()
 for name, B, G, res, (amin, amax, asp), levels, mode, predict in CONFIGS:
     cfg = EngineConfig(batch=B, x_dim=G, y_dim=G, resolution=res, min_altitude=amin, max_altitude=amax, altitude_spacing=asp,
-                       layout=capi.LAYOUT_TILED, seed=1, stream=stream.cuda_stream)
+                       layout=capi.LAYOUT_SUPER, seed=1, stream=stream.cuda_stream)
     with BatchedEngine(cfg) as eng, torch.cuda.stream(stream):
         eng.reset(0.5, 1.82)
         eng.synth_ground_truth(seed=3)
@@ -47,6 +47,7 @@ for name, B, G, res, (amin, amax, asp), levels, mode, predict in CONFIGS:
             else:
                 eng.step_device(action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=rew.data_ptr(), reward_mode=mode)
 
+        la0, ll0 = eng.path_launches("async"), eng.path_launches("lsu")
         for t in range(W):
             go(t)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -61,5 +62,8 @@ for name, B, G, res, (amin, amax, asp), levels, mode, predict in CONFIGS:
         alg = (per_cell * float(sum(cells[t % POOL] for t in range(W, W + K))) / K + 16.0 * B)
         gbs = alg / (ms * 1e-3) / 1e9
         print(json.dumps({"config": name, "batch": B, "ms_per_step": ms, "env_steps_per_sec": B / (ms * 1e-3), "algorithmic_GB/s": gbs,
-                          "frac_of_hbm_peak": gbs / peak, "mean_cells": float(cells.mean() / B), "step_path": eng.step_path,
+                          "frac_of_hbm_peak": gbs / peak, "mean_cells": float(cells.mean() / B),
+                          # the kernel that actually ran (launch counters), not the engine's path option
+                          "kernel": ("ipp_step_bulk_kernel" + ("<MODE_PREDICT>" if predict else "")) if eng.path_launches("async") - la0 >= K
+                          else ("ipp_step_kernel" + ("<MODE_PREDICT>" if predict else "")) if eng.path_launches("lsu") - ll0 >= K else "mixed",
                           "state_bytes": eng.device_bytes}))
