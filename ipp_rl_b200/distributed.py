@@ -42,9 +42,24 @@ def sharded_config(cfg: EngineConfig, total_envs: int, world_size: int, rank: in
     return EngineConfig(**kw)
 
 
-def gather_rows(local, total_envs: int, group=None):
+_scratch = {}
+
+
+def _scratch_tensor(key, shape, dtype, device):
+    """Reused staging tensors of the uneven-split path (a trainer calls the gathers every step)."""
+    import torch
+
+    t = _scratch.get(key)
+    if t is None or t.shape != shape or t.dtype != dtype or t.device != device:
+        t = torch.zeros(shape, dtype=dtype, device=device)
+        _scratch[key] = t
+    return t
+
+
+def gather_rows(local, total_envs: int, group=None, out=None):
     """All-gather per-env rows of every rank into one (total_envs, ...) tensor ordered by global env id.  ``local`` is
-    this rank's torch tensor whose first dimension is its env slice (CUDA with the nccl backend, CPU with gloo)."""
+    this rank's torch tensor whose first dimension is its env slice (CUDA with the nccl backend, CPU with gloo); ``out``
+    (optional) receives the result — with it and an even split the call allocates nothing."""
     import torch
     import torch.distributed as dist
 
@@ -54,17 +69,24 @@ def gather_rows(local, total_envs: int, group=None):
     if local.shape[0] != mine:
         raise ValueError(f"local rows: {local.shape[0]}, this rank owns {mine} envs")
     tail = tuple(local.shape[1:])
-    if len(set(counts)) == 1:
+    if out is None:
         out = torch.empty((total_envs,) + tail, dtype=local.dtype, device=local.device)
+    elif tuple(out.shape) != (total_envs,) + tail or out.dtype != local.dtype:
+        raise ValueError("out must be (total_envs, ...) with the dtype of the local rows")
+    if len(set(counts)) == 1:
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
-    # uneven split: pad every shard to the largest one, gather, drop the padding
+    # uneven split: pad every shard to the largest one (reused staging), gather, copy the slices into place
     width = max(counts)
-    padded = torch.zeros((width,) + tail, dtype=local.dtype, device=local.device)
+    padded = _scratch_tensor(("pad", tail), (width,) + tail, local.dtype, local.device)
     padded[:mine] = local
-    out = torch.empty((world * width,) + tail, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded, group=group)
-    return torch.cat([out[r * width : r * width + c] for r, c in enumerate(counts)])
+    wide = _scratch_tensor(("wide", tail, world), (world * width,) + tail, local.dtype, local.device)
+    dist.all_gather_into_tensor(wide, padded, group=group)
+    first = 0
+    for r, c in enumerate(counts):
+        out[first : first + c] = wide[r * width : r * width + c]
+        first += c
+    return out
 
 
 def gather_rewards(local, total_envs: int, group=None):
