@@ -60,6 +60,12 @@ extern "C" {
                                touches in one tile row are ONE contiguous run of ~0.6-1.3 KB holding everything the fused
                                step reads: the persistent step kernel stages it with one cp.async.bulk (TMA) per tile row
                                and DRAM serves ~1 KB bursts instead of 128-byte lines.  Internal like IPP_LAYOUT_TILED. */
+#define IPP_LAYOUT_SPLIT 4  /* the super-tile cut in two arrays: var[B][tiles][16] (64 B per 4x4-cell tile) and
+                               {mean x 16 | gt x 16}[B][tiles] (128 B per tile, line aligned).  The fused step stages two
+                               runs per tile row (the same bytes as IPP_LAYOUT_SUPER); the covariance-only paths
+                               (simulate_prediction_step: ipp_predict, the tree search's rollouts) stage and write the
+                               variance run alone: 4 + 4 bytes per cell instead of dragging mean and ground truth along.
+                               Internal like IPP_LAYOUT_TILED. */
 
 /* ---- cost model (planning/common/actions.py:8-41) ---------------------------------------- */
 #define IPP_COST_DISTANCE 0    /* uav_specifications is None -> Euclidean distance */
@@ -275,8 +281,9 @@ int ipp_observe(ipp_engine *e, int32_t first_env, int32_t n_env, const double *p
                 uint32_t flags, float *out, int32_t out_is_device);
 
 /* ---- interop ----------------------------------------------------------------------------------- */
-#define IPP_PTR_MEAN 0   /* PLANES: float[B][Y][X];  MV: float2[B][Y][X] base (mean at .x);  TILED: float2 tiles */
-#define IPP_PTR_VAR 1    /* PLANES: float[B][Y][X];  MV / TILED: same base + 1 float (stride 2) */
+#define IPP_PTR_MEAN 0   /* PLANES: float[B][Y][X];  MV: float2[B][Y][X] base (mean at .x);  TILED / SUPER: float2 tiles;
+                            SPLIT: {mean x 16 | gt x 16} tiles */
+#define IPP_PTR_VAR 1    /* PLANES: float[B][Y][X];  MV / TILED / SUPER: same base + 1 float (stride 2);  SPLIT: float[16] tiles */
 #define IPP_PTR_GT 2
 #define IPP_PTR_REWARD 3 /* engine-owned float[batch] staging of the last host-API step */
 #define IPP_PTR_STREAM 4 /* the cudaStream_t the engine launches on */

@@ -8,6 +8,7 @@ from ._capi import (  # noqa: F401
     FLAG_ADAPTIVE,
     LAYOUT_MV,
     LAYOUT_PLANES,
+    LAYOUT_SPLIT,
     LAYOUT_SUPER,
     LAYOUT_TILED,
     REWARD_GAUSS_ENTROPY,

@@ -32,7 +32,8 @@ LAYOUT_PLANES = 0
 LAYOUT_MV = 1
 LAYOUT_TILED = 2
 LAYOUT_SUPER = 3
-LAYOUT_NAMES = {"planes": LAYOUT_PLANES, "mv": LAYOUT_MV, "tiled": LAYOUT_TILED, "super": LAYOUT_SUPER}
+LAYOUT_SPLIT = 4
+LAYOUT_NAMES = {"planes": LAYOUT_PLANES, "mv": LAYOUT_MV, "tiled": LAYOUT_TILED, "super": LAYOUT_SUPER, "split": LAYOUT_SPLIT}
 FIELD_HOTSPOT, FIELD_SPLIT = 1, 2
 COST_DISTANCE = 0
 COST_FLIGHT_TIME = 1

@@ -115,7 +115,7 @@ extern "C" int ipp_generate_field(ipp_engine *e, int32_t kind, int32_t cluster_r
         return ipp_internal_fail(e, IPP_ERR_INVALID, "ipp_generate_field: cluster_radius must be smaller than the grid");
     if (n_env == 0) return IPP_OK;
     cudaStream_t stream = ipp_internal_stream(e);
-    const int tiled = ipp_internal_layout(e) == IPP_LAYOUT_TILED || ipp_internal_layout(e) == IPP_LAYOUT_SUPER;
+    const int tiled = ipp_internal_layout(e) == IPP_LAYOUT_TILED || ipp_internal_layout(e) == IPP_LAYOUT_SUPER || ipp_internal_layout(e) == IPP_LAYOUT_SPLIT;
     field_kernel<<<n_env, kFieldThreads, 0, stream>>>(const_cast<float *>(p.gt) + (size_t)first_env * p.plane_gt, kind, cluster_radius, p.X, p.Y, p.plane_gt,
                                                       tiled ? p.txg : 0, p.ts_gt, p.gw_shift, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32),
                                                       p.env_id_offset + (uint32_t)first_env);

@@ -33,12 +33,13 @@ struct ipp_engine {
     size_t plane_gt = 0;  // cells per env in the ground-truth array (TILED: whole 8x4 tiles)
     int txm = 0, txg = 0, tiles_y = 0;
     int ts_mv = 0, ts_gt = 0, gw_shift = 0;  // tile strides of the belief [float2] / ground truth [float], log2 gt tile width
-    bool tiled() const { return cfg.layout == IPP_LAYOUT_TILED || cfg.layout == IPP_LAYOUT_SUPER; }
+    bool tiled() const { return cfg.layout == IPP_LAYOUT_TILED || cfg.layout == IPP_LAYOUT_SUPER || cfg.layout == IPP_LAYOUT_SPLIT; }
+    bool split() const { return cfg.layout == IPP_LAYOUT_SPLIT; }
     // HBM
-    float *d_mean = nullptr;  // PLANES: float[B*plane]; MV / TILED: float2[B*plane_mv]
-    float *d_var = nullptr;   // PLANES only
+    float *d_mean = nullptr;  // PLANES: float[B*plane]; MV / TILED / SUPER: float2[B*plane_mv]; SPLIT: {mean x 16 | gt x 16}[B*tiles]
+    float *d_var = nullptr;   // PLANES: float[B*plane]; SPLIT: float[B*tiles*16]
     float *d_gt = nullptr;
-    bool gt_aliases_mean = false;  // SUPER: d_gt points into d_mean's allocation
+    bool gt_aliases_mean = false;  // SUPER / SPLIT: d_gt points into d_mean's allocation
     double *d_prev = nullptr;  // [B][3]
     int *d_status = nullptr;  // device alias of h_status (mapped pinned host word: no copy needed to read it back)
     // staging for the host entry points
@@ -78,6 +79,8 @@ struct ipp_engine {
     bool bulk_ok = false;
     int bulk_warps = 0, bulk_ring = 0;
     size_t bulk_smem = 0;
+    int bulk_pwarps = 0, bulk_pring = 0;  // SPLIT: the covariance-only step (variance runs alone, more warps per CTA)
+    size_t bulk_psmem = 0;
     uint64_t bulk_predict_launches = 0;
     unsigned int *d_tickets = nullptr;
     int ticket_parity = 0;
@@ -142,7 +145,10 @@ __global__ void reset_kernel(float *mean, float *var, int layout, size_t plane, 
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const float pv = prior_var_env ? prior_var_env[i / plane] : prior_var;
         if (layout == IPP_LAYOUT_SUPER && (i % 24) >= 16) continue;  // the ground-truth third of a super-tile
-        if (layout != IPP_LAYOUT_PLANES) {
+        if (layout == IPP_LAYOUT_SPLIT) {  // i runs over the var array; the mean sits at tile * 32 + cell of the {mean | gt} array
+            mean[i + (i & ~(size_t)15)] = prior_mean;
+            var[i] = pv;
+        } else if (layout != IPP_LAYOUT_PLANES) {
             reinterpret_cast<float2 *>(mean)[i] = make_float2(prior_mean, pv);
         } else {
             mean[i] = prior_mean;
@@ -200,6 +206,25 @@ __global__ void tiled_pack_kernel(float2 *mv, const float *mean, const float *va
         if (mean) t.x = mean[i];
         if (var) t.y = var[i];
         *o = t;
+    }
+}
+// dense [n][Y][X] <-> IPP_LAYOUT_SPLIT: var[tile][16], {mean[16] | gt[16]}[tile]
+__global__ void split_unpack_kernel(const float *mg, const float *vr, float *mean, float *var, TiledDims d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t env = i / d.plane;
+        const int c = (int)(i - env * d.plane), R = c / d.X, C = c - R * d.X;
+        const int k = split_index(d.txm, R, C);
+        if (mean) mean[i] = mg[env * d.plane_gt + split_mean_of(k)];
+        if (var) var[i] = vr[env * d.plane_mv + k];
+    }
+}
+__global__ void split_pack_kernel(float *mg, float *vr, const float *mean, const float *var, TiledDims d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t env = i / d.plane;
+        const int c = (int)(i - env * d.plane), R = c / d.X, C = c - R * d.X;
+        const int k = split_index(d.txm, R, C);
+        if (mean) mg[env * d.plane_gt + split_mean_of(k)] = mean[i];
+        if (var) vr[env * d.plane_mv + k] = var[i];
     }
 }
 // to_tiled != 0: dense -> tiled, else tiled -> dense
@@ -306,19 +331,23 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, c
     __shared__ double smem[(kEvalThreads / 32) * 10];
     const int env = blockIdx.x;
     const size_t plane = d.plane;
-    const bool tiled = layout == IPP_LAYOUT_TILED || layout == IPP_LAYOUT_SUPER;
+    const bool split = layout == IPP_LAYOUT_SPLIT;
+    const bool tiled = layout == IPP_LAYOUT_TILED || layout == IPP_LAYOUT_SUPER || split;
+    const bool planar = layout == IPP_LAYOUT_PLANES || split;  // mean and var in separate arrays
     const float *g = gt + (size_t)env * d.plane_gt;
-    const float *m = mean + (size_t)env * d.plane_mv * (layout != IPP_LAYOUT_PLANES ? 2 : 1);
-    const float *v = layout != IPP_LAYOUT_PLANES ? m + 1 : var + (size_t)env * plane;
-    const int es = layout != IPP_LAYOUT_PLANES ? 2 : 1;
-    // cell i of the dense map -> offsets inside the env's belief / ground-truth arrays
+    const float *m = split ? mean + (size_t)env * d.plane_gt : mean + (size_t)env * d.plane_mv * (planar ? 1 : 2);
+    const float *v = planar ? var + (size_t)env * d.plane_mv : m + 1;
+    const int es = planar ? 1 : 2;
+    // cell i of the dense map -> offsets inside the env's belief / ground-truth arrays (SPLIT: the compact tile index; the mean
+    // array is addressed through mo())
     auto bi = [&](size_t i) -> size_t { return tiled ? tiled_mv_index_rt(d.txm, d.ts_mv, (int)(i / d.X), (int)(i % d.X)) : i; };
+    auto mo = [&](size_t b) -> size_t { return split ? b + (b & ~(size_t)15) : b * es; };
     auto gi_of = [&](size_t i) -> size_t { return tiled ? tiled_gt_index_rt(d.txg, d.ts_gt, d.gw_shift, (int)(i / d.X), (int)(i % d.X)) : i; };
 
     // pass 1: min(gt), min(mean), max(gt), sum(gt)
     double a[4] = {1e300, 1e300, -1e300, 0.0};
     for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
-        const double gi = g[gi_of(i)], mi = m[bi(i) * es];
+        const double gi = g[gi_of(i)], mi = m[mo(bi(i))];
         a[0] = fmin(a[0], gi);
         a[1] = fmin(a[1], mi);
         a[2] = fmax(a[2], gi);
@@ -334,7 +363,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, c
     double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
         const size_t b = bi(i);
-        const double gi = g[gi_of(i)], mi = m[b * es], vi = v[b * es];
+        const double gi = g[gi_of(i)], mi = m[mo(b)], vi = v[b * es];
         const double sq = (gi - mi) * (gi - mi);
         const double w = ((gi - mmin) / range) / wsum;
         const double ll = 0.5 * log(2.0 * 3.141592653589793 * vi) + sq / 2.0 * vi;  // (:44) multiplies by P_ii
@@ -517,29 +546,39 @@ static int setup_async(ipp_engine *e) {
 // bulk-copy persistent path (IPP_LAYOUT_SUPER)
 // ------------------------------------------------------------------------------------------------
 typedef void (*bulk_kernel_t)(const BulkParams);
-// bit 0: entropy reward, bit 1: adaptive mask, bit 2: extras (host noise / measurement read-back), bit 3: predict-only
+// bit 0: entropy reward, bit 1: adaptive mask, bit 2: extras (host noise / measurement read-back), bit 3: predict-only,
+// bit 4: IPP_LAYOUT_SPLIT (else IPP_LAYOUT_SUPER)
 template <int V>
 static bulk_kernel_t bulk_variant_t() {
-    return ipp_step_bulk_kernel<(V & 8) ? MODE_PREDICT : MODE_KALMAN, (V & 1) != 0, (V & 2) != 0, (V & 4) != 0 && (V & 8) == 0>;
+    return ipp_step_bulk_kernel<(V & 8) ? MODE_PREDICT : MODE_KALMAN, (V & 1) != 0, (V & 2) != 0, (V & 4) != 0 && (V & 8) == 0, (V & 16) != 0>;
 }
 static bulk_kernel_t bulk_variant(int v) {
-    static const bulk_kernel_t table[16] = {bulk_variant_t<0>(),  bulk_variant_t<1>(),  bulk_variant_t<2>(),  bulk_variant_t<3>(),
-                                            bulk_variant_t<4>(),  bulk_variant_t<5>(),  bulk_variant_t<6>(),  bulk_variant_t<7>(),
-                                            bulk_variant_t<8>(),  bulk_variant_t<9>(),  bulk_variant_t<10>(), bulk_variant_t<11>(),
-                                            bulk_variant_t<8>(),  bulk_variant_t<9>(),  bulk_variant_t<10>(), bulk_variant_t<11>()};
-    return table[v & 15];
+    static const bulk_kernel_t table[32] = {
+        bulk_variant_t<0>(),  bulk_variant_t<1>(),  bulk_variant_t<2>(),  bulk_variant_t<3>(),  bulk_variant_t<4>(),  bulk_variant_t<5>(),
+        bulk_variant_t<6>(),  bulk_variant_t<7>(),  bulk_variant_t<8>(),  bulk_variant_t<9>(),  bulk_variant_t<10>(), bulk_variant_t<11>(),
+        bulk_variant_t<8>(),  bulk_variant_t<9>(),  bulk_variant_t<10>(), bulk_variant_t<11>(), bulk_variant_t<16>(), bulk_variant_t<17>(),
+        bulk_variant_t<18>(), bulk_variant_t<19>(), bulk_variant_t<20>(), bulk_variant_t<21>(), bulk_variant_t<22>(), bulk_variant_t<23>(),
+        bulk_variant_t<24>(), bulk_variant_t<25>(), bulk_variant_t<26>(), bulk_variant_t<27>(), bulk_variant_t<24>(), bulk_variant_t<25>(),
+        bulk_variant_t<26>(), bulk_variant_t<27>()};
+    return table[v & 31];
 }
+// does this variant run the covariance-only configuration (variance runs alone)?
+static bool bulk_variance_only(int v) { return (v & 16) && (v & 8) && !(v & 2); }
 
 static int setup_bulk(ipp_engine *e) {
     const ipp_config &c = e->cfg;
     e->bulk_ok = false;
-    if (c.layout != IPP_LAYOUT_SUPER) return IPP_OK;
+    const bool split = c.layout == IPP_LAYOUT_SPLIT;
+    if (c.layout != IPP_LAYOUT_SUPER && !split) return IPP_OK;
     if (c.x_dim > 32767 || c.y_dim > 32767 || e->n_levels > 255) return IPP_OK;  // BulkPlan packs cell coordinates into 16 bits
-    int max_fp = 0;  // bytes of the largest staged footprint at its worst tile alignment
+    int max_fp = 0;  // bytes of the largest staged footprint at its worst tile alignment (192 bytes per tile in either layout)
+    int max_tiles = 0;
     for (int k = 0; k < e->n_levels; ++k) {
         const int fw = std::min(2 * e->lut[k].rx + 1, c.x_dim), fh = std::min(2 * e->lut[k].ry + 1, c.y_dim);
         if (fw > 255 || fh > 255) return IPP_OK;  // BulkPlan packs footprint sizes into 8 bits
         const int ntx = std::min(e->txm, (fw + 2) / 4 + 1), ntr = std::min(e->tiles_y, (fh + 2) / 4 + 1);
+        if (ntr > (split ? 16 : 32)) return IPP_OK;  // one lane per staged run
+        max_tiles = std::max(max_tiles, ntx * ntr);
         max_fp = std::max(max_fp, ntx * ntr * kSuperTileBytes);
         const int nqx = (fw + 1) / 2, nqy = (fh + 1) / 2;
         if ((long long)nqx * nqy * std::max(nqx, nqy) >= 32768) return IPP_OK;  // 16-bit magic division of quad indices
@@ -558,7 +597,18 @@ static int setup_bulk(ipp_engine *e) {
     e->bulk_warps = warps;
     e->bulk_ring = ring;
     e->bulk_smem = (size_t)warps * ((size_t)ring + per_warp_fixed) + per_cta;
-    for (int v = 0; v < 12; ++v)
+    if (split) {  // covariance-only step: 64 bytes per staged tile, up to kBulkPredictWarps warps
+        const int max_fpv = max_tiles * kSplitVarTileBytes;
+        int pw = kBulkPredictWarps;
+        if (const char *wenv = getenv("IPP_BULK_PREDICT_WARPS")) pw = std::max(1, std::min(kBulkPredictWarps, atoi(wenv)));
+        while (pw > 1 && avail / pw < per_warp_fixed + (size_t)max_fpv) --pw;
+        int pring = (int)((avail / pw - per_warp_fixed) / 16 * 16);
+        if (const char *renv = getenv("IPP_BULK_PREDICT_RING")) pring = std::max(max_fpv, std::min(pring, atoi(renv) / 16 * 16));
+        e->bulk_pwarps = pw;
+        e->bulk_pring = pring;
+        e->bulk_psmem = (size_t)pw * ((size_t)pring + per_warp_fixed) + per_cta;
+    }
+    for (int v = 0; v < 32; ++v)
         if (cudaFuncSetAttribute(bulk_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem) != cudaSuccess) {  // per function, not per engine
             cudaGetLastError();
             return IPP_OK;
@@ -568,17 +618,20 @@ static int setup_bulk(ipp_engine *e) {
 }
 
 static int launch_bulk(ipp_engine *e, const StepParams &p, bool predict) {
+    const int variant = (((p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY) ? 1 : 0) | ((p.flags & IPP_FLAG_ADAPTIVE) ? 2 : 0) |
+                        ((!predict && (p.noise != nullptr || p.z_out != nullptr)) ? 4 : 0) | (predict ? 8 : 0) |
+                        (e->cfg.layout == IPP_LAYOUT_SPLIT ? 16 : 0);
+    const bool vonly = bulk_variance_only(variant);
+    const int warps = vonly ? e->bulk_pwarps : e->bulk_warps;
     BulkParams bp;
     bp.base = p;
     bp.tickets = e->d_tickets;
     bp.parity = e->ticket_parity;
-    bp.warps = e->bulk_warps;
-    bp.ring_bytes = e->bulk_ring;
-    const int needed = (p.n_jobs + e->bulk_warps - 1) / e->bulk_warps;
+    bp.warps = warps;
+    bp.ring_bytes = vonly ? e->bulk_pring : e->bulk_ring;
+    const int needed = (p.n_jobs + warps - 1) / warps;
     const int grid = std::max(1, std::min(e->sm_count, needed));
-    const int variant = (((p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY) ? 1 : 0) | ((p.flags & IPP_FLAG_ADAPTIVE) ? 2 : 0) |
-                        ((!predict && (p.noise != nullptr || p.z_out != nullptr)) ? 4 : 0) | (predict ? 8 : 0);
-    bulk_variant(variant)<<<grid, e->bulk_warps * 32, e->bulk_smem, e->stream>>>(bp);
+    bulk_variant(variant)<<<grid, warps * 32, vonly ? e->bulk_psmem : e->bulk_smem, e->stream>>>(bp);
     e->ticket_parity ^= 1;
     e->launches++;
     e->path_launches[IPP_PATH_ASYNC]++;
@@ -631,7 +684,8 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
     if (!(cfg->resolution > 0)) return fail(nullptr, IPP_ERR_INVALID, "ipp_create: environment.resolution must be > 0");
     if (!(cfg->angle_x_deg > 0 && cfg->angle_x_deg < 180 && cfg->angle_y_deg > 0 && cfg->angle_y_deg < 180))
         return fail(nullptr, IPP_ERR_INVALID, "ipp_create: field_of_view angles must be in (0, 180)");
-    if (cfg->layout != IPP_LAYOUT_PLANES && cfg->layout != IPP_LAYOUT_MV && cfg->layout != IPP_LAYOUT_TILED && cfg->layout != IPP_LAYOUT_SUPER)
+    if (cfg->layout != IPP_LAYOUT_PLANES && cfg->layout != IPP_LAYOUT_MV && cfg->layout != IPP_LAYOUT_TILED && cfg->layout != IPP_LAYOUT_SUPER &&
+        cfg->layout != IPP_LAYOUT_SPLIT)
         return fail(nullptr, IPP_ERR_INVALID, "ipp_create: unknown layout %d", cfg->layout);
     if (cfg->cost_mode != IPP_COST_DISTANCE && cfg->cost_mode != IPP_COST_FLIGHT_TIME)
         return fail(nullptr, IPP_ERR_INVALID, "ipp_create: unknown cost_mode %d", cfg->cost_mode);
@@ -665,6 +719,14 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         e->ts_mv = 24;
         e->ts_gt = 48;
         e->gw_shift = 2;
+    } else if (cfg->layout == IPP_LAYOUT_SPLIT) {  // var[tiles][16] and {mean x 16 | gt x 16}[tiles]
+        e->txm = e->txg = (cfg->x_dim + 3) / 4;
+        e->tiles_y = (cfg->y_dim + 3) / 4;
+        e->plane_mv = (size_t)e->tiles_y * e->txm * 16;  // floats of the var array
+        e->plane_gt = (size_t)e->tiles_y * e->txm * 32;  // floats of the {mean | gt} array
+        e->ts_mv = 16;
+        e->ts_gt = 32;
+        e->gw_shift = 2;
     }
 
     auto bail = [&](int rc) {
@@ -694,7 +756,14 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         e->own_stream = true;
     }
     const size_t cells = e->plane_mv * (size_t)cfg->batch, cells_gt = e->plane_gt * (size_t)cfg->batch;
-    if (cfg->layout != IPP_LAYOUT_PLANES) {
+    if (cfg->layout == IPP_LAYOUT_SPLIT) {
+        if ((rc = dev_alloc(e, &e->d_mean, cells_gt)) != IPP_OK) return bail(rc);
+        if ((rc = dev_alloc(e, &e->d_var, cells)) != IPP_OK) return bail(rc);
+        e->d_gt = e->d_mean + 16;  // the ground-truth half of tile 0 (same allocation)
+        e->gt_aliases_mean = true;
+        cudaMemsetAsync(e->d_mean, 0, cells_gt * sizeof(float), e->stream);  // padding cells of partial tiles are staged: keep them finite
+        cudaMemsetAsync(e->d_var, 0, cells * sizeof(float), e->stream);
+    } else if (cfg->layout != IPP_LAYOUT_PLANES) {
         if ((rc = dev_alloc(e, &e->d_mean, 2 * cells)) != IPP_OK) return bail(rc);
     } else {
         if ((rc = dev_alloc(e, &e->d_mean, cells)) != IPP_OK) return bail(rc);
@@ -704,7 +773,7 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         e->d_gt = e->d_mean + 32;  // the ground-truth third of super-tile 0 (same allocation)
         e->gt_aliases_mean = true;
         cudaMemsetAsync(e->d_mean, 0, 2 * cells * sizeof(float), e->stream);
-    } else if ((rc = dev_alloc(e, &e->d_gt, cells_gt)) != IPP_OK)
+    } else if (cfg->layout != IPP_LAYOUT_SPLIT && (rc = dev_alloc(e, &e->d_gt, cells_gt)) != IPP_OK)
         return bail(rc);
     if (cfg->layout == IPP_LAYOUT_TILED) {  // padding cells of partial tiles are staged (never used): keep them finite
         cudaMemsetAsync(e->d_gt, 0, cells_gt * sizeof(float), e->stream);
@@ -861,7 +930,10 @@ __global__ void reset_shuffled_kernel(float *mean, float *var, int layout, size_
             box_muller(r[0], r[1], n0, n1);
             pv = fmaxf(level * (1.0f + spread * ((cell & 1) ? n1 : n0)), 1.0e-6f);
         }
-        if (layout != IPP_LAYOUT_PLANES) {
+        if (layout == IPP_LAYOUT_SPLIT) {
+            mean[i + (i & ~(size_t)15)] = prior_mean;
+            var[i] = pv;
+        } else if (layout != IPP_LAYOUT_PLANES) {
             reinterpret_cast<float2 *>(mean)[i] = make_float2(prior_mean, pv);
         } else {
             mean[i] = prior_mean;
@@ -976,7 +1048,10 @@ extern "C" int ipp_get_state(ipp_engine *e, float *mean, float *var, int32_t fir
             dm = mean ? e->d_scratch : nullptr;
             dv = var ? e->d_scratch + n : nullptr;
         }
-        if (e->tiled())
+        if (e->split())
+            split_unpack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(e->d_mean + (size_t)first_env * e->plane_gt,
+                                                                                     e->d_var + (size_t)first_env * e->plane_mv, dm, dv, tiled_dims(e), n);
+        else if (e->tiled())
             tiled_unpack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(
                 reinterpret_cast<const float2 *>(e->d_mean) + (size_t)first_env * e->plane_mv, dm, dv, tiled_dims(e), n);
         else
@@ -1014,7 +1089,10 @@ extern "C" int ipp_set_state(ipp_engine *e, const float *mean, const float *var,
                 dv = e->d_scratch + n;
             }
         }
-        if (e->tiled())
+        if (e->split())
+            split_pack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(e->d_mean + (size_t)first_env * e->plane_gt,
+                                                                                   e->d_var + (size_t)first_env * e->plane_mv, dm, dv, tiled_dims(e), n);
+        else if (e->tiled())
             tiled_pack_kernel<<<grid_for(n, 256, e->sm_count), 256, 0, e->stream>>>(
                 reinterpret_cast<float2 *>(e->d_mean) + (size_t)first_env * e->plane_mv, dm, dv, tiled_dims(e), n);
         else
@@ -1092,6 +1170,8 @@ static void launch_mode(ipp_engine *e, const StepParams &p) {
         ipp_step_kernel<IPP_LAYOUT_TILED, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
     else if (e->cfg.layout == IPP_LAYOUT_SUPER)
         ipp_step_kernel<IPP_LAYOUT_SUPER, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
+    else if (e->cfg.layout == IPP_LAYOUT_SPLIT)
+        ipp_step_kernel<IPP_LAYOUT_SPLIT, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
     else if (e->cfg.layout == IPP_LAYOUT_MV)
         ipp_step_kernel<IPP_LAYOUT_MV, MODE><<<blocks, kThreads, 0, e->stream>>>(p);
     else
@@ -1393,6 +1473,7 @@ extern "C" int ipp_rollout_device(ipp_engine *e, int32_t n_jobs, int32_t horizon
     const size_t smem = (size_t)kRolloutWarps * (horizon - 1) * cells * sizeof(float);
     void (*kern)(const RolloutParams) = e->cfg.layout == IPP_LAYOUT_TILED ? ipp_rollout_kernel<IPP_LAYOUT_TILED>
                                         : e->cfg.layout == IPP_LAYOUT_SUPER ? ipp_rollout_kernel<IPP_LAYOUT_SUPER>
+                                        : e->cfg.layout == IPP_LAYOUT_SPLIT ? ipp_rollout_kernel<IPP_LAYOUT_SPLIT>
                                         : e->cfg.layout == IPP_LAYOUT_MV  ? ipp_rollout_kernel<IPP_LAYOUT_MV>
                                                                           : ipp_rollout_kernel<IPP_LAYOUT_PLANES>;
     if (smem > 48 * 1024) {
@@ -1460,7 +1541,7 @@ extern "C" void *ipp_device_ptr(ipp_engine *e, int32_t which) {
     if (!e) return nullptr;
     switch (which) {
         case IPP_PTR_MEAN: return e->d_mean;
-        case IPP_PTR_VAR: return e->cfg.layout != IPP_LAYOUT_PLANES ? (void *)(e->d_mean + 1) : (void *)e->d_var;
+        case IPP_PTR_VAR: return (e->cfg.layout != IPP_LAYOUT_PLANES && e->cfg.layout != IPP_LAYOUT_SPLIT) ? (void *)(e->d_mean + 1) : (void *)e->d_var;
         case IPP_PTR_GT: return e->d_gt;
         case IPP_PTR_REWARD:
             if (ensure_job_buffers(e, (size_t)e->cfg.batch) != IPP_OK) return nullptr;

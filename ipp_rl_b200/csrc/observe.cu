@@ -55,12 +55,18 @@ __global__ void __launch_bounds__(kObsThreads) observe_kernel(const __grid_const
     const int X = p.X, Y = p.Y;
     const size_t N = (size_t)X * Y;
     const bool planes_layout = op.layout == IPP_LAYOUT_PLANES, tiled = op.layout == IPP_LAYOUT_TILED || op.layout == IPP_LAYOUT_SUPER;
-    const float *mean_pl = p.mean + (size_t)env * p.plane, *var_pl = p.var + (size_t)env * p.plane;
+    const bool split = op.layout == IPP_LAYOUT_SPLIT;
+    const float *mean_pl = p.mean + (size_t)env * (split ? p.plane_gt : p.plane), *var_pl = p.var + (size_t)env * p.plane;
     const float2 *mv = reinterpret_cast<const float2 *>(p.mean) + (size_t)env * p.plane;
     auto load = [&](size_t i, float &m, float &v) {
         if (planes_layout) {
             m = mean_pl[i];
             v = var_pl[i];
+        } else if (split) {
+            const int R = (int)(i / X), C = (int)(i - (size_t)R * X);
+            const int k = split_index(p.txm, R, C);
+            m = mean_pl[split_mean_of(k)];
+            v = var_pl[k];
         } else {
             const int R = (int)(i / X), C = (int)(i - (size_t)R * X);
             const float2 t = mv[tiled ? tiled_mv_index_rt(p.txm, p.ts_mv, R, C) : i];

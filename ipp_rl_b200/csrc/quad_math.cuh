@@ -39,8 +39,8 @@ struct StepParams {
     float *mean;
     float *var;
     const float *gt;
-    size_t plane;     // cells per env in the belief arrays (y_dim * x_dim; TILED: padded to whole 4x4 tiles)
-    size_t plane_gt;  // cells per env in the ground-truth array (TILED: padded to whole 8x4 tiles)
+    size_t plane;     // cells per env in the belief arrays (y_dim * x_dim; TILED: padded to whole 4x4 tiles; SPLIT: floats of the var array)
+    size_t plane_gt;  // cells per env in the ground-truth array (TILED: padded to whole 8x4 tiles; SPLIT: floats of the {mean | gt} array)
     int txm, txg;     // TILED / SUPER: tiles per tile-row of the belief (ceil(X/4)) and of the ground truth (ceil(X/8); SUPER: = txm)
     int ts_mv, ts_gt; // TILED / SUPER: tile stride of the belief [float2] (16 / 24) and of the ground truth [float] (32 / 48)
     int gw_shift;     // TILED / SUPER: log2 of the ground-truth tile width (3 / 2)
@@ -168,7 +168,13 @@ __device__ __forceinline__ int tiled_gt_index(int txg, int R, int C) { return ((
 constexpr int kSuperTileBytes = 192;
 __device__ __forceinline__ int super_mv_index(int tx, int R, int C) { return ((R >> 2) * tx + (C >> 2)) * 24 + ((R & 3) << 2) + (C & 3); }
 __device__ __forceinline__ int super_gt_index(int tx, int R, int C) { return ((R >> 2) * tx + (C >> 2)) * 48 + ((R & 3) << 2) + (C & 3); }
-// run-time forms for the streaming kernels (layout TILED or SUPER; strides from StepParams / TiledDims)
+// IPP_LAYOUT_SPLIT: the super-tile cut in two arrays over the same 4 x 4-cell tiling: var[tile][16] (64 B) and
+// {mean[16] | gt[16]}[tile] (128 B, line aligned).  One compact index i = tile * 16 + cell serves both: the variance sits at
+// var[i], the mean at meangt[i + (i & ~15)] (= tile * 32 + cell), the ground truth 16 floats behind the mean.
+constexpr int kSplitVarTileBytes = 64, kSplitMgTileBytes = 128;
+__device__ __forceinline__ int split_index(int tx, int R, int C) { return (((R >> 2) * tx + (C >> 2)) << 4) + ((R & 3) << 2) + (C & 3); }
+__device__ __forceinline__ int split_mean_of(int i) { return i + (i & ~15); }
+// run-time forms for the streaming kernels (layout TILED, SUPER or SPLIT; strides from StepParams / TiledDims)
 __device__ __forceinline__ size_t tiled_mv_index_rt(int txm, int ts_mv, int R, int C) {
     return (size_t)((R >> 2) * txm + (C >> 2)) * ts_mv + ((R & 3) << 2) + (C & 3);
 }
@@ -360,6 +366,12 @@ struct GtSuper {  // global memory, IPP_LAYOUT_SUPER; g points at the env's plan
     const float *g;
     int tx, yu, xl;
     __device__ __forceinline__ float at(int r, int c) const { return __ldg(g + super_gt_index(tx, yu + r, xl + c)); }
+};
+
+struct GtSplit {  // global memory, IPP_LAYOUT_SPLIT; g points at the env's {mean | gt} array + 16 floats
+    const float *g;
+    int tx, yu, xl;
+    __device__ __forceinline__ float at(int r, int c) const { return __ldg(g + split_mean_of(split_index(tx, yu + r, xl + c))); }
 };
 
 template <class G>

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kRolloutWarps * 32) ipp_rollout_kernel(const _
                 for (int c = 0; c < 4; ++c) {
                     if (!ok[c]) continue;
                     const int off = Belief<LAYOUT>::idx(p, R0 + (c >> 1), C0 + (c & 1));
-                    if (LAYOUT == IPP_LAYOUT_PLANES || !adaptive) {
+                    if (LAYOUT == IPP_LAYOUT_PLANES || LAYOUT == IPP_LAYOUT_SPLIT || !adaptive) {
                         v[c] = bel.load_var(off);
                         if (adaptive) m[c] = bel.load_mean(off);
                     } else {

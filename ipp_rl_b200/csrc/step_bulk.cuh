@@ -18,7 +18,12 @@
 // weights are formed exactly as make_tap_entry() forms them, so the result is bit-identical to the table path of the
 // general kernel.  Clipped non-square footprints (dsize quirk) take the table path.
 //
-//   grid = #SMs (persistent, 1 CTA / SM), block = up to 16 warps, dynamic smem ~ 227 KB
+// IPP_LAYOUT_SPLIT (template parameter SPLIT): the super-tile cut in two arrays, var[tile][16] and {mean[16] | gt[16]}[tile].
+// The full step stages two runs per tile row (lanes 0.. issue the variance runs, lanes 16.. the {mean | gt} runs: the same
+// bytes as one super-tile run); the covariance-only step (MODE_PREDICT without the adaptive mask) stages, reads and writes
+// the variance runs ALONE — a third of the bytes — and runs with more warps per CTA (no ground truth, few registers).
+//
+//   grid = #SMs (persistent, 1 CTA / SM), block = up to 16 warps (24 for the covariance-only step), dynamic smem ~ 227 KB
 //   smem = [warp] byte ring | [warp] plan ring | [warp] tap tables | [warp] mbarriers
 #pragma once
 #include "step_kernel.cuh"
@@ -43,7 +48,11 @@ namespace ipp {
 #ifndef IPP_BULK_ENDGAME_DEPTH
 #define IPP_BULK_ENDGAME_DEPTH 2  // in-flight footprints per warp once the chunks have shrunk to one ticket
 #endif
+#ifndef IPP_BULK_PREDICT_WARPS
+#define IPP_BULK_PREDICT_WARPS 24  // covariance-only step: <= 85 registers per thread
+#endif
 constexpr int kBulkMaxWarps = IPP_BULK_MAX_WARPS;
+constexpr int kBulkPredictWarps = IPP_BULK_PREDICT_WARPS;
 constexpr int kBulkDepth = IPP_BULK_DEPTH;
 constexpr int kBulkChunk = IPP_BULK_CHUNK;
 constexpr int kBulkPlanRing = 16;  // live plans per warp: <= kBulkDepth in flight + <= 3 queued + a fresh chunk of <= 8
@@ -66,9 +75,10 @@ struct __align__(16) BulkPlan {
     int dims;          // nx | ny << 8 | nqx << 16 | nqy << 24
     int tiles;         // ntx | ntr << 8 | lvl << 16 | flags << 24   (flags: 1 rf == 2, 2 analytic INTER_AREA taps, 4 unsupported,
                        //                                              8 analytic weights = the level's table entry)
-    unsigned src_lo;   // byte offset of the footprint's first super-tile from the start of the belief array (64 bit)
+    unsigned src_lo;   // byte offset of the footprint's first super-tile from the start of the belief array (64 bit); SPLIT: of its
+                       // first 64-byte tile from the start of the var array (the {mean | gt} array: twice that)
     unsigned src_hi;
-    int sizes;         // bytes per staged tile row | ntr << 16
+    int sizes;         // bytes per staged tile row (SPLIT: of the variance run) | ntr << 16
     int ring_off;      // byte offset of the staged footprint in the warp's ring
     int magic_x;       // floor(65536 / nqx) + 1
     int spare;
@@ -164,6 +174,18 @@ __device__ __forceinline__ void st_row2(unsigned char *p, float a, float b) {
 #endif
 }
 
+__device__ __forceinline__ void st_row1(unsigned char *p, float a) { *reinterpret_cast<float *>(p) = a; }
+
+// staged ground truth of a footprint, IPP_LAYOUT_SPLIT ({mean | gt} runs in shared memory)
+struct GtSplitShared {
+    uint32_t base;  // shared address of the staged {mean | gt} runs
+    int ntx, a, b;
+    __device__ __forceinline__ float at(int r, int c) const {
+        const int rr = b + r, cc = a + c;
+        return lds32(base + (uint32_t)(((rr >> 2) * ntx + (cc >> 2)) * kSplitMgTileBytes + 64 + ((rr & 3) << 4) + ((cc & 3) << 2)));
+    }
+};
+
 // staged ground truth of a footprint (super-tile runs in shared memory); (r, c) relative to the footprint's top-left cell
 struct GtSuperShared {
     uint32_t base;  // shared address of the slot
@@ -176,7 +198,7 @@ struct GtSuperShared {
 
 // Plan one env-step (one lane).  Also advances the env's stored previous action (when the step commits and KEEP_PREV is
 // off) and raises the status word for footprints the INTER_AREA path cannot serve.
-template <int MODE>
+template <int MODE, bool SPLIT>
 __device__ __forceinline__ void bulk_plan_env(const StepParams &p, bool quirk, bool write_prev, int job, BulkPlan *out) {
     if (job < 0) {
         out->job = -1;
@@ -215,18 +237,22 @@ __device__ __forceinline__ void bulk_plan_env(const StepParams &p, bool quirk, b
         ps[2] = L.alt;
     }
     if (flags & 4) *(volatile int *)p.status = 1;  // mapped host word, bit 0 is the only bit
-    const unsigned long long src = (unsigned long long)job * (p.plane * sizeof(float2)) +
-                                   (unsigned long long)((yu >> 2) * p.txm + (xl >> 2)) * kSuperTileBytes;
+    const int tile_bytes = SPLIT ? kSplitVarTileBytes : kSuperTileBytes;
+    const unsigned long long src = (unsigned long long)job * (p.plane * (SPLIT ? sizeof(float) : sizeof(float2))) +
+                                   (unsigned long long)((yu >> 2) * p.txm + (xl >> 2)) * tile_bytes;
     int4 *o = reinterpret_cast<int4 *>(out);
     o[0] = make_int4(job, xl | (yu << 16), nx | (ny << 8) | (nqx << 16) | (nqy << 24), ntx | (ntr << 8) | (lvl << 16) | (flags << 24));
-    o[1] = make_int4((int)(unsigned)(src & 0xffffffffull), (int)(unsigned)(src >> 32), (ntx * kSuperTileBytes) | (ntr << 16), 0);
+    o[1] = make_int4((int)(unsigned)(src & 0xffffffffull), (int)(unsigned)(src >> 32), (ntx * tile_bytes) | (ntr << 16), 0);
     o[2] = make_int4(magic_x, 0, __float_as_int(fast_rcp(cost + 1.0f)), out_r | (out_c << 8));
 }
 
 // MODE: MODE_KALMAN (full step) or MODE_PREDICT (covariance only: no ground truth, no noise; the staged run still carries
 // both).  ENTROPY / ADAPTIVE: reward variant and adaptive mask; EXTRAS: host-supplied noise and measurement read-back.
-template <int MODE, bool ENTROPY, bool ADAPTIVE, bool EXTRAS>
-__global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(const __grid_constant__ BulkParams bp) {
+template <int MODE, bool ENTROPY, bool ADAPTIVE, bool EXTRAS, bool SPLIT>
+__global__ void __launch_bounds__((MODE == MODE_PREDICT && SPLIT && !ADAPTIVE ? kBulkPredictWarps : kBulkMaxWarps) * 32, 1)
+    ipp_step_bulk_kernel(const __grid_constant__ BulkParams bp) {
+    // SPLIT: does this variant stage the {mean | gt} runs?  (the mask needs the mean, the measurement the ground truth)
+    constexpr bool kNeedMg = !SPLIT || MODE != MODE_PREDICT || ADAPTIVE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const StepParams &p = bp.base;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -262,8 +288,9 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
     const bool quirk = (p.flags & IPP_FLAG_NO_DSIZE_QUIRK) == 0;
     const bool commit = (p.flags & IPP_FLAG_NO_COMMIT) == 0;
     const bool write_prev = commit && (p.flags & IPP_FLAG_KEEP_PREV) == 0;
-    const int grow = p.txm * kSuperTileBytes;  // HBM tile-row stride [bytes]
-    unsigned char *plane0 = reinterpret_cast<unsigned char *>(p.mean);
+    const int grow = p.txm * (SPLIT ? kSplitVarTileBytes : kSuperTileBytes);  // HBM tile-row stride [bytes] (SPLIT: of the var array)
+    unsigned char *plane0 = reinterpret_cast<unsigned char *>(SPLIT ? p.var : p.mean);
+    unsigned char *plane_mg = reinterpret_cast<unsigned char *>(p.mean);  // SPLIT: the {mean | gt} array
 
     // ---- plan ring: [c_pos, f_pos) staged (in flight), [f_pos, q_tail) planned, not yet staged ------------------------
     int c_pos = 0, f_pos = 0, q_tail = 0;
@@ -279,7 +306,7 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
         if (pl->job >= 0) {
             const int4 b = *reinterpret_cast<const int4 *>(&pl->src_lo);
             const int row_bytes = b.z & 0xffff, ntr = b.z >> 16;
-            const int bytes = ntr * row_bytes;
+            const int bytes = ntr * row_bytes * ((SPLIT && kNeedMg) ? 3 : 1);
             int off = -1;
             if (n_if == 0)
                 off = 0;
@@ -297,9 +324,13 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
                 mbar_expect_tx(bar, (uint32_t)bytes);
                 pl->ring_off = off;
             }
+            const unsigned long long src0 = ((unsigned long long)(unsigned)b.y << 32) | (unsigned)b.x;
             if (lane < ntr) {
-                const unsigned char *src = plane0 + (((unsigned long long)(unsigned)b.y << 32) | (unsigned)b.x) + (size_t)lane * grow;
+                const unsigned char *src = plane0 + src0 + (size_t)lane * grow;
                 bulk_g2s(ring + (uint32_t)(off + lane * row_bytes), src, (uint32_t)row_bytes, bar);
+            } else if (SPLIT && kNeedMg && lane >= 16 && lane - 16 < ntr) {  // the {mean | gt} runs: twice the offsets and sizes
+                const unsigned char *src = plane_mg + 2 * src0 + (size_t)(lane - 16) * (2 * grow);
+                bulk_g2s(ring + (uint32_t)(off + ntr * row_bytes + (lane - 16) * 2 * row_bytes), src, (uint32_t)(2 * row_bytes), bar);
             }
             if (n_if == 0) r_head = off;
             r_tail = off + bytes;
@@ -393,144 +424,309 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
             const bool odd = (a4 & 1) != 0;  // warp-uniform: (c0, c0 + 1) do not share a 16-byte chunk
             const int nq = unsupported ? 0 : nqx * nqy;
             int it = 0;
+            if constexpr (SPLIT) {
+                // staged runs: [ntr x var run (srow bytes)] [ntr x {mean | gt} run (2 * srow bytes)]; the same geometry in HBM with
+                // the arrays' tile-row strides (grow, 2 * grow)
+                const int ntr_s = pb.z >> 16;
+                const uint32_t slot_m = slot + (uint32_t)(ntr_s * srow);
+                unsigned char *gbase_m = plane_mg + 2 * (((unsigned long long)(unsigned)pb.y << 32) | (unsigned)pb.x);
 #pragma unroll 1
-            for (int q = lane; q < nq; q += 32, ++it) {
-                const int qy = (int)(((uint32_t)q * magic_x) >> 16);
-                const int qx = q - qy * nqx;
-                // column part
-                const int c0 = 2 * qx;
-                const bool cok = c0 + 1 < nx;
-                const int cc = a4 + c0, ic = cc & 3;
-                const bool last_c = ic == 3;
-                const int col_s = (cc >> 2) * kSuperTileBytes + (ic << 3);        // {mean,var} of column c0 inside a tile row [bytes]
-                const int col_q = (cc >> 2) * kSuperTileBytes + 128 + (ic << 2);  // ground truth of column c0
-                const int dCg = last_c ? 168 : 8;                                 // to column c0 + 1 ({mean,var})
-                const int dC = cok ? dCg : 0;                                     // ... clamped inside the footprint
-                const int dCq = cok ? (last_c ? 180 : 4) : 0;                     // ... ground truth
-                // row part
-                const int r0 = 2 * qy;
-                const bool rok = r0 + 1 < ny;
-                const bool ok3 = cok && rok;
-                const int rr = b4 + r0, trl = rr >> 2, ir = rr & 3;
-                const bool last_r = ir == 3;
-                const int row_s = trl * srow;
-                const uint32_t so = slot + (uint32_t)(row_s + (ir << 5) + col_s);  // {mean,var} of cell (r0, c0), staged
-                unsigned char *go = gbase + (trl * grow + (ir << 5) + col_s);      // ... and in HBM
-                const int dRs = rok ? (last_r ? srow - 96 : 32) : 0;               // to the quad's second row (clamped inside the footprint)
-                const int dRg = last_r ? grow - 96 : 32;
+                for (int q = lane; q < nq; q += 32, ++it) {
+                    const int qy = (int)(((uint32_t)q * magic_x) >> 16);
+                    const int qx = q - qy * nqx;
+                    const int c0 = 2 * qx, r0 = 2 * qy;
+                    const bool cok = c0 + 1 < nx, rok = r0 + 1 < ny, ok3 = cok && rok;
+                    const int cc = a4 + c0, ic = cc & 3, tcx = cc >> 2;
+                    const int rr = b4 + r0, ir = rr & 3, trl = rr >> 2;
+                    const bool last_c = ic == 3, last_r = ir == 3;
+                    const int u = (ir << 4) + (ic << 2);                    // byte offset of cell (r0, c0) inside a 64-byte tile field
+                    const int tv = trl * srow + tcx * kSplitVarTileBytes + u;  // ... inside the staged variance runs
+                    const int dCv = last_c ? 52 : 4, dCm = last_c ? 116 : 4;   // to column c0 + 1 (next tile: 64 / 128 - 12)
+                    const int dRv = last_r ? srow - 48 : 16, dRm = last_r ? 2 * srow - 48 : 16;  // to row r0 + 1, staged
+                    const int dRgv = last_r ? grow - 48 : 16, dRgm = last_r ? 2 * grow - 48 : 16;  // ... in HBM
+                    const uint32_t sv = slot + (uint32_t)tv;
+                    const uint32_t sm = slot_m + (uint32_t)(2 * tv - u);    // mean of cell (r0, c0); its ground truth 64 bytes behind
 
-                float4 top, bot;
-                if (odd) {
-                    const float2 t0 = lds64(so), t1 = lds64(so + dC), b0 = lds64(so + dRs), b1 = lds64(so + dRs + dC);
-                    top = make_float4(t0.x, t0.y, t1.x, t1.y);
-                    bot = make_float4(b0.x, b0.y, b1.x, b1.y);
-                } else {
-                    top = lds128(so);
-                    bot = lds128(so + dRs);
-                }
-                const float m[4] = {top.x, cok ? top.z : 0.0f, rok ? bot.x : 0.0f, ok3 ? bot.z : 0.0f};
-                const float v[4] = {top.y, cok ? top.w : 0.0f, rok ? bot.y : 0.0f, ok3 ? bot.w : 0.0f};
-                const bool ok[4] = {true, cok, rok, ok3};
-
-                // ---- measurement --------------------------------------------------------------------------------
-                float z[4] = {0.f, 0.f, 0.f, 0.f};
-                if (MODE != MODE_PREDICT) {
-                    float eps[4];
-                    if (EXTRAS && p.noise != nullptr) {
-                        if (rf == 1) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) eps[k] = ok[k] ? __ldg(p.noise + nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)) : 0.0f;
-                        } else {
-                            eps[0] = __ldg(p.noise + nrow + q);
-                        }
-                    } else {
-                        draw_normals(p, rf, q, lane, it, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
-                    }
-                    const uint32_t gs = slot + (uint32_t)(row_s + (ir << 4) + col_q);  // gt of cell (r0, c0), staged
-                    const int dRq = rok ? (last_r ? srow - 48 : 16) : 0;
-                    if (rf == 1) {
-                        float gv[4];
+                    float v[4], m[4] = {0.f, 0.f, 0.f, 0.f};
+                    {
+                        const uint32_t sv1 = sv + (rok ? dRv : 0);
                         if (odd) {
-                            gv[0] = lds32(gs);
-                            gv[1] = lds32(gs + dCq);
-                            gv[2] = lds32(gs + dRq);
-                            gv[3] = lds32(gs + dRq + dCq);
+                            v[0] = lds32(sv);
+                            v[1] = cok ? lds32(sv + dCv) : 0.0f;
+                            v[2] = rok ? lds32(sv1) : 0.0f;
+                            v[3] = ok3 ? lds32(sv1 + dCv) : 0.0f;
                         } else {
-                            const float2 g0 = lds64(gs), g1 = lds64(gs + dRq);
-                            gv[0] = g0.x;
-                            gv[1] = g0.y;
-                            gv[2] = g1.x;
-                            gv[3] = g1.y;
+                            const float2 t = lds64(sv), b2 = lds64(sv1);
+                            v[0] = t.x;
+                            v[1] = cok ? t.y : 0.0f;
+                            v[2] = rok ? b2.x : 0.0f;
+                            v[3] = ok3 ? b2.y : 0.0f;
                         }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) z[k] = ok[k] ? __saturatef(fmaf(s2, eps[k], gv[k])) : 0.0f;
-                    } else if (analytic) {
-                        // rows {r0-1, r0, r0+1} x cols {c0-1, c0, c0+1}; taps with weight 0 are clamped onto the quad's own cells
-                        const int dU = qy > 0 ? ((ir == 0) ? -(srow - 48) : -16) : 0;
-                        const int dL = qx > 0 ? ((ic == 0) ? -180 : -4) : 0;  // to column c0 - 1 (ground truth), clamped
-                        const float wl = (float)qx * inv_nx, wr_ = (float)(nqx - 1 - qx) * inv_nx;
-                        const float wu = (float)qy * inv_ny, wb = (float)(nqy - 1 - qy) * inv_ny;
-                        float rs[3];
-                        const int dro[3] = {dU, 0, dRq};
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const uint32_t ra = gs + dro[k];
-                            float g0, g1;
-                            if (odd) {
-                                g0 = lds32(ra);
-                                g1 = lds32(ra + dCq);
-                            } else {
-                                const float2 t = lds64(ra);
-                                g0 = t.x;
-                                g1 = t.y;
-                            }
-                            const float gl = lds32(ra + dL);
-                            rs[k] = fmaf(wr_, g1, fmaf(wmid_x, g0, wl * gl));
-                        }
-                        float d = fmaf(wu, rs[0], 0.0f);
-                        d = fmaf(wmid_y, rs[1], d);
-                        d = fmaf(wb, rs[2], d);
-                        z[0] = __saturatef(fmaf(s2, eps[0], d));
-                    } else {
-                        const int pr = fdiv(q, out_c, inv_outc), pcc = q - pr * out_c;
-                        const float d = downsample(tap_mode, GtSuperShared{slot, ntx, a4, b4}, tapv, pr, pcc, ny, nx, pc.w & 255, out_c);
-                        z[0] = __saturatef(fmaf(s2, eps[0], d));
                     }
-                    if (EXTRAS && p.z_out != nullptr) {
-                        if (rf == 1) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (ok[k]) p.z_out[nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)] = z[k];
+                    if (kNeedMg) {
+                        const uint32_t sm1 = sm + (rok ? dRm : 0);
+                        if (odd) {
+                            m[0] = lds32(sm);
+                            m[1] = cok ? lds32(sm + dCm) : 0.0f;
+                            m[2] = rok ? lds32(sm1) : 0.0f;
+                            m[3] = ok3 ? lds32(sm1 + dCm) : 0.0f;
                         } else {
-                            p.z_out[nrow + q] = z[0];
+                            const float2 t = lds64(sm), b2 = lds64(sm1);
+                            m[0] = t.x;
+                            m[1] = cok ? t.y : 0.0f;
+                            m[2] = rok ? b2.x : 0.0f;
+                            m[3] = ok3 ? b2.y : 0.0f;
+                        }
+                    }
+                    const bool ok[4] = {true, cok, rok, ok3};
+
+                    // ---- measurement ----------------------------------------------------------------------------
+                    float z[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (MODE != MODE_PREDICT) {
+                        float eps[4];
+                        if (EXTRAS && p.noise != nullptr) {
+                            if (rf == 1) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) eps[k] = ok[k] ? __ldg(p.noise + nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)) : 0.0f;
+                            } else {
+                                eps[0] = __ldg(p.noise + nrow + q);
+                            }
+                        } else {
+                            draw_normals(p, rf, q, lane, it, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
+                        }
+                        const uint32_t gs = sm + 64u;  // gt of cell (r0, c0), staged
+                        const int dCq = cok ? dCm : 0, dRq = rok ? dRm : 0;
+                        if (rf == 1) {
+                            float gv[4];
+                            if (odd) {
+                                gv[0] = lds32(gs);
+                                gv[1] = lds32(gs + dCq);
+                                gv[2] = lds32(gs + dRq);
+                                gv[3] = lds32(gs + dRq + dCq);
+                            } else {
+                                const float2 g0 = lds64(gs), g1 = lds64(gs + dRq);
+                                gv[0] = g0.x;
+                                gv[1] = g0.y;
+                                gv[2] = g1.x;
+                                gv[3] = g1.y;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) z[k] = ok[k] ? __saturatef(fmaf(s2, eps[k], gv[k])) : 0.0f;
+                        } else if (analytic) {
+                            // rows {r0-1, r0, r0+1} x cols {c0-1, c0, c0+1}; taps with weight 0 are clamped onto the quad's own cells
+                            const int dU = qy > 0 ? ((ir == 0) ? -(2 * srow - 48) : -16) : 0;
+                            const int dL = qx > 0 ? ((ic == 0) ? -116 : -4) : 0;
+                            const float wl = (float)qx * inv_nx, wr_ = (float)(nqx - 1 - qx) * inv_nx;
+                            const float wu = (float)qy * inv_ny, wb = (float)(nqy - 1 - qy) * inv_ny;
+                            float rs[3];
+                            const int dro[3] = {dU, 0, dRq};
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const uint32_t ra = gs + dro[k];
+                                float g0, g1;
+                                if (odd) {
+                                    g0 = lds32(ra);
+                                    g1 = lds32(ra + dCq);
+                                } else {
+                                    const float2 t = lds64(ra);
+                                    g0 = t.x;
+                                    g1 = t.y;
+                                }
+                                const float gl = lds32(ra + dL);
+                                rs[k] = fmaf(wr_, g1, fmaf(wmid_x, g0, wl * gl));
+                            }
+                            float d = fmaf(wu, rs[0], 0.0f);
+                            d = fmaf(wmid_y, rs[1], d);
+                            d = fmaf(wb, rs[2], d);
+                            z[0] = __saturatef(fmaf(s2, eps[0], d));
+                        } else {
+                            const int pr = fdiv(q, out_c, inv_outc), pcc = q - pr * out_c;
+                            const float d = downsample(tap_mode, GtSplitShared{slot_m, ntx, a4, b4}, tapv, pr, pcc, ny, nx, pc.w & 255, out_c);
+                            z[0] = __saturatef(fmaf(s2, eps[0], d));
+                        }
+                        if (EXTRAS && p.z_out != nullptr) {
+                            if (rf == 1) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (ok[k]) p.z_out[nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)] = z[k];
+                            } else {
+                                p.z_out[nrow + q] = z[0];
+                            }
+                        }
+                    }
+
+                    // ---- fusion + reward, results straight to HBM --------------------------------------------------
+                    float mn[4], vn[4];
+                    bool msk[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) msk[k] = ok[k] && (!ADAPTIVE || (fmaf(p.kappa, v[k], m[k]) >= p.thr));
+                    acc += kalman_quad<ENTROPY, ADAPTIVE>(fc, cok, rok, m, v, z, msk, mn, vn);
+                    if (MODE != MODE_PREDICT || commit) {
+                        unsigned char *gv_ = gbase + (trl * grow + tcx * kSplitVarTileBytes + u);
+                        if (odd || !cok) {
+                            st_row1(gv_, vn[0]);
+                            if (cok) st_row1(gv_ + dCv, vn[1]);
+                            if (rok) st_row1(gv_ + dRgv, vn[2]);
+                            if (ok3) st_row1(gv_ + dRgv + dCv, vn[3]);
+                        } else {
+                            st_row2(gv_, vn[0], vn[1]);
+                            if (rok) st_row2(gv_ + dRgv, vn[2], vn[3]);
+                        }
+                        if (MODE != MODE_PREDICT) {
+                            unsigned char *gm_ = gbase_m + (trl * 2 * grow + tcx * kSplitMgTileBytes + u);
+                            if (odd || !cok) {
+                                st_row1(gm_, mn[0]);
+                                if (cok) st_row1(gm_ + dCm, mn[1]);
+                                if (rok) st_row1(gm_ + dRgm, mn[2]);
+                                if (ok3) st_row1(gm_ + dRgm + dCm, mn[3]);
+                            } else {
+                                st_row2(gm_, mn[0], mn[1]);
+                                if (rok) st_row2(gm_ + dRgm, mn[2], mn[3]);
+                            }
+                        }
+                    }
+                }
+            } else {
+    #pragma unroll 1
+                for (int q = lane; q < nq; q += 32, ++it) {
+                    const int qy = (int)(((uint32_t)q * magic_x) >> 16);
+                    const int qx = q - qy * nqx;
+                    // column part
+                    const int c0 = 2 * qx;
+                    const bool cok = c0 + 1 < nx;
+                    const int cc = a4 + c0, ic = cc & 3;
+                    const bool last_c = ic == 3;
+                    const int col_s = (cc >> 2) * kSuperTileBytes + (ic << 3);        // {mean,var} of column c0 inside a tile row [bytes]
+                    const int col_q = (cc >> 2) * kSuperTileBytes + 128 + (ic << 2);  // ground truth of column c0
+                    const int dCg = last_c ? 168 : 8;                                 // to column c0 + 1 ({mean,var})
+                    const int dC = cok ? dCg : 0;                                     // ... clamped inside the footprint
+                    const int dCq = cok ? (last_c ? 180 : 4) : 0;                     // ... ground truth
+                    // row part
+                    const int r0 = 2 * qy;
+                    const bool rok = r0 + 1 < ny;
+                    const bool ok3 = cok && rok;
+                    const int rr = b4 + r0, trl = rr >> 2, ir = rr & 3;
+                    const bool last_r = ir == 3;
+                    const int row_s = trl * srow;
+                    const uint32_t so = slot + (uint32_t)(row_s + (ir << 5) + col_s);  // {mean,var} of cell (r0, c0), staged
+                    unsigned char *go = gbase + (trl * grow + (ir << 5) + col_s);      // ... and in HBM
+                    const int dRs = rok ? (last_r ? srow - 96 : 32) : 0;               // to the quad's second row (clamped inside the footprint)
+                    const int dRg = last_r ? grow - 96 : 32;
+
+                    float4 top, bot;
+                    if (odd) {
+                        const float2 t0 = lds64(so), t1 = lds64(so + dC), b0 = lds64(so + dRs), b1 = lds64(so + dRs + dC);
+                        top = make_float4(t0.x, t0.y, t1.x, t1.y);
+                        bot = make_float4(b0.x, b0.y, b1.x, b1.y);
+                    } else {
+                        top = lds128(so);
+                        bot = lds128(so + dRs);
+                    }
+                    const float m[4] = {top.x, cok ? top.z : 0.0f, rok ? bot.x : 0.0f, ok3 ? bot.z : 0.0f};
+                    const float v[4] = {top.y, cok ? top.w : 0.0f, rok ? bot.y : 0.0f, ok3 ? bot.w : 0.0f};
+                    const bool ok[4] = {true, cok, rok, ok3};
+
+                    // ---- measurement --------------------------------------------------------------------------------
+                    float z[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (MODE != MODE_PREDICT) {
+                        float eps[4];
+                        if (EXTRAS && p.noise != nullptr) {
+                            if (rf == 1) {
+    #pragma unroll
+                                for (int k = 0; k < 4; ++k) eps[k] = ok[k] ? __ldg(p.noise + nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)) : 0.0f;
+                            } else {
+                                eps[0] = __ldg(p.noise + nrow + q);
+                            }
+                        } else {
+                            draw_normals(p, rf, q, lane, it, (uint32_t)job + p.env_id_offset, nrm_cache, eps);
+                        }
+                        const uint32_t gs = slot + (uint32_t)(row_s + (ir << 4) + col_q);  // gt of cell (r0, c0), staged
+                        const int dRq = rok ? (last_r ? srow - 48 : 16) : 0;
+                        if (rf == 1) {
+                            float gv[4];
+                            if (odd) {
+                                gv[0] = lds32(gs);
+                                gv[1] = lds32(gs + dCq);
+                                gv[2] = lds32(gs + dRq);
+                                gv[3] = lds32(gs + dRq + dCq);
+                            } else {
+                                const float2 g0 = lds64(gs), g1 = lds64(gs + dRq);
+                                gv[0] = g0.x;
+                                gv[1] = g0.y;
+                                gv[2] = g1.x;
+                                gv[3] = g1.y;
+                            }
+    #pragma unroll
+                            for (int k = 0; k < 4; ++k) z[k] = ok[k] ? __saturatef(fmaf(s2, eps[k], gv[k])) : 0.0f;
+                        } else if (analytic) {
+                            // rows {r0-1, r0, r0+1} x cols {c0-1, c0, c0+1}; taps with weight 0 are clamped onto the quad's own cells
+                            const int dU = qy > 0 ? ((ir == 0) ? -(srow - 48) : -16) : 0;
+                            const int dL = qx > 0 ? ((ic == 0) ? -180 : -4) : 0;  // to column c0 - 1 (ground truth), clamped
+                            const float wl = (float)qx * inv_nx, wr_ = (float)(nqx - 1 - qx) * inv_nx;
+                            const float wu = (float)qy * inv_ny, wb = (float)(nqy - 1 - qy) * inv_ny;
+                            float rs[3];
+                            const int dro[3] = {dU, 0, dRq};
+    #pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const uint32_t ra = gs + dro[k];
+                                float g0, g1;
+                                if (odd) {
+                                    g0 = lds32(ra);
+                                    g1 = lds32(ra + dCq);
+                                } else {
+                                    const float2 t = lds64(ra);
+                                    g0 = t.x;
+                                    g1 = t.y;
+                                }
+                                const float gl = lds32(ra + dL);
+                                rs[k] = fmaf(wr_, g1, fmaf(wmid_x, g0, wl * gl));
+                            }
+                            float d = fmaf(wu, rs[0], 0.0f);
+                            d = fmaf(wmid_y, rs[1], d);
+                            d = fmaf(wb, rs[2], d);
+                            z[0] = __saturatef(fmaf(s2, eps[0], d));
+                        } else {
+                            const int pr = fdiv(q, out_c, inv_outc), pcc = q - pr * out_c;
+                            const float d = downsample(tap_mode, GtSuperShared{slot, ntx, a4, b4}, tapv, pr, pcc, ny, nx, pc.w & 255, out_c);
+                            z[0] = __saturatef(fmaf(s2, eps[0], d));
+                        }
+                        if (EXTRAS && p.z_out != nullptr) {
+                            if (rf == 1) {
+    #pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (ok[k]) p.z_out[nrow + (r0 + (k >> 1)) * nx + c0 + (k & 1)] = z[k];
+                            } else {
+                                p.z_out[nrow + q] = z[0];
+                            }
+                        }
+                    }
+
+                    // ---- fusion + reward, results straight to HBM ------------------------------------------------------
+                    float mn[4], vn[4];
+                    bool msk[4];
+    #pragma unroll
+                    for (int k = 0; k < 4; ++k) msk[k] = ok[k] && (!ADAPTIVE || (fmaf(p.kappa, v[k], m[k]) >= p.thr));
+                    acc += kalman_quad<ENTROPY, ADAPTIVE>(fc, cok, rok, m, v, z, msk, mn, vn);
+                    if (MODE == MODE_PREDICT) {  // covariance only: the mean goes back as it came
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) mn[k] = m[k];
+                    }
+                    if (MODE != MODE_PREDICT || commit) {
+                        if (odd) {
+                            st_row2(go, mn[0], vn[0]);
+                            if (cok) st_row2(go + dCg, mn[1], vn[1]);
+                            if (rok) st_row2(go + dRg, mn[2], vn[2]);
+                            if (ok3) st_row2(go + dRg + dCg, mn[3], vn[3]);
+                        } else if (cok) {
+                            st_row4(go, mn[0], vn[0], mn[1], vn[1]);
+                            if (rok) st_row4(go + dRg, mn[2], vn[2], mn[3], vn[3]);
+                        } else {
+                            st_row2(go, mn[0], vn[0]);
+                            if (rok) st_row2(go + dRg, mn[2], vn[2]);
                         }
                     }
                 }
 
-                // ---- fusion + reward, results straight to HBM ------------------------------------------------------
-                float mn[4], vn[4];
-                bool msk[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) msk[k] = ok[k] && (!ADAPTIVE || (fmaf(p.kappa, v[k], m[k]) >= p.thr));
-                acc += kalman_quad<ENTROPY, ADAPTIVE>(fc, cok, rok, m, v, z, msk, mn, vn);
-                if (MODE == MODE_PREDICT) {  // covariance only: the mean goes back as it came
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) mn[k] = m[k];
-                }
-                if (MODE != MODE_PREDICT || commit) {
-                    if (odd) {
-                        st_row2(go, mn[0], vn[0]);
-                        if (cok) st_row2(go + dCg, mn[1], vn[1]);
-                        if (rok) st_row2(go + dRg, mn[2], vn[2]);
-                        if (ok3) st_row2(go + dRg + dCg, mn[3], vn[3]);
-                    } else if (cok) {
-                        st_row4(go, mn[0], vn[0], mn[1], vn[1]);
-                        if (rok) st_row4(go + dRg, mn[2], vn[2], mn[3], vn[3]);
-                    } else {
-                        st_row2(go, mn[0], vn[0]);
-                        if (rok) st_row2(go + dRg, mn[2], vn[2]);
-                    }
-                }
             }
 
             // per-env information gain: fp32 partials per lane, fp32 tree across the warp; the cost term comes from the plan
@@ -554,7 +750,7 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) ipp_step_bulk_kernel(co
             if (chunk_base < (unsigned)n_jobs) {
                 if (lane < req) {
                     const unsigned int t = chunk_base + (unsigned)lane;
-                    bulk_plan_env<MODE>(p, quirk, write_prev, t < (unsigned)n_jobs ? (int)t : -1, plans + ((q_tail + lane) & (kBulkPlanRing - 1)));
+                    bulk_plan_env<MODE, SPLIT>(p, quirk, write_prev, t < (unsigned)n_jobs ? (int)t : -1, plans + ((q_tail + lane) & (kBulkPlanRing - 1)));
                 }
                 q_tail = (q_tail + req) & (kBulkPlanRing - 1);
                 n_wait += req;

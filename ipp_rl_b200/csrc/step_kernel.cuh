@@ -68,6 +68,26 @@ struct Belief<IPP_LAYOUT_PLANES> {
     __device__ __forceinline__ void store_var(int i, float var) const { v[i] = var; }
 };
 
+// IPP_LAYOUT_SPLIT: var[tile][16] and {mean[16] | gt[16]}[tile] (quad_math.cuh); i = the compact tile index
+template <>
+struct Belief<IPP_LAYOUT_SPLIT> {
+    float *m, *v;
+    __device__ __forceinline__ Belief(const StepParams &p, size_t env) : m(p.mean + env * p.plane_gt), v(p.var + env * p.plane) {}
+    static __device__ __forceinline__ int idx(const StepParams &p, int R, int C) { return split_index(p.txm, R, C); }
+    static __device__ __forceinline__ int gidx(const StepParams &p, int R, int C) { return split_mean_of(split_index(p.txm, R, C)); }
+    __device__ __forceinline__ void load(int i, float &mean, float &var) const {
+        mean = __ldcg(m + split_mean_of(i));
+        var = __ldcg(v + i);
+    }
+    __device__ __forceinline__ float load_mean(int i) const { return __ldcg(m + split_mean_of(i)); }
+    __device__ __forceinline__ float load_var(int i) const { return __ldcg(v + i); }
+    __device__ __forceinline__ void store(int i, float mean, float var) const {
+        m[split_mean_of(i)] = mean;
+        v[i] = var;
+    }
+    __device__ __forceinline__ void store_mean(int i, float mean) const { m[split_mean_of(i)] = mean; }
+    __device__ __forceinline__ void store_var(int i, float var) const { v[i] = var; }
+};
 
 template <int LAYOUT, int MODE>
 __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constant__ StepParams p) {
@@ -182,6 +202,8 @@ __global__ void __launch_bounds__(kThreads) ipp_step_kernel(const __grid_constan
                         d = downsample(tap_mode, GtTiled{gt, p.txg, g.yu, g.xl}, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
                     else if (LAYOUT == IPP_LAYOUT_SUPER)
                         d = downsample(tap_mode, GtSuper{gt, p.txm, g.yu, g.xl}, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
+                    else if (LAYOUT == IPP_LAYOUT_SPLIT)
+                        d = downsample(tap_mode, GtSplit{gt, p.txm, g.yu, g.xl}, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
                     else
                         d = downsample(tap_mode, GtRowMajor{gt + g.yu * p.X + g.xl, p.X}, tapv, pr, pc, g.ny, g.nx, out_r, out_c);
                     z[0] = __saturatef(fmaf(g.s2, eps[0], d));

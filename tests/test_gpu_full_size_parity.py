@@ -37,7 +37,7 @@ def _engine(params, batch, **kw):
     return BatchedEngine(engine_cfg(params, batch, **kw))
 
 
-@pytest.mark.parametrize("size,layout", [("C3", 3), ("C3", 2), ("C5", 3), ("C2", 3), ("C2", 2)])
+@pytest.mark.parametrize("size,layout", [("C3", 3), ("C3", 4), ("C3", 2), ("C5", 3), ("C5", 4), ("C2", 3), ("C2", 4), ("C2", 2)])
 def test_full_batch_values_vs_oracle_and_lsu(size, layout):
     import torch
 
@@ -107,7 +107,7 @@ def test_full_batch_values_vs_oracle_and_lsu(size, layout):
         assert np.array_equal(fast.get_prev_pose(), ref.get_prev_pose())
 
 
-@pytest.mark.parametrize("layout", [3, 2])
+@pytest.mark.parametrize("layout", [3, 4, 2])
 def test_full_batch_predict_vs_oracle_and_lsu(layout):
     """The persistent predict-only path (whole batch, action ids) at C3 size against the LSU kernel (bit-identical) and the
     oracle's simulate_prediction_step on sampled envs; NO_COMMIT leaves the belief untouched."""
@@ -135,7 +135,7 @@ def test_full_batch_predict_vs_oracle_and_lsu(layout):
             prev = fast.get_prev_pose()[sample]
             la = fast.path_launches("async")
             r_fast = fast.predict(ids, commit=commit, reward_mode=mode, adaptive=adaptive).copy()
-            if layout == 3:
+            if layout in (3, 4):
                 assert fast.path_launches("async") == la + 1, "whole-batch prediction steps must take the persistent path"
             r_ref = ref.predict(ids, commit=commit, reward_mode=mode, adaptive=adaptive).copy()
             assert np.array_equal(r_fast, r_ref), (t, int(np.sum(r_fast != r_ref)))

@@ -23,7 +23,7 @@ def _engine(params, batch, **kw):
     return BatchedEngine(engine_cfg(params, batch, **kw))
 
 
-@pytest.mark.parametrize("layout", [0, 1, 2, 3])
+@pytest.mark.parametrize("layout", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("adaptive,reward_mode", [(False, 0), (True, 0), (False, 1)])
 def test_rollout_matches_chained_oracle_steps(layout, adaptive, reward_mode):
     X, Y = 27, 27  # square: the reference's action-id formula collides on non-square grids (oracle.enumerate_actions)
@@ -86,7 +86,7 @@ def _dense_stub_evaluator(mcts, root_prev, budget0, num_actions, res, altitudes)
 
 
 @pytest.mark.parametrize("case", ["A", "B", "C"])
-@pytest.mark.parametrize("layout", [1, 2, 3])
+@pytest.mark.parametrize("layout", [1, 2, 3, 4])
 def test_batched_search_reproduces_the_reference_mcts(case, layout):
     """Root statistics of the REAL reference MCTS (golden_mcts.npz) from the GPU search, three identical trees."""
     from ipp_rl_b200.planning.mcts_zero import BatchedMCTS

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 ATOL = 1e-5
 RTOL = 1e-5
-LAYOUTS = [0, 1, 2, 3]  # planes, {mean,var} row-major, 128-byte tiles, 192-byte super-tiles
+LAYOUTS = [0, 1, 2, 3, 4]  # planes, {mean,var} row-major, 128-byte tiles, 192-byte super-tiles, split var / {mean | gt} tiles
 
 
 def _engine(params, batch, **kw):
@@ -445,7 +445,7 @@ def test_invalid_action_ids_are_reported():
     from ipp_rl_b200._capi import IPP_ERR_INVALID, IppError
 
     params = make_params(24, 24, 1.0, 8, 20, 6)
-    for layout in (1, 3):
+    for layout in (1, 3, 4):
         with _engine(params, 8, layout=layout) as eng:
             eng.reset(0.5, 1.82)
             ids = np.arange(8, dtype=np.int32)

@@ -34,7 +34,7 @@ def test_persistent_paths_are_bit_identical_to_lsu_path(grid, reward_mode, adapt
     var0 = rng.uniform(0.05, 2.0, (B, Y, X)).astype(np.float32)
     out = {}
     # (layout, path): the tiled layout (any grid shape, incl. partial tiles) must agree with the row-major ones bit for bit
-    combos = [(1, "lsu"), (2, "lsu"), (2, "async"), (3, "lsu"), (3, "async")] + ([(1, "async")] if X % 4 == 0 else [])
+    combos = [(1, "lsu"), (2, "lsu"), (2, "async"), (3, "lsu"), (3, "async"), (4, "lsu"), (4, "async")] + ([(1, "async")] if X % 4 == 0 else [])
     for layout, path in combos:
         with _engine(params, B, layout=layout, seed=99) as eng:
             eng.set_step_path(path)
@@ -63,9 +63,10 @@ def test_persistent_paths_are_bit_identical_to_lsu_path(grid, reward_mode, adapt
             assert np.array_equal(a, b), key
     assert np.array_equal(out[(2, "async")][5], gt.astype(np.float32))
     assert np.array_equal(out[(3, "async")][5], gt.astype(np.float32))
+    assert np.array_equal(out[(4, "async")][5], gt.astype(np.float32))
 
 
-@pytest.mark.parametrize("path,layout", [("async", 1), ("async", 2), ("async", 3)])
+@pytest.mark.parametrize("path,layout", [("async", 1), ("async", 2), ("async", 3), ("async", 4)])
 def test_persistent_windowed_golden_by_action_id(path, layout):
     """Reference-pinned T2 vectors (200x200) through the persistent paths: poses at cell centres -> action ids."""
     g = golden("golden_windowed_T2.npz")
@@ -120,7 +121,7 @@ SIZES = {  # BASELINE.json configurations at their full per-GPU sizes
 }
 
 
-@pytest.mark.parametrize("path,layout,size", [("async", 3, "C3"), ("async", 2, "C3"), ("async", 1, "C3"), ("lsu", 1, "C3"), ("async", 3, "C5"),
+@pytest.mark.parametrize("path,layout,size", [("async", 3, "C3"), ("async", 4, "C3"), ("async", 2, "C3"), ("async", 1, "C3"), ("lsu", 1, "C3"), ("async", 3, "C5"),
                                               ("async", 2, "C5"), ("async", 3, "C2"), ("async", 2, "C2"), ("lsu", 0, "C2")])
 def test_full_size_properties(path, layout, size):
     """Size-independent properties at BASELINE.json's full sizes: cells outside the footprint untouched bit for bit, variance

@@ -14,7 +14,7 @@ def _engine(params, batch, **kw):
     return BatchedEngine(engine_cfg(params, batch, **kw))
 
 
-@pytest.mark.parametrize("layout", [0, 1, 2, 3])
+@pytest.mark.parametrize("layout", [0, 1, 2, 3, 4])
 def test_device_grf_matches_reference_fields(layout):
     g = golden("golden_grf.npz")
     for name in g["names"]:
@@ -48,7 +48,7 @@ def test_device_grf_philox_mode_is_shard_invariant_and_smooth():
     assert np.all(corr > 0.9)  # k^-5 spectrum: strongly correlated neighbours (white noise would give ~0)
 
 
-@pytest.mark.parametrize("layout", [0, 1, 2, 3])
+@pytest.mark.parametrize("layout", [0, 1, 2, 3, 4])
 def test_observation_planes_match_reference_feature_planes(layout):
     """ipp_observe vs the REAL reference generate_input_feature_planes on a diagonal state (golden_features.npz)."""
     from tests._util import params_from_json
@@ -76,7 +76,7 @@ def test_observation_planes_match_reference_feature_planes(layout):
             assert np.max(np.abs(obs[0, 5] - cost[X * cols + rows])) <= 1e-6
 
 
-@pytest.mark.parametrize("layout", [1, 3])
+@pytest.mark.parametrize("layout", [1, 3, 4])
 def test_device_hotspot_and_split_fields(layout):
     """ipp_generate_field: the reference's construction (simulations/simulations.py:57-125) per env on the device — two-valued
     maps with the reference's value ranges and geometry, keyed by the global env id (sharding invariance), and the same
@@ -132,7 +132,7 @@ def test_device_hotspot_and_split_fields(layout):
     assert 0.4 < by_rows_dev < 0.6
 
 
-@pytest.mark.parametrize("layout", [0, 3])
+@pytest.mark.parametrize("layout", [0, 3, 4])
 def test_device_shuffled_priors(layout):
     """ipp_reset_shuffled: Mapping.init_priors(shuffle_prior_cov=True) per env (mapping/mappings.py:219-240)."""
     X = Y = 20

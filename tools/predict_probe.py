@@ -10,7 +10,9 @@ from ipp_rl_b200 import BatchedEngine, EngineConfig, _capi as capi
 B = 65536
 W = dict(x_dim=200, y_dim=200, resolution=1.0, min_altitude=8.0, max_altitude=20.0, altitude_spacing=6.0)
 stream = torch.cuda.Stream()
-eng = BatchedEngine(EngineConfig(batch=B, layout=capi.LAYOUT_SUPER, seed=1, stream=stream.cuda_stream, **W))
+LAYOUT = sys.argv[1] if len(sys.argv) > 1 else "super"
+eng = BatchedEngine(EngineConfig(batch=B, layout=capi.LAYOUT_NAMES[LAYOUT], seed=1, stream=stream.cuda_stream, **W))
+print(f"layout {LAYOUT}")
 eng.reset(0.5, 1.82)
 eng.synth_ground_truth(1)
 rng = np.random.RandomState(0)
