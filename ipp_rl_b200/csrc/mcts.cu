@@ -4,7 +4,8 @@
 //
 //   mcts_select_kernel   PUCT descent root -> leaf (compute_uct incl. forced playouts at the root,
 //                        planning/mcts_zero/mcts.py:280-296), creation of the child of a new edge
-//   ipp_rollout_device   rewards of the path's prediction steps (rollout_kernel.cuh)
+//   mcts_rollout_kernel  reward of the path's NEW prediction step; the steps above it were rolled out when their edges
+//                        were created: an edge caches its reward, a node the variances its step left behind (overlay)
 //   -- evaluator call-out (policy/value network; not part of this library) --
 //   mcts_expand_kernel   mask + normalise the leaf's priors (mcts.py:196-237), back the value up
 //                        (mcts.py:248-265)
@@ -26,6 +27,7 @@
 
 #include "../../include/ipp_mcts.h"
 #include "engine_internal.h"
+#include "step_kernel.cuh"
 
 using namespace ipp;
 
@@ -45,7 +47,7 @@ struct __align__(16) Edge {
     int parent, slot;
     float prior, q;
     int n, child;
-    int pad[2];
+    int pad[2];  // [0] action id (cached when the child node is created), [1] reward bits (cached by the edge's first rollout)
 };
 static_assert(sizeof(Edge) == 32, "Edge layout");
 constexpr int kNoNode = -1;
@@ -63,6 +65,8 @@ struct TreeArrays {
     int *path_action;  // [T][max_path]  (-1 padded)
     float *path_reward;  // [T][max_path]
     int *leaf;           // [T][IPP_MCTS_LEAF_WORDS]
+    float *overlay;      // [T][M][tile]  variances of a node's footprint after its prediction step (row-major, pitch = its nx)
+    int tile;            // floats per overlay (largest footprint)
 };
 
 __device__ __forceinline__ int pack_pos(int col, int row, int lvl) { return col | (row << 12) | ((lvl + 1) << 24); }
@@ -281,6 +285,177 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
         lf[5] = depth;
         lf[6] = __float_as_int(budget);
         lf[7] = len;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rollout: the reward of the path's newest prediction step
+// ------------------------------------------------------------------------------------------------
+// The reference replays the whole path every simulation: one simulate_prediction_step per level on a copy of the covariance
+// (planning/mcts_zero/mcts.py:239-246 -> planning/common/optimization.py:14-30).  A prediction step is deterministic given
+// the path above it, so the search memoises it: an edge keeps the reward of its step (first rollout), a node the variances
+// its step left on its footprint (<= `tile` floats in HBM).  A simulation then costs ONE footprint — the new edge's: its
+// variances come from the latest ancestor overlay that covers a cell, else from the env's belief (which must not change
+// between ipp_mcts_begin and the search's last simulation) — instead of one footprint per level; paths that end on an edge
+// visited before (terminal edges) cost nothing.  Same arithmetic as ipp_rollout_kernel (rollout_kernel.cuh): bit-identical
+// rewards, hence identical trees.
+template <int LAYOUT>
+__global__ void __launch_bounds__(kTreeWarps * 32) mcts_rollout_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a, uint32_t flags) {
+    __shared__ int4 s_rect[kTreeWarps][IPP_MCTS_MAX_PATH];  // {xl, yu, nx, ny} of the nodes on the path
+    __shared__ int s_node[kTreeWarps][IPP_MCTS_MAX_PATH];
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int t = blockIdx.x * kTreeWarps + wib;
+    if (t >= d.T) return;
+    const int *lf = a.leaf + (size_t)t * IPP_MCTS_LEAF_WORDS;
+    const int len = lf[7];
+    if (len == 0) return;
+    const int *pe = a.path_edge + (size_t)t * d.max_path;
+    const int *pa = a.path_action + (size_t)t * d.max_path;
+    float *pr = a.path_reward + (size_t)t * d.max_path;
+    Edge *edges = a.edges + (size_t)t * d.E;
+
+    // steps above the new one: cached rewards; rectangles and nodes of the path for the overlay look-up
+    bool last_cached = false;
+    if (lane < len) {
+        const Edge ed = edges[pe[lane]];
+        // the last step is new when its edge has never been backed up; a path that ends on an unexpanded node is rolled out
+        // again (same values): the node's overlay must exist whatever happened before
+        bool cached = lane < len - 1 || ed.n > 0;
+        if (lane == len - 1 && lf[0] == IPP_MCTS_LEAF_EVAL && lf[1] > 0 && lf[1] == ed.child) cached = false;
+        if (cached) pr[lane] = __int_as_float(ed.pad[1]);
+        if (lane == len - 1) last_cached = cached;
+        if (lane < len - 1) {
+            int lvl, col, row;
+            decode_id(p, pa[lane], lvl, col, row);
+            Geom g;
+            clip_footprint(p, col, row, p.lut[lvl].rx, p.lut[lvl].ry, g);
+            s_rect[wib][lane] = make_int4(g.xl, g.yu, g.nx, g.ny);
+            s_node[wib][lane] = ed.child;
+        }
+    }
+    last_cached = __shfl_sync(0xffffffffu, last_cached, len - 1);
+    if (last_cached) return;
+    __syncwarp();
+
+    const int k = len - 1;  // the new step
+    const int env = d.first_env + t;
+    const Belief<LAYOUT> bel(p, (size_t)env);
+    const bool adaptive = (flags & IPP_FLAG_ADAPTIVE) != 0;
+    const bool entropy = (flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY;
+    int lvl, col, row;
+    decode_id(p, pa[k], lvl, col, row);
+    const Geom g = geom_from_cell(p, lvl, col, row);
+    FuseCtx fc;
+    fc.rf = g.rf;
+    fc.R = g.R;
+    fc.invR = fast_rcp(g.R);
+    const int nqx = (g.nx + 1) >> 1, nqy = (g.ny + 1) >> 1, nq = nqx * nqy;
+    const float inv_nqx = __frcp_rn((float)nqx);
+    // the node this step creates keeps its variances for its descendants (none when the search stopped at a terminal edge)
+    const int new_node = lf[0] == IPP_MCTS_LEAF_EVAL ? lf[1] : -1;
+    float *mine = new_node > 0 ? a.overlay + ((size_t)t * d.M + new_node) * a.tile : nullptr;
+    const float *ov = a.overlay + (size_t)t * d.M * a.tile;
+
+    float acc = 0.0f;
+    for (int q = lane; q < nq; q += 32) {
+        const int qyy = fdiv(q, nqx, inv_nqx), qxx = q - qyy * nqx;
+        const int r0 = 2 * qyy, c0 = 2 * qxx;
+        const bool cok = c0 + 1 < g.nx, rok = r0 + 1 < g.ny;
+        const bool ok[4] = {true, cok, rok, cok && rok};
+        float m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
+        const int R0 = g.yu + r0, C0 = g.xl + c0;
+        // the quad's variance: the latest path node whose footprint covers it, else the env's belief; a quad that straddles a
+        // rectangle border goes cell by cell
+        int src = -1;  // >= 0: overlay of that path node; -1: belief; -2: mixed
+        int4 rc = make_int4(0, 0, 0, 0);
+        for (int s = k - 1; s >= 0; --s) {
+            rc = s_rect[wib][s];
+            const int dx0 = C0 - rc.x, dy0 = R0 - rc.y, dx1 = dx0 + (cok ? 1 : 0), dy1 = dy0 + (rok ? 1 : 0);
+            const bool in_x0 = (unsigned)dx0 < (unsigned)rc.z, in_x1 = (unsigned)dx1 < (unsigned)rc.z;
+            const bool in_y0 = (unsigned)dy0 < (unsigned)rc.w, in_y1 = (unsigned)dy1 < (unsigned)rc.w;
+            if (in_x0 && in_x1 && in_y0 && in_y1) {
+                src = s;
+                break;
+            }
+            if ((in_x0 || in_x1) && (in_y0 || in_y1)) {
+                src = -2;
+                break;
+            }
+        }
+        if (src >= 0) {
+            const float *tl = ov + (size_t)s_node[wib][src] * a.tile + (R0 - rc.y) * rc.z + (C0 - rc.x);
+            v[0] = __ldcg(tl);
+            if (cok) v[1] = __ldcg(tl + 1);
+            if (rok) v[2] = __ldcg(tl + rc.z);
+            if (cok && rok) v[3] = __ldcg(tl + rc.z + 1);
+            if (adaptive) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (ok[c]) m[c] = bel.load_mean(Belief<LAYOUT>::idx(p, R0 + (c >> 1), C0 + (c & 1)));
+            }
+        } else if (src == -1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (!ok[c]) continue;
+                const int off = Belief<LAYOUT>::idx(p, R0 + (c >> 1), C0 + (c & 1));
+                if (LAYOUT == IPP_LAYOUT_PLANES || LAYOUT == IPP_LAYOUT_SPLIT || !adaptive) {
+                    v[c] = bel.load_var(off);
+                    if (adaptive) m[c] = bel.load_mean(off);
+                } else {
+                    bel.load(off, m[c], v[c]);  // one 8-byte load for {mean, var}
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (!ok[c]) continue;
+                const int R = R0 + (c >> 1), C = C0 + (c & 1);
+                bool found = false;
+                for (int s = k - 1; s >= 0 && !found; --s) {
+                    const int4 r4 = s_rect[wib][s];
+                    const int dx = C - r4.x, dy = R - r4.y;
+                    if ((unsigned)dx < (unsigned)r4.z && (unsigned)dy < (unsigned)r4.w) {
+                        v[c] = __ldcg(ov + (size_t)s_node[wib][s] * a.tile + dy * r4.z + dx);
+                        found = true;
+                    }
+                }
+                const int off = Belief<LAYOUT>::idx(p, R, C);
+                if (!found) v[c] = bel.load_var(off);
+                if (adaptive) m[c] = bel.load_mean(off);  // the mean never changes in a prediction step
+            }
+        }
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        float mn[4], vn[4];
+        bool msk[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) msk[c] = ok[c] && (!adaptive || (fmaf(p.kappa, v[c], m[c]) >= p.thr));
+        acc += kalman_quad_rt(entropy, adaptive, fc, cok, rok, m, v, z, msk, mn, vn);
+        if (mine) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (ok[c]) mine[(r0 + (c >> 1)) * g.nx + c0 + (c & 1)] = vn[c];
+        }
+    }
+    float accd = acc;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, s);
+    if (lane == 0) {
+        // cost from the pose the step starts at: the root's (any pose) or the lattice cell of the step above
+        double qx, qy, qh;
+        if (k == 0) {
+            qx = a.root_pose[3 * t], qy = a.root_pose[3 * t + 1], qh = a.root_pose[3 * t + 2];
+        } else {
+            int l2, c2, r2;
+            decode_id(p, pa[k - 1], l2, c2, r2);
+            qx = __dadd_rn(__dmul_rn(p.res, (double)c2), __dmul_rn(0.5, p.res));
+            qy = __dadd_rn(__dmul_rn(p.res, (double)r2), __dmul_rn(0.5, p.res));
+            qh = p.lut[l2].alt;
+        }
+        const float cost = job_cost(p, g.px, g.py, g.ph, qx, qy, qh);
+        const float reward = accd * fast_rcp(cost + 1.0f);
+        pr[k] = reward;
+        edges[pe[k]].pad[1] = __float_as_int(reward);
     }
 }
 
@@ -551,6 +726,10 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
         (rc = malloc_dev(m, &a.path_reward, TP)) || (rc = malloc_dev(m, &a.leaf, (size_t)d.T * IPP_MCTS_LEAF_WORDS)) ||
         (rc = malloc_dev(m, &m->d_env_index, (size_t)d.T)) || (rc = malloc_dev(m, &m->d_budgets, (size_t)d.T)))
         return bail(rc);
+    a.tile = 1;
+    for (int k = 0; k < info.num_altitude_levels; ++k)
+        a.tile = std::max(a.tile, std::min(2 * info.radius_x[k] + 1, info.x_dim) * std::min(2 * info.radius_y[k] + 1, info.y_dim));
+    if ((rc = malloc_dev(m, &a.overlay, TM * (size_t)a.tile))) return bail(rc);
     iota_kernel<<<(d.T + 255) / 256, 256, 0, m->stream>>>(m->d_env_index, d.T, d.first_env);
     m->launches++;
     if (cudaStreamSynchronize(m->stream) != cudaSuccess) return bail(mfail(m, IPP_ERR_CUDA, "ipp_mcts_create: device initialisation failed"));
@@ -617,11 +796,20 @@ extern "C" int ipp_mcts_simulate_begin(ipp_mcts *m, int32_t *leaf_info) {
     mcts_select_kernel<<<blocks, kTreeWarps * 32, 0, m->stream>>>(m->sp, d, m->a);
     m->launches++;
     MCU(m, cudaGetLastError());
-    // rewards of the path's prediction steps, from the env's current belief (nothing is written)
-    int rc = ipp_rollout_device(m->env, d.T, d.max_path, m->d_env_index, m->a.path_action, m->a.root_pose, m->a.path_reward,
-                                m->cfg.step_flags & (IPP_REWARD_MASK | IPP_FLAG_ADAPTIVE));
-    if (rc != IPP_OK) return mfail(m, rc, "ipp_mcts_simulate_begin: %s", ipp_last_error(m->env));
-    m->launches++;
+    // reward of the path's new prediction step (the steps above it are cached in their edges); the belief is only read
+    {
+        const uint32_t fl = m->cfg.step_flags & (IPP_REWARD_MASK | IPP_FLAG_ADAPTIVE);
+        const int layout = ipp_internal_layout(m->env);
+        void (*kern)(const StepParams, TreeDims, TreeArrays, uint32_t) =
+            layout == IPP_LAYOUT_TILED   ? mcts_rollout_kernel<IPP_LAYOUT_TILED>
+            : layout == IPP_LAYOUT_SUPER ? mcts_rollout_kernel<IPP_LAYOUT_SUPER>
+            : layout == IPP_LAYOUT_SPLIT ? mcts_rollout_kernel<IPP_LAYOUT_SPLIT>
+            : layout == IPP_LAYOUT_MV    ? mcts_rollout_kernel<IPP_LAYOUT_MV>
+                                         : mcts_rollout_kernel<IPP_LAYOUT_PLANES>;
+        kern<<<blocks, kTreeWarps * 32, 0, m->stream>>>(m->sp, d, m->a, fl);
+        m->launches++;
+        MCU(m, cudaGetLastError());
+    }
     if (leaf_info) {
         MCU(m, cudaMemcpyAsync(leaf_info, m->a.leaf, (size_t)d.T * IPP_MCTS_LEAF_WORDS * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
         MCU(m, cudaStreamSynchronize(m->stream));
