@@ -288,7 +288,7 @@ def run_ours(args, rank, world, local_rank):
         reward_dev = torch.empty(B, dtype=torch.float32, device="cuda")
         torch.cuda.synchronize()
 
-        def timed_device_loop(fn, tag):
+        def timed_device_loop(fn, tag, eng=eng):
             """W warm-up launches, then K launches between two CUDA events on the engine's stream; max over ranks."""
             eng.reset(PRIOR_MEAN, PRIOR_VAR)
             for t in range(W):
@@ -312,20 +312,24 @@ def run_ours(args, rank, world, local_rank):
             results[name] = timed_device_loop(
                 lambda t, mode=mode: eng.step_device(action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=mode),
                 f"step[{name}]")
-        # predict-only leg: the covariance-only step the planners' rollouts run (simulate_prediction_step,
-        # planning/common/optimization.py:14-30), whole batch, committing — the persistent kernel's MODE_PREDICT
-        pl0 = eng.path_launches("async")
-        results["predict"] = timed_device_loop(
-            lambda t: eng.predict_device(B, action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), commit=True,
-                                         reward_mode=capi.REWARD_TRACE),
-            "predict")
-        predict_persistent = eng.path_launches("async") - pl0 >= K
-        # ... and the evaluate-only form (IPP_FLAG_NO_COMMIT: rewards of candidate actions, nothing written — what greedy_search
-        # and the tree search ask for): the same staged reads without the write-back
-        results["predict_eval"] = timed_device_loop(
-            lambda t: eng.predict_device(B, action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), commit=False,
-                                         reward_mode=capi.REWARD_TRACE),
-            "predict[no commit]")
+        # predict-only legs: the covariance-only step the planners' rollouts run (simulate_prediction_step,
+        # planning/common/optimization.py:14-30), whole batch — the persistent kernel's MODE_PREDICT.  Committing, and the
+        # evaluate-only form (IPP_FLAG_NO_COMMIT: rewards of candidate actions, nothing written — what greedy_search and the
+        # tree search ask for).  Timed on the step engine's layout here and on the search engine's (below).
+        def predict_legs(e, suffix):
+            pl0 = e.path_launches("async")
+            results["predict" + suffix] = timed_device_loop(
+                lambda t: e.predict_device(B, action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), commit=True,
+                                           reward_mode=capi.REWARD_TRACE),
+                "predict" + suffix, eng=e)
+            persistent = e.path_launches("async") - pl0 >= K
+            results["predict_eval" + suffix] = timed_device_loop(
+                lambda t: e.predict_device(B, action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), commit=False,
+                                           reward_mode=capi.REWARD_TRACE),
+                "predict[no commit]" + suffix, eng=e)
+            return persistent
+
+        predict_persistent = predict_legs(eng, "@step_layout")
 
         # the clock sampler polls nvidia-smi, which takes driver locks for ~1 ms at a time: stop it before the latency-bound legs
         clocks = sampler.stop() if sampler else None
@@ -341,8 +345,8 @@ def run_ours(args, rank, world, local_rank):
             shared = SharedRewards(rank, world, B, tag=os.environ.get("MASTER_PORT", "0"))
         eng.reset(PRIOR_MEAN, PRIOR_VAR)
         if args.zero_copy is not None:
-            eng.set_zero_copy(rewards="r" in args.zero_copy, ids="i" in args.zero_copy)
-        zc0 = eng.zero_copy_steps
+            eng.set_zero_copy(rewards="r" in args.zero_copy, ids="i" in args.zero_copy, ids_fetch="f" in args.zero_copy)
+        zc0, if0 = eng.zero_copy_steps, eng.ids_fetch_steps
         e2e_mode = reward_modes[HEAD]
         checksum = [0.0]
 
@@ -374,6 +378,7 @@ def run_ours(args, rank, world, local_rank):
         nvtx.range_pop()
         launches_e2e = eng.launches - launches_e2e0
         zero_copy_steps = eng.zero_copy_steps - zc0
+        ids_fetch_steps = eng.ids_fetch_steps - if0
         if shared is None:
             assert np.isfinite(out_np).all()
         else:
@@ -426,6 +431,22 @@ def run_ours(args, rank, world, local_rank):
         if shared is not None:
             shared.close()
 
+        # ---- search engine: the covariance-only paths (whole-batch prediction steps, tree search) only read / write the
+        #      variance, so they run on IPP_LAYOUT_SPLIT (variance tiles in their own array: 4 + 4 B per cell move, not the
+        #      ~27 B of the interleaved super-tiles).  Same workload, its own 31.5 GB of maps; a few executed steps first so
+        #      that the beliefs are not uniform.
+        seng = eng
+        if args.search_layout != args.layout:
+            scfg = EngineConfig(batch=B, layout=capi.LAYOUT_NAMES[args.search_layout], device=local_rank, seed=20260925, env_id_offset=rank * B,
+                                stream=stream.cuda_stream, **WORKLOAD)
+            seng = BatchedEngine(scfg)
+            seng.reset(PRIOR_MEAN, PRIOR_VAR)
+            seng.synth_ground_truth(seed=1000)
+            predict_persistent_search = predict_legs(seng, "")
+        else:
+            results["predict"], results["predict_eval"] = results["predict@step_layout"], results["predict_eval@step_layout"]
+            predict_persistent_search = predict_persistent
+
     # ---- secondary leg (BASELINE.json configs[3], "C4"): mcts_zero rollouts on the same beliefs.  Lock-step search over
     #      `--mcts-trees` envs, `--mcts-sims` simulations, episode_horizon 5, max_valid_action_distance 11.5 m, uniform
     #      priors / zero values (no network: the policy/value net is outside this library).  Reported beside the headline.
@@ -438,19 +459,13 @@ def run_ours(args, rank, world, local_rank):
                      forced_playout_factor=2.0, max_valid_action_distance=11.5)
         meta = dict(episode_horizon=5, scenario_info=None)
         budgets = np.full(Tm, 150.0, np.float32)
-        # The search only READS the variance (4 B per footprint cell): it runs on its own engine in the layout that drags the
-        # fewest other bytes through the 128-byte lines DRAM serves (--mcts-layout; the step engine's super-tiles interleave
-        # mean, variance and ground truth for the full step).  A few executed steps first, so that the beliefs are not uniform.
-        meng = eng
-        if args.mcts_layout != args.layout:
-            mcfg = EngineConfig(batch=Tm, layout=capi.LAYOUT_NAMES[args.mcts_layout], device=local_rank, seed=20260925, env_id_offset=rank * B,
-                                stream=stream.cuda_stream, **WORKLOAD)
-            meng = BatchedEngine(mcfg)
-            meng.reset(PRIOR_MEAN, PRIOR_VAR)
-            meng.synth_ground_truth(seed=1000)
-            with torch.cuda.stream(stream):
-                for t in range(4):
-                    meng.step(np.ascontiguousarray(ids_host[t % POOL][:Tm]), reward_mode=capi.REWARD_TRACE)
+        # The search runs on the search engine (first Tm envs), after a few executed steps so that the beliefs are not uniform.
+        meng = seng
+        meng.reset(PRIOR_MEAN, PRIOR_VAR)
+        with torch.cuda.stream(stream):
+            for t in range(4):
+                meng.step_device(action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=capi.REWARD_TRACE)
+            meng.sync()
         with torch.cuda.stream(stream):
             with BatchedMCTS(meng, hyper, meta, n_trees=Tm) as mcts:
                 # pass 1 (untimed, host-synchronous): count the prediction steps / expansions of the search (it is deterministic)
@@ -486,10 +501,12 @@ def run_ours(args, rank, world, local_rank):
                             "ms_per_lockstep_simulation": ms_m / Sm, "gpu_launches": int(mcts.launches - l0),
                             "algorithmic_bytes": alg_mcts, "achieved_gbs": alg_mcts / (ms_m * 1e-3) / 1e9,
                             "tree_bytes_per_gpu": int(mcts.info.device_bytes),
-                            "layout": args.mcts_layout,
+                            "layout": args.search_layout,
+                            "rollouts": "memoised: an edge caches its reward, a node the variances its prediction step left behind; a simulation "
+                                        "computes at most ONE prediction step (the reference replays one per level: prediction_steps counts those)",
                             "evaluator": "uniform priors, zero values (network outside this library)"}
-        if meng is not eng:
-            meng.close()
+    if seng is not eng:
+        seng.close()
 
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
     cpu = None
@@ -516,7 +533,7 @@ def run_ours(args, rank, world, local_rank):
 
         modes = {n: mode_block(n, alg_bytes_per_launch) for n in reward_modes}
         head = modes[HEAD]
-        kernel = {"super": "ipp_step_bulk_kernel", "tiled": "ipp_step_async_kernel", "mv": "ipp_step_async_kernel"}.get(args.layout, "ipp_step_kernel") \
+        kernel = {"super": "ipp_step_bulk_kernel", "split": "ipp_step_bulk_kernel", "tiled": "ipp_step_async_kernel", "mv": "ipp_step_async_kernel"}.get(args.layout, "ipp_step_kernel") \
             if eng.step_path == "async" else "ipp_step_kernel"
         traffic, traffic_note = None, "no ncu capture committed for this kernel"
         tp = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
@@ -529,14 +546,22 @@ def run_ours(args, rank, world, local_rank):
                     traffic_note = f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, captured at commit {ent.get('commit', '?')} ({ent.get('how', '')})"
             except Exception:
                 pass
-        pred = mode_block("predict", alg_bytes_predict)
-        pred.update({"unit": "predict-steps/s", "kernel": "ipp_step_bulk_kernel<MODE_PREDICT>" if predict_persistent else "ipp_step_kernel<MODE_PREDICT>",
-                     "bytes_per_cell": 8, "note": "covariance-only step on the interleaved {mean,var} layout: the staged run and the written "
-                                                 "sectors carry the mean (and, in the super-tile layout, the ground truth) too, so ~27 B per "
-                                                 "cell move where 8 B are algorithmic (DESIGN.md 3.1)"})
-        pe = mode_block("predict_eval", (4.0 * cells_timed_total + 16.0 * B * K) / K)
-        pred["evaluate_only"] = {"value": pe["value"], "ms_per_launch": pe["ms_per_launch"], "achieved": pe["achieved"], "frac": pe["frac"],
-                                 "bytes_per_cell": 4, "note": "IPP_FLAG_NO_COMMIT: the variance is read, nothing is written"}
+        def predict_block(suffix, persistent, layout, note):
+            pb = mode_block("predict" + suffix, alg_bytes_predict)
+            pb.update({"unit": "predict-steps/s", "kernel": "ipp_step_bulk_kernel<MODE_PREDICT>" if persistent else "ipp_step_kernel<MODE_PREDICT>",
+                       "layout": layout, "bytes_per_cell": 8, "note": note})
+            pe = mode_block("predict_eval" + suffix, (4.0 * cells_timed_total + 16.0 * B * K) / K)
+            pb["evaluate_only"] = {"value": pe["value"], "ms_per_launch": pe["ms_per_launch"], "achieved": pe["achieved"], "frac": pe["frac"],
+                                   "bytes_per_cell": 4, "note": "IPP_FLAG_NO_COMMIT: the variance is read, nothing is written"}
+            return pb
+
+        note_inter = ("covariance-only step on the interleaved layout: the staged run and the written sectors carry the mean (and, in the "
+                      "super-tile layout, the ground truth) too, so ~27 B per cell move where 8 B are algorithmic (DESIGN.md 3.1)")
+        note_split = ("covariance-only step on IPP_LAYOUT_SPLIT: the variance tiles have their own array, the kernel stages and writes "
+                      "them alone (DESIGN.md 3.1)")
+        pred = predict_block("", predict_persistent_search, args.search_layout, note_split if args.search_layout == "split" else note_inter)
+        if args.search_layout != args.layout:
+            pred["on_step_layout"] = predict_block("@step_layout", predict_persistent, args.layout, note_inter)
         line = {
             "metric": "env_steps_per_sec", "value": head["value"], "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": head["ms_per_launch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -558,7 +583,9 @@ def run_ours(args, rank, world, local_rank):
                     "pipelined_value": world * B * KE / pipe_s,
                     "pipelined_path": "ipp_step_submit / ipp_step_wait, 2 slots: same per-step H2D ids + rewards to pinned host memory, upload of "
                                       "step t+1 under the kernel of step t",
-                    "path": ("BatchedEngine.step (ipp_step: pinned host ids -> H2D -> fused kernel -> "
+                    "path": ("BatchedEngine.step (ipp_step: pinned host ids -> "
+                             + ("fetched by the fused kernel itself, 512-byte slices over PCIe under its first footprints -> "
+                                if ids_fetch_steps > 0 else "H2D -> fused kernel -> ")
                              + ("rewards written by the kernel into the caller's pinned buffer [zero-copy D2H, 4 B/env over PCIe])"
                                 if zero_copy_steps > 0 else "D2H rewards)"))
                             + ("" if dist is None else "; every rank writes its slice of ONE pinned segment shared by the node's ranks "
@@ -586,15 +613,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="envs per GPU")
-    ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "super"), choices=["planes", "mv", "tiled", "super"])
+    ap.add_argument("--layout", default=os.environ.get("IPP_LAYOUT", "super"), choices=["planes", "mv", "tiled", "super", "split"])
     ap.add_argument("--cpu-envs", type=int, default=4096, help="env sample of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=300, help="steps of the host-buffer (e2e) legs (independent of --steps)")
-    ap.add_argument("--zero-copy", default=None, choices=["", "r", "i", "ri"],
-                    help="e2e leg: host buffers the kernel accesses in place (r = rewards, i = action ids); default = the engine's (r)")
+    ap.add_argument("--zero-copy", default=None, choices=["", "r", "i", "ri", "f", "rf"],
+                    help="e2e leg: host buffers the kernel accesses in place (r = rewards, i = action ids read in place, f = action ids fetched "
+                         "by the persistent kernel); default = the engine's (rf)")
     ap.add_argument("--mcts-trees", type=int, default=16384, help="trees of the secondary mcts_zero rollout leg = BASELINE.json C4 per-GPU share (0 = skip)")
     ap.add_argument("--mcts-sims", type=int, default=32)
-    ap.add_argument("--mcts-layout", default="planes", choices=["planes", "mv", "tiled", "super"], help="belief layout of the search leg's engine")
+    ap.add_argument("--search-layout", "--mcts-layout", dest="search_layout", default="split", choices=["planes", "mv", "tiled", "super", "split"],
+                    help="belief layout of the search engine (whole-batch prediction steps + tree search legs)")
     ap.add_argument("--max-altitude", type=float, default=None, help="experiments only: override the top altitude of the action set")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -305,10 +305,16 @@ void *ipp_device_ptr(ipp_engine *e, int32_t which);
  * passes page-locked, mapped host memory (ipp_host_alloc, cudaHostAlloc/cudaHostRegister, torch pin_memory):
  * rewards are then written by the fused kernel straight into the caller's buffer (4 B per env over PCIe, inside
  * the kernel) and action ids are read from it, instead of separate stream copies around the launch.  Pageable
- * buffers always take the copy path.  Default IPP_ZERO_COPY_REWARDS; env IPP_ZERO_COPY="" | "r" | "i" | "ri".
- * IPP_OPT_ZERO_COPY_STEPS (read only) counts the steps whose rewards went out that way. */
+ * buffers always take the copy path.  IPP_ZERO_COPY_IDS_FETCH: the persistent step kernel pulls the ids itself, in
+ * 512-byte slices over PCIe into device memory while its first footprints are already being planned — no separate
+ * H2D copy for the kernel to wait for (16 us at 65 536 envs); needs a 16-byte aligned buffer, other kernels ignore it.
+ * Default IPP_ZERO_COPY_REWARDS | IPP_ZERO_COPY_IDS_FETCH; env IPP_ZERO_COPY = any of "r", "i", "f" (or "").
+ * IPP_OPT_ZERO_COPY_STEPS (read only) counts the steps whose rewards went out that way, IPP_OPT_IDS_FETCH_STEPS those
+ * whose ids the kernel fetched. */
 #define IPP_ZERO_COPY_REWARDS 1
 #define IPP_ZERO_COPY_IDS 2
+#define IPP_ZERO_COPY_IDS_FETCH 4
+#define IPP_OPT_IDS_FETCH_STEPS 6
 #define IPP_OPT_ZERO_COPY 4
 #define IPP_OPT_ZERO_COPY_STEPS 5
 int ipp_set_option(ipp_engine *e, int32_t option, int64_t value);

@@ -62,7 +62,7 @@ struct ipp_engine {
     int32_t *d_actions_slot[IPP_STEP_SLOTS] = {nullptr, nullptr};
     float *d_reward_slot[IPP_STEP_SLOTS] = {nullptr, nullptr};
     bool slot_busy[IPP_STEP_SLOTS] = {false, false};
-    int zero_copy = IPP_ZERO_COPY_REWARDS;  // IPP_OPT_ZERO_COPY / env IPP_ZERO_COPY
+    int zero_copy = IPP_ZERO_COPY_REWARDS | IPP_ZERO_COPY_IDS_FETCH;  // IPP_OPT_ZERO_COPY / env IPP_ZERO_COPY
     uint64_t zero_copy_steps = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -84,6 +84,9 @@ struct ipp_engine {
     uint64_t bulk_predict_launches = 0;
     unsigned int *d_tickets = nullptr;
     int ticket_parity = 0;
+    unsigned int *d_slice_state = nullptr;  // in-kernel fetch of host action ids (BulkParams::host_ids)
+    unsigned int slice_epoch = 0;
+    uint64_t ids_fetched_steps = 0;
     uint64_t launches = 0;
     uint64_t steps = 0;
     uint64_t device_bytes = 0;
@@ -617,7 +620,7 @@ static int setup_bulk(ipp_engine *e) {
     return IPP_OK;
 }
 
-static int launch_bulk(ipp_engine *e, const StepParams &p, bool predict) {
+static int launch_bulk(ipp_engine *e, const StepParams &p, bool predict, const int32_t *host_ids = nullptr) {
     const int variant = (((p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY) ? 1 : 0) | ((p.flags & IPP_FLAG_ADAPTIVE) ? 2 : 0) |
                         ((!predict && (p.noise != nullptr || p.z_out != nullptr)) ? 4 : 0) | (predict ? 8 : 0) |
                         (e->cfg.layout == IPP_LAYOUT_SPLIT ? 16 : 0);
@@ -629,6 +632,23 @@ static int launch_bulk(ipp_engine *e, const StepParams &p, bool predict) {
     bp.parity = e->ticket_parity;
     bp.warps = warps;
     bp.ring_bytes = vonly ? e->bulk_pring : e->bulk_ring;
+    bp.host_ids = nullptr;
+    bp.slice_state = nullptr;
+    bp.epoch = 0;
+    if (host_ids) {
+        const size_t n_slices = ((size_t)e->cfg.batch + kIdSlice - 1) / kIdSlice;
+        if (!e->d_slice_state || e->slice_epoch > 0xfffffff0u) {
+            int rc;
+            if (!e->d_slice_state && (rc = dev_alloc(e, &e->d_slice_state, n_slices)) != IPP_OK) return rc;
+            CU(e, cudaMemsetAsync(e->d_slice_state, 0, n_slices * sizeof(unsigned int), e->stream));
+            e->slice_epoch = 0;
+        }
+        e->slice_epoch += 2;
+        bp.host_ids = host_ids;
+        bp.slice_state = e->d_slice_state;
+        bp.epoch = e->slice_epoch;
+        e->ids_fetched_steps++;
+    }
     const int needed = (p.n_jobs + warps - 1) / warps;
     const int grid = std::max(1, std::min(e->sm_count, needed));
     bulk_variant(variant)<<<grid, warps * 32, vonly ? e->bulk_psmem : e->bulk_smem, e->stream>>>(bp);
@@ -791,6 +811,7 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         e->zero_copy = 0;
         if (strchr(zc, 'r')) e->zero_copy |= IPP_ZERO_COPY_REWARDS;
         if (strchr(zc, 'i')) e->zero_copy |= IPP_ZERO_COPY_IDS;
+        if (strchr(zc, 'f')) e->zero_copy |= IPP_ZERO_COPY_IDS_FETCH;
     }
     if ((rc = setup_async(e)) != IPP_OK) return bail(rc);
     if ((rc = setup_bulk(e)) != IPP_OK) return bail(rc);
@@ -806,7 +827,7 @@ extern "C" void ipp_destroy(ipp_engine *e) {
     if (!e) return;
     if (e->stream) cudaStreamSynchronize(e->stream);
     void *ptrs[] = {e->d_mean, e->d_var, e->gt_aliases_mean ? nullptr : e->d_gt, e->d_prev, e->d_actions, e->d_poses, e->d_prev_in, e->d_env_index,
-                    e->d_reward, e->d_noise, e->d_z, e->d_metrics, e->d_scratch, e->d_tickets, e->d_level_taps};
+                    e->d_reward, e->d_noise, e->d_z, e->d_metrics, e->d_scratch, e->d_tickets, e->d_level_taps, e->d_slice_state};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->h_status) cudaFreeHost(e->h_status);
@@ -865,6 +886,7 @@ static int status_error(ipp_engine *e) {
     const int st = *(volatile int *)e->h_status;
     if (st == 0) return IPP_OK;
     *(volatile int *)e->h_status = 0;
+    if (st & 4) return fail(e, IPP_ERR_CUDA, "the step kernel timed out waiting for a slice of host action ids (IPP_ZERO_COPY_IDS_FETCH)");
     if (st & 2)
         return fail(e, IPP_ERR_INVALID, "action id outside the action table (planning/common/actions.py:73-91: level * N + x_dim * col + row); the step ran on the clamped id");
     return fail(e, IPP_ERR_UNSUPPORTED, "footprint needs cv2 INTER_AREA with an up-sampling axis (non-square FoV/grid corner case); not supported");
@@ -1197,8 +1219,14 @@ static int validate_step_args(ipp_engine *e, const void *ids, const void *poses,
     return IPP_OK;
 }
 
-extern "C" int ipp_step_device(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise, int32_t noise_stride,
-                               float *reward, float *measurements, uint32_t flags) {
+// does a Kalman step on action ids with these flags take the bulk-copy persistent kernel?
+static bool takes_bulk(const ipp_engine *e, const void *action_ids, uint32_t flags) {
+    return action_ids != nullptr && (flags & (IPP_FLAG_LOGODDS | IPP_FLAG_NO_COMMIT)) == 0 && effective_path(e) == IPP_PATH_ASYNC && e->bulk_ok;
+}
+
+// host_ids: device alias of the caller's mapped host id buffer the bulk kernel fetches into action_ids itself, or nullptr
+static int step_device_impl(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise, int32_t noise_stride,
+                            float *reward, float *measurements, uint32_t flags, const int32_t *host_ids) {
     int rc = validate_step_args(e, action_ids, poses, "ipp_step_device");
     if (rc != IPP_OK) return rc;
     if ((noise || measurements) && noise_stride < e->max_meas)
@@ -1215,13 +1243,18 @@ extern "C" int ipp_step_device(ipp_engine *e, const int32_t *action_ids, const d
     p.flags = flags;
     const int path = (action_ids != nullptr && (flags & (IPP_FLAG_LOGODDS | IPP_FLAG_NO_COMMIT)) == 0) ? effective_path(e) : IPP_PATH_LSU;
     if (path == IPP_PATH_ASYNC)
-        rc = e->bulk_ok ? launch_bulk(e, p, false) : launch_async(e, p);
+        rc = e->bulk_ok ? launch_bulk(e, p, false, host_ids) : launch_async(e, p);
     else {
         rc = launch_step(e, p, (flags & IPP_FLAG_LOGODDS) ? MODE_LOGODDS : MODE_KALMAN);
         e->path_launches[IPP_PATH_LSU]++;
     }
     if (rc == IPP_OK) e->steps++;
     return rc;
+}
+
+extern "C" int ipp_step_device(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise, int32_t noise_stride,
+                               float *reward, float *measurements, uint32_t flags) {
+    return step_device_impl(e, action_ids, poses, noise, noise_stride, reward, measurements, flags, nullptr);
 }
 
 static int ensure_job_buffers(ipp_engine *e, size_t n) {
@@ -1267,9 +1300,14 @@ extern "C" int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *
     if ((noise || measurements) && noise_stride < e->max_meas)
         return fail(e, IPP_ERR_INVALID, "ipp_step: noise_stride %d < max_measurements %d", noise_stride, e->max_meas);
     // zero-copy: mapped pinned caller buffers go to the kernel as they are (IPP_OPT_ZERO_COPY)
-    const int32_t *ids_dev = nullptr;
+    const int32_t *ids_dev = nullptr, *ids_fetch = nullptr;
     float *reward_dev = nullptr;
-    if (action_ids && (e->zero_copy & IPP_ZERO_COPY_IDS)) ids_dev = (const int32_t *)mapped_alias(action_ids);
+    if (action_ids && (e->zero_copy & IPP_ZERO_COPY_IDS_FETCH) && takes_bulk(e, action_ids, flags)) {
+        ids_fetch = (const int32_t *)mapped_alias(action_ids);  // the kernel pulls the ids into d_actions itself
+        if (((uintptr_t)ids_fetch & 15) != 0) ids_fetch = nullptr;
+        if (ids_fetch) ids_dev = e->d_actions;
+    }
+    if (action_ids && !ids_dev && (e->zero_copy & IPP_ZERO_COPY_IDS)) ids_dev = (const int32_t *)mapped_alias(action_ids);
     if (reward && (e->zero_copy & IPP_ZERO_COPY_REWARDS)) reward_dev = (float *)mapped_alias(reward);
     if (action_ids && !ids_dev) {
         CU(e, cudaMemcpyAsync(e->d_actions, action_ids, B * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
@@ -1285,8 +1323,8 @@ extern "C" int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *
         // entries past an env's measurement count are unspecified by the kernels: hand back zeros, not stale device memory
         CU(e, cudaMemsetAsync(e->d_z, 0, B * (size_t)noise_stride * sizeof(float), e->stream));
     }
-    rc = ipp_step_device(e, ids_dev, poses ? e->d_poses : nullptr, noise ? e->d_noise : nullptr, noise_stride,
-                         reward_dev ? reward_dev : e->d_reward, measurements ? e->d_z : nullptr, flags);
+    rc = step_device_impl(e, ids_dev, poses ? e->d_poses : nullptr, noise ? e->d_noise : nullptr, noise_stride,
+                          reward_dev ? reward_dev : e->d_reward, measurements ? e->d_z : nullptr, flags, ids_fetch);
     if (rc != IPP_OK) return rc;
     if (reward_dev)
         e->zero_copy_steps++;
@@ -1559,7 +1597,7 @@ extern "C" int ipp_set_option(ipp_engine *e, int32_t option, int64_t value) {
             e->step_path = (int)value;
             return IPP_OK;
         case IPP_OPT_ZERO_COPY:
-            if (value < 0 || value > (IPP_ZERO_COPY_REWARDS | IPP_ZERO_COPY_IDS))
+            if (value < 0 || value > (IPP_ZERO_COPY_REWARDS | IPP_ZERO_COPY_IDS | IPP_ZERO_COPY_IDS_FETCH))
                 return fail(e, IPP_ERR_INVALID, "ipp_set_option: zero-copy mask %lld unknown", (long long)value);
             e->zero_copy = (int)value;
             return IPP_OK;
@@ -1576,6 +1614,7 @@ extern "C" int64_t ipp_get_option(const ipp_engine *e, int32_t option) {
         case IPP_OPT_LAUNCHES_ASYNC: return (int64_t)e->path_launches[IPP_PATH_ASYNC];
         case IPP_OPT_ZERO_COPY: return e->zero_copy;
         case IPP_OPT_ZERO_COPY_STEPS: return (int64_t)e->zero_copy_steps;
+        case IPP_OPT_IDS_FETCH_STEPS: return (int64_t)e->ids_fetched_steps;
         default: return -1;
     }
 }

@@ -42,6 +42,9 @@ namespace ipp {
 #ifndef IPP_BULK_GUIDE
 #define IPP_BULK_GUIDE 3
 #endif
+#ifndef IPP_BULK_GUIDE_PREDICT
+#define IPP_BULK_GUIDE_PREDICT 2  // covariance-only step (variance runs alone): little work per env, larger chunks pay
+#endif
 #ifndef IPP_BULK_TARGET_DEPTH
 #define IPP_BULK_TARGET_DEPTH 3  // after a consumed footprint: stage one, and more while fewer than this many are in flight
 #endif
@@ -66,7 +69,58 @@ struct BulkParams {
     int parity;             // counter consumed by this launch; the other one is zeroed for the next
     int warps;              // warps per CTA
     int ring_bytes;         // per-warp staging ring (multiple of 16, >= the largest footprint)
+    // action ids fetched by the kernel itself from the caller's mapped pinned host buffer (ipp_step, IPP_ZERO_COPY_IDS): the
+    // ids are pulled over PCIe in 512-byte slices into base.action_ids (device memory) while the first footprints are
+    // already being planned, instead of by a separate H2D copy the kernel has to wait for (16 us at 65 536 envs).
+    const int32_t *host_ids;    // device alias of the host buffer (16-byte aligned), or nullptr: base.action_ids is complete
+    unsigned int *slice_state;  // [ceil(n_jobs / 128)] epoch + 1: being copied, epoch + 2: in device memory
+    unsigned int epoch;         // even, grows by 2 per launch of this kind
 };
+constexpr int kIdSlice = 128;  // ids per slice: one 16-byte load per lane
+
+// Make slice s of the host ids available in device memory (warp-collective).  Whoever gets there first copies it, everyone else
+// waits for that warp — which is running, since it set the state — so no CTA ever waits for one that has not started.
+__device__ __forceinline__ void bulk_fetch_ids(const BulkParams &bp, int s, int lane) {
+    const unsigned ready = bp.epoch + 2u, busy = bp.epoch + 1u;
+    volatile unsigned *w = bp.slice_state + s;
+    unsigned st = 0;
+    if (lane == 0) {
+        st = *w;
+        if (st != ready && st != busy) st = atomicCAS(bp.slice_state + s, st, busy) == st ? 0xffffffffu : *w;
+    }
+    st = __shfl_sync(0xffffffffu, st, 0);
+    if (st == 0xffffffffu) {  // this warp copies
+        const int i0 = s * kIdSlice + lane * 4;
+        int32_t *dst = const_cast<int32_t *>(bp.base.action_ids);
+        if (i0 + 3 < bp.base.n_jobs) {
+            int4 v;
+            asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(bp.host_ids + i0));
+            __stcg(reinterpret_cast<int4 *>(dst + i0), v);
+        } else {
+            for (int i = i0; i < bp.base.n_jobs && i < i0 + 4; ++i) {
+                int v;
+                asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(bp.host_ids + i));
+                __stcg(dst + i, v);
+            }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *w = ready;
+    } else {
+        unsigned spins = 0;
+        while (st != ready) {
+            if (lane == 0) {
+                __nanosleep(100);
+                st = *w;
+                if (++spins > (1u << 24)) {  // ~2 s: the copying warp died (never in a healthy launch) — report instead of hanging
+                    *(volatile int *)bp.base.status = 4;
+                    st = ready;
+                }
+            }
+            st = __shfl_sync(0xffffffffu, st, 0);
+        }
+    }
+}
 
 // Per-env plan (48 B in shared memory), written by the planning lane; ring_off by the lane that starts the copies.
 struct __align__(16) BulkPlan {
@@ -204,7 +258,7 @@ __device__ __forceinline__ void bulk_plan_env(const StepParams &p, bool quirk, b
         out->job = -1;
         return;
     }
-    const int id = __ldg(p.action_ids + job);
+    const int id = __ldcg(p.action_ids + job);  // L2: with BulkParams::host_ids the ids are written by this very launch
     double *ps = p.prev_state + 3 * (size_t)job;
     const double *pv = (MODE == MODE_PREDICT && p.prev_in != nullptr) ? p.prev_in + 3 * (size_t)job : ps;
     const double q0 = pv[0], q1 = pv[1], q2 = pv[2];
@@ -284,6 +338,13 @@ __global__ void __launch_bounds__((MODE == MODE_PREDICT && SPLIT && !ADAPTIVE ? 
     unsigned int *ticket = bp.tickets + bp.parity;
     if (blockIdx.x == 0 && threadIdx.x == 0) bp.tickets[bp.parity ^ 1] = 0u;  // for the next launch
 
+    // ids still on the host: the warps of the grid pull one slice each (one PCIe round trip for the whole batch)
+    const bool fetch_ids = bp.host_ids != nullptr;
+    if (fetch_ids) {
+        const int n_slices = (p.n_jobs + kIdSlice - 1) / kIdSlice;
+        for (int sl = blockIdx.x + gridDim.x * w; sl < n_slices; sl += gridDim.x * bp.warps) bulk_fetch_ids(bp, sl, lane);
+    }
+
     const int n_jobs = p.n_jobs;
     const bool quirk = (p.flags & IPP_FLAG_NO_DSIZE_QUIRK) == 0;
     const bool commit = (p.flags & IPP_FLAG_NO_COMMIT) == 0;
@@ -345,7 +406,8 @@ __global__ void __launch_bounds__((MODE == MODE_PREDICT && SPLIT && !ADAPTIVE ? 
     // The first pass of the loop finds nothing staged: it only takes the warp's first chunk of tickets, plans and stages it.
     unsigned int chunk_base = 0;
     bool exhausted = false;  // no ticket left behind this warp's last chunk
-    const float inv_guide = __frcp_rn((float)(max(IPP_BULK_GUIDE, 1) * (int)gridDim.x * bp.warps));
+    constexpr int kGuide = (SPLIT && !kNeedMg) ? IPP_BULK_GUIDE_PREDICT : IPP_BULK_GUIDE;
+    const float inv_guide = __frcp_rn((float)(max(kGuide, 1) * (int)gridDim.x * bp.warps));
 
 #pragma unroll 1
     while (true) {
@@ -748,6 +810,11 @@ __global__ void __launch_bounds__((MODE == MODE_PREDICT && SPLIT && !ADAPTIVE ? 
             chunk_base = __shfl_sync(0xffffffffu, fresh, 0);
             exhausted = chunk_base + (unsigned)req >= (unsigned)n_jobs;
             if (chunk_base < (unsigned)n_jobs) {
+                if (fetch_ids) {  // the slices this chunk's ids live in (ready long ago, except right after the start)
+                    const int s0 = (int)chunk_base / kIdSlice, s1 = (int)(min(chunk_base + (unsigned)req, (unsigned)n_jobs) - 1u) / kIdSlice;
+                    bulk_fetch_ids(bp, s0, lane);
+                    if (s1 != s0) bulk_fetch_ids(bp, s1, lane);
+                }
                 if (lane < req) {
                     const unsigned int t = chunk_base + (unsigned)lane;
                     bulk_plan_env<MODE, SPLIT>(p, quirk, write_prev, t < (unsigned)n_jobs ? (int)t : -1, plans + ((q_tail + lane) & (kBulkPlanRing - 1)));

@@ -227,16 +227,22 @@ class BatchedEngine:
     def path_launches(self, path: str) -> int:
         return int(self._lib.ipp_get_option(self._h, capi.OPT_LAUNCHES_LSU + self.PATHS[path]))
 
-    def set_zero_copy(self, rewards: bool = True, ids: bool = False) -> None:
+    def set_zero_copy(self, rewards: bool = True, ids: bool = False, ids_fetch: bool = True) -> None:
         """Which pinned+mapped host buffers of ``step`` the kernel accesses in place (no stream copies around the
-        launch): rewards written straight to the caller's buffer, action ids read from it.  Pageable buffers always
-        take the copy path."""
-        mask = (capi.ZERO_COPY_REWARDS if rewards else 0) | (capi.ZERO_COPY_IDS if ids else 0)
+        launch): rewards written straight to the caller's buffer; action ids read from it (``ids``), or pulled by the
+        persistent kernel itself into device memory under its first footprints (``ids_fetch``).  Pageable buffers
+        always take the copy path."""
+        mask = (capi.ZERO_COPY_REWARDS if rewards else 0) | (capi.ZERO_COPY_IDS if ids else 0) | (capi.ZERO_COPY_IDS_FETCH if ids_fetch else 0)
         self._ck(self._lib.ipp_set_option(self._h, capi.OPT_ZERO_COPY, mask))
 
     @property
     def zero_copy_steps(self) -> int:
         return int(self._lib.ipp_get_option(self._h, capi.OPT_ZERO_COPY_STEPS))
+
+    @property
+    def ids_fetch_steps(self) -> int:
+        """steps whose action ids the kernel fetched from the caller's pinned buffer itself"""
+        return int(self._lib.ipp_get_option(self._h, capi.OPT_IDS_FETCH_STEPS))
 
     # -- reset / world -------------------------------------------------------------------------
     def reset(self, prior_mean: float = 0.5, prior_var: float = 1.82, prior_var_per_env=None, init_pose=None) -> None:

@@ -327,20 +327,20 @@ def test_unsupported_footprint_is_reported_through_the_status_word():
             assert np.isfinite(r).all() and (r > 0).all()
 
 
-@pytest.mark.parametrize("layout", [1, 2])
-def test_zero_copy_host_buffers_are_bit_identical_to_the_copy_path(layout):
-    """ipp_step with pinned+mapped caller buffers (rewards written by the kernel in place, ids read in place) gives
-    the same bits as the staged-copy path with pageable buffers; the counter proves which path ran."""
+@pytest.mark.parametrize("layout,B", [(1, 512), (2, 512), (3, 512), (3, 1301), (4, 1301), (3, 40000)])
+def test_zero_copy_host_buffers_are_bit_identical_to_the_copy_path(layout, B):
+    """ipp_step with pinned+mapped caller buffers (rewards written by the kernel in place; ids read in place, or fetched by the
+    persistent kernel itself in 128-id slices — batches that end inside a slice / a 16-byte group included) gives the same bits
+    as the staged-copy path with pageable buffers; the counters prove which path ran."""
     import torch
 
     params = make_params(64, 64, 1.0, 8, 20, 6)
-    B = 512
     rng = np.random.RandomState(5)
     gt = np.stack([smooth_field(rng, (64, 64)) for _ in range(8)]).astype(np.float32)[rng.randint(0, 8, B)]
     results = {}
-    for mode in ("copy", "r", "ri"):
+    for mode in ("copy", "r", "ri", "rf"):
         with _engine(params, B, layout=layout, seed=99) as eng:
-            eng.set_zero_copy(rewards="r" in mode, ids="i" in mode)
+            eng.set_zero_copy(rewards="r" in mode, ids="i" in mode, ids_fetch="f" in mode)
             eng.reset()
             eng.set_ground_truth(gt)
             idrng = np.random.RandomState(17)
@@ -357,8 +357,9 @@ def test_zero_copy_host_buffers_are_bit_identical_to_the_copy_path(layout):
                     eng.step(ids_pin.numpy(), out=out_pin.numpy())
                     rs.append(out_pin.numpy().copy())
             assert eng.zero_copy_steps == (0 if mode == "copy" else 4)
+            assert eng.ids_fetch_steps == (4 if mode == "rf" and layout in (3, 4) else 0)
             results[mode] = (np.stack(rs),) + eng.get_state()
-    for mode in ("r", "ri"):
+    for mode in ("r", "ri", "rf"):
         for a, b in zip(results["copy"], results[mode]):
             assert np.array_equal(a, b), mode
 
