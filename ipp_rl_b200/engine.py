@@ -153,6 +153,30 @@ def _f32(a, shape=None) -> np.ndarray:
     return a
 
 
+def pinned_array(shape, dtype) -> np.ndarray:
+    """A NumPy array on page-locked, mapped host memory (``ipp_host_alloc``): ``step`` reads ids from / writes rewards to such
+    buffers without stream copies (IPP_OPT_ZERO_COPY).  The memory lives until the process exits or ``free_pinned(a)``."""
+    lib = capi.load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    rc = lib.ipp_host_alloc(C.byref(ptr), max(n, 1))
+    if rc != capi.IPP_OK:
+        raise capi.IppError(rc, "ipp_host_alloc failed")
+    buf = (C.c_char * max(n, 1)).from_address(ptr.value)
+    a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[a.__array_interface__["data"][0]] = ptr
+    return a
+
+
+def free_pinned(a: np.ndarray) -> None:
+    ptr = _PINNED.pop(a.__array_interface__["data"][0], None)
+    if ptr is not None:
+        capi.load_library().ipp_host_free(ptr)
+
+
+_PINNED = {}
+
+
 class BatchedEngine:
     """``batch`` env instances on one B200; see module docstring."""
 

@@ -1,7 +1,8 @@
 """Small, fast exercise of every hand-written kernel for compute-sanitizer (memcheck / racecheck / synccheck runs are 10-100x
-slower than native, so the sizes are tiny but cover: all four layouts, the three step kernels (bulk / cp.async / LSU), both
+slower than native, so the sizes are tiny but cover: all five layouts, the three step kernels (bulk / cp.async / LSU), both
 reward modes, the adaptive mask, host noise + measurement read-back, clipped / corner footprints, predict (persistent and
-job-list), path rollouts, the lock-step MCTS kernels, eval, observe, GRF / field / prior reset).
+job-list), path rollouts, the lock-step MCTS kernels (memoised rollouts), eval, observe, GRF / field / prior reset, the host step
+with pinned buffers (ids fetched by the persistent kernel, rewards written in place, completion word).
 
     compute-sanitizer --tool racecheck python tools/sanitize_small.py
 """
@@ -14,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from ipp_rl_b200 import BatchedEngine, EngineConfig  # noqa: E402
+from ipp_rl_b200.engine import pinned_array  # noqa: E402
 from ipp_rl_b200.planning.mcts_zero import BatchedMCTS  # noqa: E402
 
 
@@ -21,7 +23,8 @@ def main():
     X, Y, B = 48, 40, 600  # > 148 SMs x 4 warps: the ticket counter and the plan rings wrap a few times
     rng = np.random.RandomState(0)
     gt = rng.uniform(0, 1, (B, Y, X)).astype(np.float32)
-    layouts = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3]
+    layouts = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4]
+    ids_pin, out_pin = pinned_array((B,), np.int32), pinned_array((B,), np.float32)
     for layout in layouts:
         cfg = EngineConfig(batch=B, x_dim=X, y_dim=Y, resolution=1.0, min_altitude=8.0, max_altitude=20.0, altitude_spacing=6.0,
                            layout=layout, seed=7, interval_factor=0.25, value_threshold=0.45)
@@ -38,6 +41,11 @@ def main():
                         eng.step(ids, noise=noise, reward_mode=t & 1, adaptive=True, return_measurements=True)
                     else:
                         eng.step(ids, reward_mode=t & 1, adaptive=(t == 3))
+                for poll in (False, True):  # pinned host buffers: ids fetched by the kernel (bulk path), rewards in place
+                    eng.set_poll_done(poll)
+                    ids_pin[:] = rng.randint(0, eng.num_actions, B)
+                    eng.step(ids_pin, out=out_pin)
+                eng.predict(rng.randint(0, eng.num_actions, B).astype(np.int32), commit=True)
                 eng.predict(rng.randint(0, eng.num_actions, B).astype(np.int32), commit=True, adaptive=True)
                 eng.predict(rng.randint(0, eng.num_actions, B).astype(np.int32), commit=False, reward_mode=1)
                 eng.predict(rng.randint(0, eng.num_actions, 50).astype(np.int32), env_index=rng.randint(0, B, 50).astype(np.int32),
