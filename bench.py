@@ -621,7 +621,7 @@ def main():
                     help="e2e leg: host buffers the kernel accesses in place (r = rewards, i = action ids read in place, f = action ids fetched "
                          "by the persistent kernel); default = the engine's (rf)")
     ap.add_argument("--mcts-trees", type=int, default=16384, help="trees of the secondary mcts_zero rollout leg = BASELINE.json C4 per-GPU share (0 = skip)")
-    ap.add_argument("--mcts-sims", type=int, default=32)
+    ap.add_argument("--mcts-sims", type=int, default=100, help="simulations per decision (BASELINE.json C4: 100)")
     ap.add_argument("--search-layout", "--mcts-layout", dest="search_layout", default="split", choices=["planes", "mv", "tiled", "super", "split"],
                     help="belief layout of the search engine (whole-batch prediction steps + tree search legs)")
     ap.add_argument("--max-altitude", type=float, default=None, help="experiments only: override the top altitude of the action set")

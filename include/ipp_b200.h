@@ -315,12 +315,6 @@ void *ipp_device_ptr(ipp_engine *e, int32_t which);
 #define IPP_ZERO_COPY_IDS 2
 #define IPP_ZERO_COPY_IDS_FETCH 4
 #define IPP_OPT_IDS_FETCH_STEPS 6
-/* IPP_OPT_POLL_DONE (0 / 1, default 0; env IPP_POLL_DONE): ipp_step with zero-copy rewards returns on the kernel's own
- * completion word (mapped host memory, written by the last CTA after every reward is visible system-wide) instead of
- * waiting for the stream to drain.  Measured 1.6 us per step slower than cudaStreamSynchronize at 65 536 envs
- * (tools/e2e_ab.py), hence off.  IPP_OPT_POLLED_STEPS (read only) counts the calls that returned that way. */
-#define IPP_OPT_POLLED_STEPS 7
-#define IPP_OPT_POLL_DONE 8
 #define IPP_OPT_ZERO_COPY 4
 #define IPP_OPT_ZERO_COPY_STEPS 5
 int ipp_set_option(ipp_engine *e, int32_t option, int64_t value);

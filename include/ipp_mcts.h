@@ -76,8 +76,11 @@ int ipp_mcts_get_info(const ipp_mcts *m, ipp_mcts_info *out);
 int ipp_mcts_begin(ipp_mcts *m, const double *root_poses, const float *budgets);
 
 /* First half of one lock-step simulation (mcts.py:166-265): PUCT descent with forced playouts at
- * the root, creation of the child node of a new edge, and the path's prediction-step rewards
- * (ipp_rollout_device).  leaf_info (host, may be NULL): int32[n_trees][IPP_MCTS_LEAF_WORDS]. */
+ * the root, creation of the child node of a new edge, and the path's prediction-step rewards — memoised:
+ * an edge keeps the reward of its step, a node the variances its step left on its footprint, so a simulation
+ * computes the path's NEW step only (the reference replays one simulate_prediction_step per level, mcts.py:239-246;
+ * same values).  The belief of the searched envs must not change between ipp_mcts_begin and the last simulation.
+ * leaf_info (host, may be NULL): int32[n_trees][IPP_MCTS_LEAF_WORDS]. */
 int ipp_mcts_simulate_begin(ipp_mcts *m, int32_t *leaf_info);
 
 /* Second half: expand the leaves with the evaluator's output and back the values up.
@@ -93,6 +96,11 @@ int ipp_mcts_simulate_end(ipp_mcts *m, const float *priors_window, const float *
  * invalid slots, mcts.py:220-234), Qsa, Nsa, and the action id of every slot (-1 outside the grid);
  * ns[n_trees] = Ns of the root. */
 int ipp_mcts_root_stats(ipp_mcts *m, float *ps, float *qsa, int32_t *nsa, int32_t *action_ids, int32_t *ns);
+
+/* The paths of the simulation in flight (between simulate_begin and simulate_end; host arrays, either may be NULL):
+ * actions[n_trees][max_path] action ids root -> leaf (-1 padded), rewards[n_trees][max_path] of their prediction steps
+ * (entries past a path's length are unspecified). */
+int ipp_mcts_get_paths(ipp_mcts *m, int32_t *actions, float *rewards);
 
 /* Device views for evaluators that stay on the GPU (valid until ipp_mcts_destroy). */
 #define IPP_MCTS_PTR_LEAF_INFO 0    /* int32[n_trees][IPP_MCTS_LEAF_WORDS] */

@@ -44,7 +44,7 @@ PTR_MEAN, PTR_VAR, PTR_GT, PTR_REWARD, PTR_STREAM = range(5)
 PATH_LSU, PATH_ASYNC = 0, 1
 OPT_STEP_PATH = 1
 OPT_LAUNCHES_LSU, OPT_LAUNCHES_ASYNC = 2, 3
-OPT_ZERO_COPY, OPT_ZERO_COPY_STEPS, OPT_IDS_FETCH_STEPS, OPT_POLLED_STEPS, OPT_POLL_DONE = 4, 5, 6, 7, 8
+OPT_ZERO_COPY, OPT_ZERO_COPY_STEPS, OPT_IDS_FETCH_STEPS = 4, 5, 6
 ZERO_COPY_REWARDS, ZERO_COPY_IDS, ZERO_COPY_IDS_FETCH = 1, 2, 4
 STEP_SLOTS = 2
 
@@ -222,6 +222,7 @@ SIGNATURES = {
     "ipp_mcts_simulate_begin": (C.c_int, [_P, _P]),
     "ipp_mcts_simulate_end": (C.c_int, [_P, _P, _P, _P, _P, _I32]),
     "ipp_mcts_root_stats": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "ipp_mcts_get_paths": (C.c_int, [_P, _P, _P]),
     "ipp_mcts_device_ptr": (_P, [_P, _I32]),
     # include/ipp_experience.h
     "ipp_ring_create": (C.c_int, [C.POINTER(ipp_ring_config), C.POINTER(_P)]),

@@ -84,15 +84,9 @@ struct ipp_engine {
     uint64_t bulk_predict_launches = 0;
     unsigned int *d_tickets = nullptr;
     int ticket_parity = 0;
-    unsigned int *h_done = nullptr, *d_done = nullptr;  // completion word (mapped pinned) the bulk kernel's last CTA writes
-    unsigned int *d_done_ctr = nullptr;
-    unsigned int done_epoch = 0;
-    bool done_pending = false;  // the last launch will write done_epoch to h_done
-    int poll_done = 0;          // IPP_OPT_POLL_DONE / env IPP_POLL_DONE=1 (measured 1.6 us per step SLOWER than the stream's own completion)
     unsigned int *d_slice_state = nullptr;  // in-kernel fetch of host action ids (BulkParams::host_ids)
     unsigned int slice_epoch = 0;
     uint64_t ids_fetched_steps = 0;
-    uint64_t polled_steps = 0;
     uint64_t launches = 0;
     uint64_t steps = 0;
     uint64_t device_bytes = 0;
@@ -626,7 +620,7 @@ static int setup_bulk(ipp_engine *e) {
     return IPP_OK;
 }
 
-static int launch_bulk(ipp_engine *e, const StepParams &p, bool predict, const int32_t *host_ids = nullptr, bool want_done = false) {
+static int launch_bulk(ipp_engine *e, const StepParams &p, bool predict, const int32_t *host_ids = nullptr) {
     const int variant = (((p.flags & IPP_REWARD_MASK) == IPP_REWARD_GAUSS_ENTROPY) ? 1 : 0) | ((p.flags & IPP_FLAG_ADAPTIVE) ? 2 : 0) |
                         ((!predict && (p.noise != nullptr || p.z_out != nullptr)) ? 4 : 0) | (predict ? 8 : 0) |
                         (e->cfg.layout == IPP_LAYOUT_SPLIT ? 16 : 0);
@@ -641,31 +635,6 @@ static int launch_bulk(ipp_engine *e, const StepParams &p, bool predict, const i
     bp.host_ids = nullptr;
     bp.slice_state = nullptr;
     bp.epoch = 0;
-    bp.done_host = nullptr;
-    bp.done_ctr = nullptr;
-    bp.done_epoch = 0;
-    e->done_pending = false;
-    if (want_done && e->poll_done) {
-        if (!e->h_done) {
-            if (cudaHostAlloc((void **)&e->h_done, sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess ||
-                cudaHostGetDevicePointer((void **)&e->d_done, e->h_done, 0) != cudaSuccess) {
-                cudaGetLastError();
-                e->h_done = nullptr;
-                e->poll_done = 0;
-            } else {
-                *e->h_done = 0;
-                int rc;
-                if ((rc = dev_alloc(e, &e->d_done_ctr, 1)) != IPP_OK) return rc;
-                CU(e, cudaMemsetAsync(e->d_done_ctr, 0, sizeof(unsigned int), e->stream));
-            }
-        }
-        if (e->h_done) {
-            bp.done_host = e->d_done;
-            bp.done_ctr = e->d_done_ctr;
-            bp.done_epoch = ++e->done_epoch;
-            e->done_pending = true;
-        }
-    }
     if (host_ids) {
         const size_t n_slices = ((size_t)e->cfg.batch + kIdSlice - 1) / kIdSlice;
         if (!e->d_slice_state || e->slice_epoch > 0xfffffff0u) {
@@ -844,7 +813,6 @@ extern "C" int ipp_create(const ipp_config *cfg, ipp_engine **out) {
         if (strchr(zc, 'i')) e->zero_copy |= IPP_ZERO_COPY_IDS;
         if (strchr(zc, 'f')) e->zero_copy |= IPP_ZERO_COPY_IDS_FETCH;
     }
-    if (const char *pd = getenv("IPP_POLL_DONE")) e->poll_done = atoi(pd) != 0;
     if ((rc = setup_async(e)) != IPP_OK) return bail(rc);
     if ((rc = setup_bulk(e)) != IPP_OK) return bail(rc);
     if (const char *sp = getenv("IPP_STEP_PATH")) {
@@ -863,8 +831,6 @@ extern "C" void ipp_destroy(ipp_engine *e) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->h_status) cudaFreeHost(e->h_status);
-    if (e->h_done) cudaFreeHost(e->h_done);
-    if (e->d_done_ctr) cudaFree(e->d_done_ctr);
     for (int k = 0; k < IPP_STEP_SLOTS; ++k) {
         if (e->ev_h2d[k]) cudaEventDestroy(e->ev_h2d[k]);
         if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
@@ -1260,7 +1226,7 @@ static bool takes_bulk(const ipp_engine *e, const void *action_ids, uint32_t fla
 
 // host_ids: device alias of the caller's mapped host id buffer the bulk kernel fetches into action_ids itself, or nullptr
 static int step_device_impl(ipp_engine *e, const int32_t *action_ids, const double *poses, const float *noise, int32_t noise_stride,
-                            float *reward, float *measurements, uint32_t flags, const int32_t *host_ids, bool want_done = false) {
+                            float *reward, float *measurements, uint32_t flags, const int32_t *host_ids) {
     int rc = validate_step_args(e, action_ids, poses, "ipp_step_device");
     if (rc != IPP_OK) return rc;
     if ((noise || measurements) && noise_stride < e->max_meas)
@@ -1277,7 +1243,7 @@ static int step_device_impl(ipp_engine *e, const int32_t *action_ids, const doub
     p.flags = flags;
     const int path = (action_ids != nullptr && (flags & (IPP_FLAG_LOGODDS | IPP_FLAG_NO_COMMIT)) == 0) ? effective_path(e) : IPP_PATH_LSU;
     if (path == IPP_PATH_ASYNC)
-        rc = e->bulk_ok ? launch_bulk(e, p, false, host_ids, want_done) : launch_async(e, p);
+        rc = e->bulk_ok ? launch_bulk(e, p, false, host_ids) : launch_async(e, p);
     else {
         rc = launch_step(e, p, (flags & IPP_FLAG_LOGODDS) ? MODE_LOGODDS : MODE_KALMAN);
         e->path_launches[IPP_PATH_LSU]++;
@@ -1357,38 +1323,14 @@ extern "C" int ipp_step(ipp_engine *e, const int32_t *action_ids, const double *
         // entries past an env's measurement count are unspecified by the kernels: hand back zeros, not stale device memory
         CU(e, cudaMemsetAsync(e->d_z, 0, B * (size_t)noise_stride * sizeof(float), e->stream));
     }
-    // nothing queued behind the kernel (rewards go out zero-copy): its last CTA tells the host directly when it is done
-    const bool want_done = (reward_dev != nullptr || reward == nullptr) && !measurements;
-    e->done_pending = false;
     rc = step_device_impl(e, ids_dev, poses ? e->d_poses : nullptr, noise ? e->d_noise : nullptr, noise_stride,
-                          reward_dev ? reward_dev : e->d_reward, measurements ? e->d_z : nullptr, flags, ids_fetch, want_done);
+                          reward_dev ? reward_dev : e->d_reward, measurements ? e->d_z : nullptr, flags, ids_fetch);
     if (rc != IPP_OK) return rc;
     if (reward_dev)
         e->zero_copy_steps++;
     else if (reward)
         CU(e, cudaMemcpyAsync(reward, e->d_reward, B * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     if (measurements) CU(e, cudaMemcpyAsync(measurements, e->d_z, B * (size_t)noise_stride * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-    if (e->done_pending) {
-        // poll the completion word (a few microseconds sooner than the stream's own completion reaches the host); the stream
-        // is the fallback should the word not arrive
-        e->done_pending = false;
-        const unsigned int want = e->done_epoch;
-        volatile unsigned int *w = e->h_done;
-        bool seen = false;
-        for (unsigned spins = 0; spins < (1u << 22); ++spins) {
-            if (*w == want) {
-                seen = true;
-                break;
-            }
-            __builtin_ia32_pause();
-            if ((spins & 1023u) == 1023u && cudaStreamQuery(e->stream) == cudaSuccess) break;  // finished (or failed): take the normal path
-        }
-        if (seen) {
-            e->polled_steps++;
-            for (int k = 0; k < IPP_STEP_SLOTS; ++k) e->slot_busy[k] = false;  // in-order stream: everything before the kernel is done too
-            return status_error(e);
-        }
-    }
     return check_status(e);
 }
 
@@ -1659,9 +1601,6 @@ extern "C" int ipp_set_option(ipp_engine *e, int32_t option, int64_t value) {
                 return fail(e, IPP_ERR_INVALID, "ipp_set_option: zero-copy mask %lld unknown", (long long)value);
             e->zero_copy = (int)value;
             return IPP_OK;
-        case IPP_OPT_POLL_DONE:
-            e->poll_done = value != 0;
-            return IPP_OK;
         default:
             return fail(e, IPP_ERR_INVALID, "ipp_set_option: unknown option %d", option);
     }
@@ -1676,8 +1615,6 @@ extern "C" int64_t ipp_get_option(const ipp_engine *e, int32_t option) {
         case IPP_OPT_ZERO_COPY: return e->zero_copy;
         case IPP_OPT_ZERO_COPY_STEPS: return (int64_t)e->zero_copy_steps;
         case IPP_OPT_IDS_FETCH_STEPS: return (int64_t)e->ids_fetched_steps;
-        case IPP_OPT_POLLED_STEPS: return (int64_t)e->polled_steps;
-        case IPP_OPT_POLL_DONE: return e->poll_done;
         default: return -1;
     }
 }

@@ -886,6 +886,16 @@ extern "C" int ipp_mcts_root_stats(ipp_mcts *m, float *ps, float *qsa, int32_t *
     return IPP_OK;
 }
 
+extern "C" int ipp_mcts_get_paths(ipp_mcts *m, int32_t *actions, float *rewards) {
+    if (!m) return IPP_ERR_INVALID;
+    if (!m->pending) return mfail(m, IPP_ERR_INVALID, "ipp_mcts_get_paths: no simulation in flight");
+    const size_t TP = (size_t)m->d.T * m->d.max_path;
+    if (actions) MCU(m, cudaMemcpyAsync(actions, m->a.path_action, TP * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    if (rewards) MCU(m, cudaMemcpyAsync(rewards, m->a.path_reward, TP * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    MCU(m, cudaStreamSynchronize(m->stream));
+    return IPP_OK;
+}
+
 extern "C" void *ipp_mcts_device_ptr(ipp_mcts *m, int32_t which) {
     if (!m) return nullptr;
     switch (which) {

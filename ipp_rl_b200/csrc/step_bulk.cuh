@@ -75,11 +75,6 @@ struct BulkParams {
     const int32_t *host_ids;    // device alias of the host buffer (16-byte aligned), or nullptr: base.action_ids is complete
     unsigned int *slice_state;  // [ceil(n_jobs / 128)] epoch + 1: being copied, epoch + 2: in device memory
     unsigned int epoch;         // even, grows by 2 per launch of this kind
-    // completion word in mapped host memory (ipp_step with zero-copy rewards): the last CTA to finish writes done_epoch there after
-    // every reward has been made visible system-wide; the host polls it instead of waiting for the stream to drain
-    unsigned int *done_host;    // nullptr: not requested
-    unsigned int *done_ctr;     // device counter of finished CTAs (left at 0)
-    unsigned int done_epoch;
 };
 constexpr int kIdSlice = 128;  // ids per slice: one 16-byte load per lane
 
@@ -880,17 +875,6 @@ __global__ void __launch_bounds__((MODE == MODE_PREDICT && SPLIT && !ADAPTIVE ? 
         __syncwarp();  // ring_off of the freshly staged footprints is visible to every lane
     }
     if (kTmaStore) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory must outlive the bulk stores reading it
-    if (bp.done_host != nullptr) {
-        __threadfence_system();  // this thread's rewards (mapped host memory) and status before the CTA's arrival
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (atomicAdd(bp.done_ctr, 1u) == gridDim.x - 1) {
-                *bp.done_ctr = 0u;
-                __threadfence_system();
-                *(volatile unsigned int *)bp.done_host = bp.done_epoch;
-            }
-        }
-    }
 }
 
 }  // namespace ipp

@@ -268,14 +268,6 @@ class BatchedEngine:
         """steps whose action ids the kernel fetched from the caller's pinned buffer itself"""
         return int(self._lib.ipp_get_option(self._h, capi.OPT_IDS_FETCH_STEPS))
 
-    @property
-    def polled_steps(self) -> int:
-        """steps that returned on the kernel's completion word instead of a stream synchronisation"""
-        return int(self._lib.ipp_get_option(self._h, capi.OPT_POLLED_STEPS))
-
-    def set_poll_done(self, on: bool = True) -> None:
-        self._ck(self._lib.ipp_set_option(self._h, capi.OPT_POLL_DONE, 1 if on else 0))
-
     # -- reset / world -------------------------------------------------------------------------
     def reset(self, prior_mean: float = 0.5, prior_var: float = 1.82, prior_var_per_env=None, init_pose=None) -> None:
         pv = None if prior_var_per_env is None else _f32(prior_var_per_env, (self.batch,))

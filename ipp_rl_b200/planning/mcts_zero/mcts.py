@@ -203,6 +203,14 @@ class BatchedMCTS:
         self._ck(self._lib.ipp_mcts_simulate_end(self._h, _ptr(pw), _ptr(pd), _ptr(v), _ptr(rn), 0))
         return leaf
 
+    def paths(self):
+        """(actions, rewards) of the simulation in flight — callable from an evaluator: action ids root -> leaf (-1 padded)
+        and the rewards of their prediction steps, both (n_trees, max_path)."""
+        P = self.info.max_path
+        a, r = np.empty((self.n_trees, P), np.int32), np.empty((self.n_trees, P), np.float32)
+        self._ck(self._lib.ipp_mcts_get_paths(self._h, _ptr(a), _ptr(r)))
+        return a, r
+
     def root_stats(self) -> Dict[str, np.ndarray]:
         T, W = self.n_trees, self.window_slots
         ps, qsa = np.empty((T, W), np.float32), np.empty((T, W), np.float32)

@@ -67,6 +67,50 @@ def test_rollout_matches_chained_oracle_steps(layout, adaptive, reward_mode):
             assert abs(r[j, k] - ro) <= tol, (j, k, r[j, k], ro)
 
 
+@pytest.mark.parametrize("layout", [0, 3, 4])
+@pytest.mark.parametrize("adaptive,reward_mode", [(False, 0), (True, 0), (False, 1)])
+def test_memoised_search_rollouts_equal_whole_path_rollouts(layout, adaptive, reward_mode):
+    """The search memoises prediction steps (an edge keeps its reward, a node the variances its step left behind) and computes only
+    the path's new step per simulation.  Every simulation's path rewards must be, bit for bit, what the whole-path rollout kernel
+    (ipp_rollout: every step replayed from the env's belief, pinned against the oracle above) returns for the same paths."""
+    from ipp_rl_b200.planning.mcts_zero import BatchedMCTS
+
+    X = Y = 40
+    params = make_params(X, Y, 1.0, 8, 20, 6, kappa=0.3, thr=0.5)
+    T, S = 48, 40
+    rng = np.random.RandomState(8)
+    mean0 = rng.uniform(0, 1, (T, Y, X)).astype(np.float32)
+    var0 = rng.uniform(0.05, 2.0, (T, Y, X)).astype(np.float32)
+    hyper = dict(puct_init=4.0, puct_base=10000, num_mcts_simulations=S, gamma=0.95, dirichlet_alpha=0.3, dirichlet_eps=0.0,
+                 forced_playout_factor=2.0, max_valid_action_distance=7.5)
+    prev = np.stack([rng.randint(2, X - 2, T) + 0.5, rng.randint(2, Y - 2, T) + 0.5, rng.choice([8.0, 14.0, 20.0], T)], axis=1)
+    budgets = rng.uniform(10.0, 60.0, T).astype(np.float32)  # small budgets too: paths that end on terminal edges are revisited
+    checked = [0, 0]
+    with _engine(params, T, layout=layout) as eng:
+        eng.reset(0.5, 1.0)
+        eng.set_state(mean0, var0)
+        meta = dict(episode_horizon=4, scenario_info={"adaptive": True} if adaptive else None)  # any scenario_info = adaptive mission
+        with BatchedMCTS(eng, hyper, meta, reward_mode=reward_mode) as mcts:
+            def ev(leaf):
+                acts, rew = mcts.paths()
+                whole = eng.rollout(acts, env_index=np.arange(T, dtype=np.int32), prev_poses=prev, reward_mode=reward_mode, adaptive=adaptive)
+                for t in range(T):
+                    n = int(leaf.path_len[t])
+                    assert np.all(acts[t, :n] >= 0) and np.all(acts[t, n:] < 0)
+                    assert np.array_equal(rew[t, :n], whole[t, :n]), (t, n, rew[t, :n], whole[t, :n])
+                    checked[0] += n
+                    checked[1] = max(checked[1], n)
+                prior = np.random.RandomState(int(leaf.depth.sum()) + 1).uniform(0.01, 1.0, (T, mcts.window_slots)).astype(np.float32)
+                return prior, np.full(T, 0.1, np.float32)
+
+            mcts.begin(budgets, prev)
+            for _ in range(S):
+                mcts.simulate(ev)
+        m1, v1 = eng.get_state()
+    assert np.array_equal(m1, mean0) and np.array_equal(v1, var0)
+    assert checked[0] > 3 * T * S // 2 and checked[1] >= 3, checked  # deep paths were exercised
+
+
 def _dense_stub_evaluator(mcts, root_prev, budget0, num_actions, res, altitudes):
     def ev(leaf):
         pri = np.zeros((mcts.n_trees, num_actions), np.float32)

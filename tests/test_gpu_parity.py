@@ -338,10 +338,9 @@ def test_zero_copy_host_buffers_are_bit_identical_to_the_copy_path(layout, B):
     rng = np.random.RandomState(5)
     gt = np.stack([smooth_field(rng, (64, 64)) for _ in range(8)]).astype(np.float32)[rng.randint(0, 8, B)]
     results = {}
-    for mode in ("copy", "r", "ri", "rf", "rfp"):  # p: return on the kernel's completion word instead of a stream synchronisation
+    for mode in ("copy", "r", "ri", "rf"):
         with _engine(params, B, layout=layout, seed=99) as eng:
             eng.set_zero_copy(rewards="r" in mode, ids="i" in mode, ids_fetch="f" in mode)
-            eng.set_poll_done("p" in mode)
             eng.reset()
             eng.set_ground_truth(gt)
             idrng = np.random.RandomState(17)
@@ -359,9 +358,8 @@ def test_zero_copy_host_buffers_are_bit_identical_to_the_copy_path(layout, B):
                     rs.append(out_pin.numpy().copy())
             assert eng.zero_copy_steps == (0 if mode == "copy" else 4)
             assert eng.ids_fetch_steps == (4 if "f" in mode and layout in (3, 4) else 0)
-            assert eng.polled_steps == (4 if "p" in mode and layout in (3, 4) else 0)
             results[mode] = (np.stack(rs),) + eng.get_state()
-    for mode in ("r", "ri", "rf", "rfp"):
+    for mode in ("r", "ri", "rf"):
         for a, b in zip(results["copy"], results[mode]):
             assert np.array_equal(a, b), mode
 

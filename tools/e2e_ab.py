@@ -18,14 +18,13 @@ ids = torch.from_numpy(rng.randint(0, eng.num_actions, size=(64, B)).astype(np.i
 out = torch.empty(B, dtype=torch.float32).pin_memory()
 ids_np, out_np = ids.numpy(), out.numpy()
 rows = [ids_np[k] for k in range(64)]
-MODES = {"copy ids, sync": (False, False), "copy ids, poll": (False, True), "fetch ids, sync": (True, False), "fetch ids, poll": (True, True)}
+MODES = {"copy ids": (False, False), "fetch ids": (True, False)}
 res = {k: [] for k in MODES}
 N, REPS = 300, 5
 with torch.cuda.stream(stream):
     for rep in range(REPS):
         for name, (fetch, poll) in MODES.items():
             eng.set_zero_copy(rewards=True, ids=False, ids_fetch=fetch)
-            eng.set_poll_done(poll)
             for t in range(10):
                 eng.step(rows[t], reward_mode=capi.REWARD_TRACE, out=out_np)
             t0 = time.perf_counter()

@@ -2,7 +2,7 @@
 slower than native, so the sizes are tiny but cover: all five layouts, the three step kernels (bulk / cp.async / LSU), both
 reward modes, the adaptive mask, host noise + measurement read-back, clipped / corner footprints, predict (persistent and
 job-list), path rollouts, the lock-step MCTS kernels (memoised rollouts), eval, observe, GRF / field / prior reset, the host step
-with pinned buffers (ids fetched by the persistent kernel, rewards written in place, completion word).
+with pinned buffers (ids fetched by the persistent kernel, rewards written in place).
 
     compute-sanitizer --tool racecheck python tools/sanitize_small.py
 """
@@ -41,8 +41,7 @@ def main():
                         eng.step(ids, noise=noise, reward_mode=t & 1, adaptive=True, return_measurements=True)
                     else:
                         eng.step(ids, reward_mode=t & 1, adaptive=(t == 3))
-                for poll in (False, True):  # pinned host buffers: ids fetched by the kernel (bulk path), rewards in place
-                    eng.set_poll_done(poll)
+                for rep in range(2):  # pinned host buffers: ids fetched by the kernel (bulk path), rewards in place
                     ids_pin[:] = rng.randint(0, eng.num_actions, B)
                     eng.step(ids_pin, out=out_pin)
                 eng.predict(rng.randint(0, eng.num_actions, B).astype(np.int32), commit=True)
