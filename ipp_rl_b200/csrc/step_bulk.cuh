@@ -197,6 +197,11 @@ __device__ __forceinline__ void sts64(uint32_t a, float x, float y) { asm volati
 // staged runs in shared memory and writes them back with one bulk store per tile row (whole 64-byte tiles: full-line writes from
 // the TMA unit instead of 8-byte scattered stores from every lane).  Measured at C3: 57.5 us per launch against 56.6 us with
 // the per-lane stores (the write-back is not bound by store transactions; +33 % bytes for the cells around the footprint).
+// IPP_BULK_NOSTORE (experiment switch): the full step on super-tiles computes everything and skips the write-back (wrong results:
+// timing probe only) — what do the stores cost?
+#ifndef IPP_BULK_NOSTORE
+#define IPP_BULK_NOSTORE 0
+#endif
 #ifndef IPP_BULK_PREDICT_TMASTORE
 #define IPP_BULK_PREDICT_TMASTORE 0
 #endif
@@ -807,7 +812,8 @@ __global__ void __launch_bounds__((MODE == MODE_PREDICT && SPLIT && !ADAPTIVE ? 
     #pragma unroll
                         for (int k = 0; k < 4; ++k) mn[k] = m[k];
                     }
-                    if (MODE != MODE_PREDICT || commit) {
+                    if (IPP_BULK_NOSTORE != 0) acc += 1.0e-30f * ((mn[0] + mn[1]) + (mn[2] + mn[3]));  // keep the mean update alive
+                    if ((IPP_BULK_NOSTORE == 0) && (MODE != MODE_PREDICT || commit)) {
                         if (odd) {
                             st_row2(go, mn[0], vn[0]);
                             if (cok) st_row2(go + dCg, mn[1], vn[1]);
