@@ -3,9 +3,10 @@
 // (simulate_begin, simulate_end) pair:
 //
 //   mcts_select_kernel   PUCT descent root -> leaf (compute_uct incl. forced playouts at the root,
-//                        planning/mcts_zero/mcts.py:280-296), creation of the child of a new edge
-//   mcts_rollout_kernel  reward of the path's NEW prediction step; the steps above it were rolled out when their edges
-//                        were created: an edge caches its reward, a node the variances its step left behind (overlay)
+//                        planning/mcts_zero/mcts.py:280-296), creation of the child of a new edge, and — same launch,
+//                        mcts_rollout_body — the reward of the path's NEW prediction step; the steps above it were rolled
+//                        out when their edges were created: an edge caches its reward, a node the variances its step left
+//                        behind (overlay)
 //   -- evaluator call-out (policy/value network; not part of this library) --
 //   mcts_expand_kernel   mask + normalise the leaf's priors (mcts.py:196-237), back the value up
 //                        (mcts.py:248-265)
@@ -34,6 +35,13 @@ using namespace ipp;
 namespace {
 
 constexpr int kTreeWarps = 4;  // trees per CTA
+// experiment switches (measured in DESIGN.md section 9)
+#ifndef IPP_MCTS_PUCT_TABLE
+#define IPP_MCTS_PUCT_TABLE 1  // exploration constant and sqrt(Ns + 1) of compute_uct from a table by visit count: 0.0710 -> 0.0673 ms
+#endif
+#ifndef IPP_MCTS_EDGE_CACHE
+#define IPP_MCTS_EDGE_CACHE 0  // a tree's edge pool read once per simulation into the lanes' registers (<= 128 edges): 10 % SLOWER
+#endif                         // (0.0780 vs 0.0710 ms per simulation: 20 more live registers per lane), kept as a switch
 
 struct TreeDims {
     int T, M, W, D, r, L, H;  // trees, nodes per tree, window slots, window width, radius, levels, episode horizon
@@ -65,6 +73,7 @@ struct TreeArrays {
     int *path_action;  // [T][max_path]  (-1 padded)
     float *path_reward;  // [T][max_path]
     int *leaf;           // [T][IPP_MCTS_LEAF_WORDS]
+    float2 *puct;        // [M + 1]  {exploration constant, sqrt(Ns + 1)} of compute_uct by node visit count (mcts.py:282-284)
     float *overlay;      // [T][M][tile]  variances of a node's footprint after its prediction step (row-major, pitch = its nx)
     int tile;            // floats per overlay (largest footprint)
 };
@@ -106,6 +115,31 @@ __device__ __forceinline__ int warp_argmax_lowest_slot(float value, int slot, fl
     return __ffs(__ballot_sync(0xffffffffu, k == kmax && slot == best_slot)) - 1;
 }
 
+// Per-lane best (largest prior >= 0, lowest slot among equals) of a node's prior row, 16-byte loads over the aligned middle of the
+// row (rows start at any 4-byte offset: W is not a multiple of 4).
+__device__ __forceinline__ void best_prior_scan(const float *P, int W, int lane, float &bp, int &bs) {
+    auto take = [&](float pr, int s) {
+        if (pr >= 0.0f && (pr > bp || (pr == bp && s < bs))) {
+            bp = pr;
+            bs = s;
+        }
+    };
+    const int head = min(W, (int)((4u - (unsigned)(((uintptr_t)P >> 2) & 3u)) & 3u));
+    const int nvec = (W - head) >> 2;
+    if (lane < head) take(P[lane], lane);
+    const float4 *P4 = reinterpret_cast<const float4 *>(P + head);
+    for (int v = lane; v < nvec; v += 32) {
+        const float4 q = P4[v];
+        const int s0 = head + 4 * v;
+        take(q.x, s0);
+        take(q.y, s0 + 1);
+        take(q.z, s0 + 2);
+        take(q.w, s0 + 3);
+    }
+    const int tail0 = head + 4 * nvec;
+    if (tail0 + lane < W) take(P[tail0 + lane], tail0 + lane);
+}
+
 struct Slot {
     int lvl, col, row;
     bool in_grid;
@@ -130,7 +164,16 @@ __device__ __forceinline__ void slot_pose(const StepParams &p, const Slot &c, do
 // ------------------------------------------------------------------------------------------------
 // selection: one warp walks one tree from the root to a leaf
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a) {
+template <int LAYOUT>
+__device__ __forceinline__ void mcts_rollout_body(const StepParams &p, const TreeDims &d, const TreeArrays &a, uint32_t flags, int t, int lane,
+                                                  int4 *s_rect_w, int *s_node_w);
+
+// The rollout of the path's new prediction step (mcts_rollout_body, below) runs at the end of the same launch: it needs nothing
+// but the path this warp has just walked, and its memory latency hides under the other warps' descents.
+template <int LAYOUT>
+__global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a, uint32_t flags) {
+    __shared__ int4 s_rect[kTreeWarps][IPP_MCTS_MAX_PATH];  // {xl, yu, nx, ny} of the nodes on the path (rollout)
+    __shared__ int s_node[kTreeWarps][IPP_MCTS_MAX_PATH];
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * kTreeWarps + (threadIdx.x >> 5);
     if (t >= d.T) return;
@@ -138,6 +181,25 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
     int node = 0, depth = 0, len = 0, kind = IPP_MCTS_LEAF_TERMINAL;
     int ccol = 0, crow = 0, lvl = -1;
     float budget = 0.0f;
+    // The tree's edges do not change while the warp walks down (a new edge ends the descent): when they fit the lanes' registers
+    // (<= 32 * kEdgeCache edges: one 16-byte load {parent, slot, prior, q} + the visit count per edge) they are read ONCE per
+    // simulation and every level filters them by parent; larger pools are scanned in two passes per level.
+    constexpr int kEdgeCache = 4;
+    Edge *edges = a.edges + (size_t)t * d.E;
+    const int ne = a.n_edges[t];
+    const bool cached = (IPP_MCTS_EDGE_CACHE != 0) && ne <= 32 * kEdgeCache;
+    int4 ea[kEdgeCache];
+    int en[kEdgeCache];
+#pragma unroll
+    for (int i = 0; i < kEdgeCache; ++i) {
+        const int e = lane + 32 * i;
+        ea[i] = make_int4(-2, 0, 0, 0);  // parent -2: no node
+        en[i] = 0;
+        if (cached && e < ne) {
+            ea[i] = *reinterpret_cast<const int4 *>(edges + e);
+            en[i] = edges[e].n;
+        }
+    }
     while (true) {
         const int4 h = hdr[node];
         unpack_pos(h.x, ccol, crow, lvl);
@@ -154,35 +216,58 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             break;
         }
         float *P = a.P + ((size_t)t * d.M + node) * d.W;
-        Edge *edges = a.edges + (size_t)t * d.E;
-        const int ne = a.n_edges[t];
         // normalize_q_values (mcts.py:267-278) over the dense action vector: every action that is not an edge has Q = 0
         float qmin = 0.0f, qmax = 0.0f;
-        for (int e = lane; e < ne; e += 32) {
-            if (edges[e].parent != node) continue;
-            const float q = edges[e].q;
-            qmin = fminf(qmin, q);
-            qmax = fmaxf(qmax, q);
+        if (cached) {
+#pragma unroll
+            for (int i = 0; i < kEdgeCache; ++i) {
+                if (ea[i].x == node) {
+                    const float q = __int_as_float(ea[i].w);
+                    qmin = fminf(qmin, q);
+                    qmax = fmaxf(qmax, q);
+                }
+            }
+        } else {
+            for (int e = lane; e < ne; e += 32) {
+                if (edges[e].parent != node) continue;
+                const float q = edges[e].q;
+                qmin = fminf(qmin, q);
+                qmax = fmaxf(qmax, q);
+            }
         }
         qmin = fkey_inv(__reduce_min_sync(0xffffffffu, fkey(qmin)));
         qmax = fkey_inv(__reduce_max_sync(0xffffffffu, fkey(qmax)));
         const float qscale = qmax > qmin ? 1.0f / (qmax - qmin) : 0.0f;  // all zero -> values unchanged (= 0)
         // compute_uct (mcts.py:280-296): the node's edges, then its best unvisited action (Q = N = 0)
+#if IPP_MCTS_PUCT_TABLE
+        const float2 pt = a.puct[Ns];  // {c_init + log((Ns + c_base + 1) / c_base), sqrt(Ns + 1)}: a visit count is at most M
+        const float prior_c = pt.x, sq = pt.y;
+#else
         const float prior_c = d.c_init + logf(((float)Ns + d.c_base + 1.0f) / d.c_base);
         const float sq = sqrtf((float)Ns + 1.0f);
+#endif
         const bool force = depth == 0;
         float best = -INFINITY;
         int best_s = 0x7fffffff, best_e = -1;
-        for (int e = lane; e < ne; e += 32) {
-            const Edge ed = edges[e];
-            if (ed.parent != node) continue;
-            const float n = (float)ed.n;
-            float u = (ed.q - qmin) * qscale + prior_c * ed.prior * (sq / (1.0f + n));
-            if (force && n > 0.0f && n < ceilf(sqrtf(d.forced_k * ed.prior * (float)Ns))) u = INFINITY;
-            if (u > best || (u == best && ed.slot < best_s)) {
+        auto consider = [&](int e, int slot, float prior, float q, int visits) {
+            const float n = (float)visits;
+            float u = (q - qmin) * qscale + prior_c * prior * (sq / (1.0f + n));
+            if (force && n > 0.0f && n < ceilf(sqrtf(d.forced_k * prior * (float)Ns))) u = INFINITY;
+            if (u > best || (u == best && slot < best_s)) {
                 best = u;
-                best_s = ed.slot;
+                best_s = slot;
                 best_e = e;
+            }
+        };
+        if (cached) {
+#pragma unroll
+            for (int i = 0; i < kEdgeCache; ++i)
+                if (ea[i].x == node) consider(lane + 32 * i, ea[i].y, __int_as_float(ea[i].z), __int_as_float(ea[i].w), en[i]);
+        } else {
+            for (int e = lane; e < ne; e += 32) {
+                const Edge ed = edges[e];
+                if (ed.parent != node) continue;
+                consider(e, ed.slot, ed.prior, ed.q, ed.n);
             }
         }
         const int2 bu = a.bu[(size_t)t * d.M + node];
@@ -213,13 +298,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             __syncwarp();
             float bp = -1.0f;
             int bs = 0x7fffffff;
-            for (int s = lane; s < d.W; s += 32) {
-                const float pr = P[s];
-                if (pr >= 0.0f && pr > bp) {  // strict: the lowest slot among equal priors stays
-                    bp = pr;
-                    bs = s;
-                }
-            }
+            best_prior_scan(P, d.W, lane, bp, bs);
             warp_argmax_lowest_slot(bp, bs, bp, bs);
             if (lane == 0) a.bu[(size_t)t * d.M + node] = make_int2(bp >= 0.0f ? bs : -1, __float_as_int(bp));
         } else {
@@ -286,6 +365,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
         lf[6] = __float_as_int(budget);
         lf[7] = len;
     }
+    __syncwarp();  // the path and the leaf record written by lane 0 are read by every lane below
+    mcts_rollout_body<LAYOUT>(p, d, a, flags, t, lane, s_rect[threadIdx.x >> 5], s_node[threadIdx.x >> 5]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -300,13 +381,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
 // visited before (terminal edges) cost nothing.  Same arithmetic as ipp_rollout_kernel (rollout_kernel.cuh): bit-identical
 // rewards, hence identical trees.
 template <int LAYOUT>
-__global__ void __launch_bounds__(kTreeWarps * 32) mcts_rollout_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a, uint32_t flags) {
-    __shared__ int4 s_rect[kTreeWarps][IPP_MCTS_MAX_PATH];  // {xl, yu, nx, ny} of the nodes on the path
-    __shared__ int s_node[kTreeWarps][IPP_MCTS_MAX_PATH];
-
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int t = blockIdx.x * kTreeWarps + wib;
-    if (t >= d.T) return;
+__device__ __forceinline__ void mcts_rollout_body(const StepParams &p, const TreeDims &d, const TreeArrays &a, uint32_t flags, int t, int lane,
+                                                  int4 *s_rect_w /* [IPP_MCTS_MAX_PATH] */, int *s_node_w /* [IPP_MCTS_MAX_PATH] */) {
     const int *lf = a.leaf + (size_t)t * IPP_MCTS_LEAF_WORDS;
     const int len = lf[7];
     if (len == 0) return;
@@ -330,8 +406,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_rollout_kernel(const __g
             decode_id(p, pa[lane], lvl, col, row);
             Geom g;
             clip_footprint(p, col, row, p.lut[lvl].rx, p.lut[lvl].ry, g);
-            s_rect[wib][lane] = make_int4(g.xl, g.yu, g.nx, g.ny);
-            s_node[wib][lane] = ed.child;
+            s_rect_w[lane] = make_int4(g.xl, g.yu, g.nx, g.ny);
+            s_node_w[lane] = ed.child;
         }
     }
     last_cached = __shfl_sync(0xffffffffu, last_cached, len - 1);
@@ -370,7 +446,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_rollout_kernel(const __g
         int src = -1;  // >= 0: overlay of that path node; -1: belief; -2: mixed
         int4 rc = make_int4(0, 0, 0, 0);
         for (int s = k - 1; s >= 0; --s) {
-            rc = s_rect[wib][s];
+            rc = s_rect_w[s];
             const int dx0 = C0 - rc.x, dy0 = R0 - rc.y, dx1 = dx0 + (cok ? 1 : 0), dy1 = dy0 + (rok ? 1 : 0);
             const bool in_x0 = (unsigned)dx0 < (unsigned)rc.z, in_x1 = (unsigned)dx1 < (unsigned)rc.z;
             const bool in_y0 = (unsigned)dy0 < (unsigned)rc.w, in_y1 = (unsigned)dy1 < (unsigned)rc.w;
@@ -384,7 +460,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_rollout_kernel(const __g
             }
         }
         if (src >= 0) {
-            const float *tl = ov + (size_t)s_node[wib][src] * a.tile + (R0 - rc.y) * rc.z + (C0 - rc.x);
+            const float *tl = ov + (size_t)s_node_w[src] * a.tile + (R0 - rc.y) * rc.z + (C0 - rc.x);
             v[0] = __ldcg(tl);
             if (cok) v[1] = __ldcg(tl + 1);
             if (rok) v[2] = __ldcg(tl + rc.z);
@@ -413,10 +489,10 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_rollout_kernel(const __g
                 const int R = R0 + (c >> 1), C = C0 + (c & 1);
                 bool found = false;
                 for (int s = k - 1; s >= 0 && !found; --s) {
-                    const int4 r4 = s_rect[wib][s];
+                    const int4 r4 = s_rect_w[s];
                     const int dx = C - r4.x, dy = R - r4.y;
                     if ((unsigned)dx < (unsigned)r4.z && (unsigned)dy < (unsigned)r4.w) {
-                        v[c] = __ldcg(ov + (size_t)s_node[wib][s] * a.tile + dy * r4.z + dx);
+                        v[c] = __ldcg(ov + (size_t)s_node_w[s] * a.tile + dy * r4.z + dx);
                         found = true;
                     }
                 }
@@ -534,15 +610,32 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
             const float uniform = 1.0f / (float)n_valid;
             float bp = -1.0f;  // best (largest prior, lowest slot) action: the node's first unvisited candidate
             int bs = 0x7fffffff;
-            for (int s = lane; s < d.W; s += 32) {
-                float pr = P[s];
-                if (pr < 0.0f) continue;
-                pr = total > 0.0f ? pr * scale : uniform;
-                P[s] = pr;
-                if (pr > bp) {
-                    bp = pr;
-                    bs = s;
+            {  // in place, 16-byte accesses over the aligned middle of the row
+                const bool use_scale = total > 0.0f;
+                auto norm = [&](float pr, int s) -> float {
+                    if (pr < 0.0f) return pr;
+                    pr = use_scale ? pr * scale : uniform;
+                    if (pr > bp || (pr == bp && s < bs)) {
+                        bp = pr;
+                        bs = s;
+                    }
+                    return pr;
+                };
+                const int head = min(d.W, (int)((4u - (unsigned)(((uintptr_t)P >> 2) & 3u)) & 3u));
+                const int nvec = (d.W - head) >> 2;
+                if (lane < head) P[lane] = norm(P[lane], lane);
+                float4 *P4 = reinterpret_cast<float4 *>(P + head);
+                for (int v = lane; v < nvec; v += 32) {
+                    float4 q = P4[v];
+                    const int s0 = head + 4 * v;
+                    q.x = norm(q.x, s0);
+                    q.y = norm(q.y, s0 + 1);
+                    q.z = norm(q.z, s0 + 2);
+                    q.w = norm(q.w, s0 + 3);
+                    P4[v] = q;
                 }
+                const int tail0 = head + 4 * nvec;
+                if (tail0 + lane < d.W) P[tail0 + lane] = norm(P[tail0 + lane], tail0 + lane);
             }
             warp_argmax_lowest_slot(bp, bs, bp, bs);
             if (lane == 0) {
@@ -552,16 +645,29 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
             value = values ? values[t] : 0.0f;
         }
     }
-    // backup (mcts.py:248-265), deepest edge first
-    if (lane == 0) {
-        for (int k = len - 1; k >= 0; --k) {
-            value = a.path_reward[(size_t)t * d.max_path + k] + d.gamma * value;
-            Edge *ed = a.edges + (size_t)t * d.E + a.path_edge[(size_t)t * d.max_path + k];
-            const int visits = ed->n;
-            ed->q = visits > 0 ? ((float)visits * ed->q + value) / (float)(visits + 1) : value;
-            ed->n = visits + 1;
-            hdr[ed->parent].z += 1;
-        }
+    // backup (mcts.py:248-265), deepest edge first.  Lane k owns edge k of the path: the loads (reward, edge, parent header) of all
+    // levels are in flight at once, the discounted sum runs down the path through shuffles, every lane writes its own edge back
+    // (the edges of a path have distinct parents).
+    float r_k = 0.0f, q_k = 0.0f;
+    int n_k = 0, z_k = 0, parent_k = 0;
+    Edge *ed = nullptr;
+    if (lane < len) {
+        r_k = a.path_reward[(size_t)t * d.max_path + lane];
+        ed = a.edges + (size_t)t * d.E + a.path_edge[(size_t)t * d.max_path + lane];
+        n_k = ed->n;
+        q_k = ed->q;
+        parent_k = ed->parent;
+        z_k = hdr[parent_k].z;
+    }
+    float mine = 0.0f;
+    for (int k = len - 1; k >= 0; --k) {  // warp-uniform
+        value = __shfl_sync(0xffffffffu, r_k, k) + d.gamma * value;
+        if (lane == k) mine = value;
+    }
+    if (lane < len) {
+        ed->q = n_k > 0 ? ((float)n_k * q_k + mine) / (float)(n_k + 1) : mine;
+        ed->n = n_k + 1;
+        hdr[parent_k].z = z_k + 1;
     }
 }
 
@@ -605,6 +711,12 @@ __global__ void mcts_root_export_kernel(const __grid_constant__ StepParams p, Tr
         if (nsa) nsa[o] = ed.n;
     }
     if (ns && threadIdx.x == 0) ns[t] = h.z;
+}
+
+// the visit-count dependent factors of compute_uct (mcts.py:280-296), tabulated once per search object
+__global__ void puct_table_kernel(float2 *tab, int n, float c_init, float c_base) {
+    const int Ns = blockIdx.x * blockDim.x + threadIdx.x;
+    if (Ns < n) tab[Ns] = make_float2(c_init + logf(((float)Ns + c_base + 1.0f) / c_base), sqrtf((float)Ns + 1.0f));
 }
 
 __global__ void iota_kernel(int *out, int n, int first) {
@@ -729,7 +841,9 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
     a.tile = 1;
     for (int k = 0; k < info.num_altitude_levels; ++k)
         a.tile = std::max(a.tile, std::min(2 * info.radius_x[k] + 1, info.x_dim) * std::min(2 * info.radius_y[k] + 1, info.y_dim));
-    if ((rc = malloc_dev(m, &a.overlay, TM * (size_t)a.tile))) return bail(rc);
+    if ((rc = malloc_dev(m, &a.overlay, TM * (size_t)a.tile)) || (rc = malloc_dev(m, &a.puct, (size_t)d.M + 1))) return bail(rc);
+    puct_table_kernel<<<(d.M + 256) / 256, 256, 0, m->stream>>>(a.puct, d.M + 1, d.c_init, d.c_base);
+    m->launches++;
     iota_kernel<<<(d.T + 255) / 256, 256, 0, m->stream>>>(m->d_env_index, d.T, d.first_env);
     m->launches++;
     if (cudaStreamSynchronize(m->stream) != cudaSuccess) return bail(mfail(m, IPP_ERR_CUDA, "ipp_mcts_create: device initialisation failed"));
@@ -793,19 +907,17 @@ extern "C" int ipp_mcts_simulate_begin(ipp_mcts *m, int32_t *leaf_info) {
     if (m->simulations >= m->cfg.num_simulations) return mfail(m, IPP_ERR_INVALID, "ipp_mcts_simulate_begin: node capacity (num_simulations) used up");
     const TreeDims &d = m->d;
     const int blocks = (d.T + kTreeWarps - 1) / kTreeWarps;
-    mcts_select_kernel<<<blocks, kTreeWarps * 32, 0, m->stream>>>(m->sp, d, m->a);
-    m->launches++;
-    MCU(m, cudaGetLastError());
-    // reward of the path's new prediction step (the steps above it are cached in their edges); the belief is only read
+    // PUCT descent + the reward of the path's new prediction step (the steps above it are cached in their edges); the belief
+    // is only read
     {
         const uint32_t fl = m->cfg.step_flags & (IPP_REWARD_MASK | IPP_FLAG_ADAPTIVE);
         const int layout = ipp_internal_layout(m->env);
         void (*kern)(const StepParams, TreeDims, TreeArrays, uint32_t) =
-            layout == IPP_LAYOUT_TILED   ? mcts_rollout_kernel<IPP_LAYOUT_TILED>
-            : layout == IPP_LAYOUT_SUPER ? mcts_rollout_kernel<IPP_LAYOUT_SUPER>
-            : layout == IPP_LAYOUT_SPLIT ? mcts_rollout_kernel<IPP_LAYOUT_SPLIT>
-            : layout == IPP_LAYOUT_MV    ? mcts_rollout_kernel<IPP_LAYOUT_MV>
-                                         : mcts_rollout_kernel<IPP_LAYOUT_PLANES>;
+            layout == IPP_LAYOUT_TILED   ? mcts_select_kernel<IPP_LAYOUT_TILED>
+            : layout == IPP_LAYOUT_SUPER ? mcts_select_kernel<IPP_LAYOUT_SUPER>
+            : layout == IPP_LAYOUT_SPLIT ? mcts_select_kernel<IPP_LAYOUT_SPLIT>
+            : layout == IPP_LAYOUT_MV    ? mcts_select_kernel<IPP_LAYOUT_MV>
+                                         : mcts_select_kernel<IPP_LAYOUT_PLANES>;
         kern<<<blocks, kTreeWarps * 32, 0, m->stream>>>(m->sp, d, m->a, fl);
         m->launches++;
         MCU(m, cudaGetLastError());

@@ -216,7 +216,7 @@ def test_batched_search_matches_oracle_on_a_deeper_problem():
             for _ in range(hyper["num_mcts_simulations"]):
                 mcts.simulate(ev)
             st = mcts.root_stats()
-            assert mcts.launches >= 3 * hyper["num_mcts_simulations"]
+            assert mcts.launches >= 2 * hyper["num_mcts_simulations"]  # select (+ rollout) and expand per simulation
     exact = 0
     for t in range(T):
         o = morc.OracleMCTS(cfg, hyper, H, evaluator=lambda info: policy_of(info["previous_action"], np.float32(info["budget"])))
