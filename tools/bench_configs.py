@@ -27,8 +27,10 @@ CONFIGS = [
 K, W, POOL = 300, 10, 16
 stream = torch.cuda.Stream()
 for name, B, G, res, (amin, amax, asp), levels, mode, predict in CONFIGS:
+    # stepping engines on super-tiles, covariance-only (search) engines on the split layout
+    layout = capi.LAYOUT_SPLIT if predict else capi.LAYOUT_SUPER
     cfg = EngineConfig(batch=B, x_dim=G, y_dim=G, resolution=res, min_altitude=amin, max_altitude=amax, altitude_spacing=asp,
-                       layout=capi.LAYOUT_SUPER, seed=1, stream=stream.cuda_stream)
+                       layout=layout, seed=1, stream=stream.cuda_stream)
     with BatchedEngine(cfg) as eng, torch.cuda.stream(stream):
         eng.reset(0.5, 1.82)
         eng.synth_ground_truth(seed=3)
@@ -66,4 +68,4 @@ for name, B, G, res, (amin, amax, asp), levels, mode, predict in CONFIGS:
                           # the kernel that actually ran (launch counters), not the engine's path option
                           "kernel": ("ipp_step_bulk_kernel" + ("<MODE_PREDICT>" if predict else "")) if eng.path_launches("async") - la0 >= K
                           else ("ipp_step_kernel" + ("<MODE_PREDICT>" if predict else "")) if eng.path_launches("lsu") - ll0 >= K else "mixed",
-                          "state_bytes": eng.device_bytes}))
+                          "layout": "split" if predict else "super", "state_bytes": eng.device_bytes}))

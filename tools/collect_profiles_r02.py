@@ -62,9 +62,35 @@ if "tiled_bytes_per_launch" in tj:  # round-1 numbers of the cp.async kernel, ke
     tj["kernels"].setdefault("ipp_step_async_kernel:mv", {"bytes_per_launch": tj["mv_bytes_per_launch"], "commit": "bb84100 (round 1)", "how": tj.get("how", "")})
 json.dump(tj, open(tj_path, "w"), indent=1)
 
+# the covariance-only persistent kernel on the split layout (committing)
+pp = os.path.join(G, f"{tag}_traffic_predict_split.csv")
+if os.path.exists(pp):
+    shutil.copy(pp, os.path.join(P, f"{out}_traffic_predict_split.csv"))
+    m2 = defaultdict(list)
+    for r in rows(pp):
+        m2[r["Metric Name"]].append(val(r))
+    mean = lambda xs: sum(xs) / len(xs)
+    tj["kernels"]["ipp_step_bulk_kernel<MODE_PREDICT>:split"] = {
+        "read_bytes_per_launch": mean(m2["dram__bytes_read.sum"]), "write_bytes_per_launch": mean(m2["dram__bytes_write.sum"]),
+        "bytes_per_launch": mean(m2["dram__bytes_read.sum"]) + mean(m2["dram__bytes_write.sum"]),
+        "warp_instructions_per_launch": mean(m2["smsp__inst_executed.sum"]), "us_per_launch_under_ncu": mean(m2["gpu__time_duration.sum"]),
+        "commit": commit, "how": "ncu (same metrics) -k regex:ipp_step_bulk -s 114 -c 6 of tools/predict_probe.py split: committing whole-batch "
+                                 f"prediction steps, 65536 envs, mean of 6 launches; raw: profiles/{out}_traffic_predict_split.csv"}
+    json.dump(tj, open(tj_path, "w"), indent=1)
+rep2 = os.path.join(G, f"{tag}_predict_split.ncu-rep")
+if os.path.exists(rep2):
+    for tool, suffix, args in (("ncu_summary.py", "ncu_summary", []), ("ncu_lines.py", "hotlines", ["ipp_step_bulk_kernelILi1ELb0ELb0ELb0ELb1E", "60"])):
+        txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), rep2] + args, capture_output=True, text=True).stdout
+        open(os.path.join(P, f"{out}_predict_split_{suffix}.txt"), "w").write(txt)
+rep3 = os.path.join(G, f"{tag}_mcts_select.ncu-rep")
+if os.path.exists(rep3):
+    for tool, suffix, args in (("ncu_summary.py", "ncu_summary", []), ("ncu_lines.py", "hotlines", ["mcts_select_kernelILi4E", "50"])):
+        txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), rep3] + args, capture_output=True, text=True).stdout
+        open(os.path.join(P, f"{out}_mcts_select_{suffix}.txt"), "w").write(txt)
+
 # full capture of the step kernel
 rep = os.path.join(G, f"{tag}_bulk_step.ncu-rep")
-kern = "ipp_step_bulk_kernelILi0ELb0ELb0ELb0E"
+kern = "ipp_step_bulk_kernelILi0ELb0ELb0ELb0ELb0E"
 for tool, suffix, args in (("ncu_summary.py", "ncu_summary", []), ("ncu_lines.py", "hotlines", [kern, "90"]), ("ncu_groups_bulk.py", "groups", [kern, "65536"])):
     txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), rep] + args, capture_output=True, text=True).stdout
     open(os.path.join(P, f"{out}_bulk_step_{suffix}.txt"), "w").write(txt)
@@ -74,7 +100,7 @@ mm = defaultdict(lambda: defaultdict(list))
 for r in rows(os.path.join(G, f"{tag}_mcts_launches.csv")):
     mm[r["Kernel Name"].split("(")[0]][r["Metric Name"]].append(val(r))
 with open(os.path.join(P, f"{out}_mcts_launches.txt"), "w") as f:
-    f.write("# per launch, 16 384 trees, bench.py --mcts-sims 24 (search leg on a PLANES-layout engine); ncu --clock-control none, mean (max) over the launches\n")
+    f.write("# per launch, 16 384 trees, bench.py --mcts-sims 24 (search leg on the SPLIT-layout search engine; the rollout runs inside the select launch); ncu --clock-control none, mean (max) over the launches\n")
     for k, d in mm.items():
         f.write(f"{k}\n")
         for name, xs in d.items():
@@ -84,7 +110,10 @@ for src, dst in ((f"{tag}_bench.json", f"{out}_bench.json"), (f"{tag}_bench_k20.
                  (f"{tag}_sanitizer_memcheck.log", f"{out}_sanitizer_memcheck.log"), (f"{tag}_sanitizer_racecheck.log", f"{out}_sanitizer_racecheck.log"),
                  (f"{tag}_sanitizer_synccheck.log", f"{out}_sanitizer_synccheck.log"), (f"{tag}_sanitizer_memcheck.out", f"{out}_sanitizer_workload.out"),
                  (f"{tag}_pytest.log", f"{out}_pytest_gpu.log"), ("c9_predict_probe.log", f"{out}_predict_probe.txt"), ("c6_probe.log", f"{out}_e2e_probe.txt"),
-                 ("n2_bench.json", f"{out}_bench_2gpus.json")):
+                 ("n2_bench.json", f"{out}_bench_2gpus.json"), ("n8_bench.json", f"{out}_bench_8gpus.json"), ("n8_ref.json", f"{out}_bench_reference_arm_8gpus.json"),
+                 (f"{tag}_predict_probe_split.txt", f"{out}_predict_probe.txt"), (f"{tag}_predict_probe_super.txt", f"{out}_predict_probe_super.txt"),
+                 (f"{tag}_e2e_ab.txt", f"{out}_e2e_ab.txt"), (f"{tag}_mcts_probe.txt", f"{out}_mcts_probe.txt"),
+                 (f"{tag}_configs_throughput.jsonl", f"{out}_configs_throughput.jsonl")):
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 open(os.path.join(P, f"{out}_sass_opcodes.txt"), "w").write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_opcodes.py")], capture_output=True, text=True).stdout)
