@@ -161,7 +161,8 @@ def test_full_batch_predict_vs_oracle_and_lsu(layout):
         assert np.array_equal(fast.get_prev_pose(), ref.get_prev_pose())
 
 
-def test_mcts_full_size_sampled_trees_vs_oracle():
+@pytest.mark.parametrize("layout", [3, 4])
+def test_mcts_full_size_sampled_trees_vs_oracle(layout):
     """16 384 trees (BASELINE.json C4 per-GPU share) on the 200x200 / 3-altitude workload, uniform priors; 48 sampled trees
     against oracle.mcts_oracle (root visit counts and Q values)."""
     from ipp_rl_b200.planning.mcts_zero import BatchedMCTS
@@ -176,7 +177,7 @@ def test_mcts_full_size_sampled_trees_vs_oracle():
     T = 16384
     rng = np.random.RandomState(4)
     sample = np.sort(rng.choice(T, 48, replace=False))
-    with _engine(params, T, layout=3, seed=3) as eng:
+    with _engine(params, T, layout=layout, seed=3) as eng:
         eng.reset(0.5, 1.82)
         eng.synth_ground_truth(5)
         for _ in range(3):  # a non-trivial belief
