@@ -491,13 +491,17 @@ def run_ours(args, rank, world, local_rank):
                 ms_m = max_over_ranks(m0.elapsed_time(m1))
                 st = mcts.root_stats()
                 assert np.all(st["Ns"] == Sm - 1)
-                # algorithmic bytes of the search: 4 B per footprint cell of every prediction step (the variance it reads; mean
-                # footprint of the 3-altitude set, unclipped), one window row of priors written per expansion, 32 B per path edge
+                # algorithmic bytes of the memoised search: per COMPUTED prediction step (= new edge) its footprint's variance read and
+                # its overlay written (4 + 4 B per cell; mean footprint of the 3-altitude set, unclipped), one window row of priors
+                # written per expansion, 32 B per path edge walked.  `prediction_steps` counts what the reference computes for the
+                # same search: one simulate_prediction_step per level of every simulation (mcts.py:239-246).
                 mean_cells = float(cells_by_level.mean())
-                alg_mcts = 4.0 * mean_cells * edges + 4.0 * mcts.window_slots * expansions + 32.0 * edges
+                computed = int(mcts.info.edges)
+                alg_mcts = 8.0 * mean_cells * computed + 4.0 * mcts.window_slots * expansions + 32.0 * edges
                 mcts_res = {"trees_per_gpu": Tm, "simulations": Sm, "episode_horizon": 5, "window_slots": mcts.window_slots,
                             "tree_simulations_per_sec": world * Tm * Sm / (ms_m * 1e-3),
-                            "prediction_steps_per_sec": world * edges / (ms_m * 1e-3), "prediction_steps": edges, "expansions": expansions,
+                            "prediction_steps_per_sec": world * edges / (ms_m * 1e-3), "prediction_steps": edges,
+                            "prediction_steps_computed": computed, "expansions": expansions,
                             "ms_per_lockstep_simulation": ms_m / Sm, "gpu_launches": int(mcts.launches - l0),
                             "algorithmic_bytes": alg_mcts, "achieved_gbs": alg_mcts / (ms_m * 1e-3) / 1e9,
                             "tree_bytes_per_gpu": int(mcts.info.device_bytes),

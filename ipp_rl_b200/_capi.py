@@ -138,6 +138,7 @@ class ipp_mcts_info(C.Structure):
         ("simulations", C.c_int32),
         ("device_bytes", C.c_uint64),
         ("launches", C.c_uint64),
+        ("edges", C.c_uint64),
     ]
 
 

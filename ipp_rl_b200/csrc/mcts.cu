@@ -73,6 +73,9 @@ struct TreeArrays {
     int *path_action;  // [T][max_path]  (-1 padded)
     float *path_reward;  // [T][max_path]
     int *leaf;           // [T][IPP_MCTS_LEAF_WORDS]
+    const int *slot_info;   // [W]     slot -> level | a << 8 | b << 16 (window column / row index)
+    const float *slot_dist; // [L][W]  distance from a LATTICE node at level ln to slot s (valid when the lattice arithmetic is exact)
+    int tables_ok;
     float2 *puct;        // [M + 1]  {exploration constant, sqrt(Ns + 1)} of compute_uct by node visit count (mcts.py:282-284)
     float *overlay;      // [T][M][tile]  variances of a node's footprint after its prediction step (row-major, pitch = its nx)
     int tile;            // floats per overlay (largest footprint)
@@ -128,13 +131,20 @@ __device__ __forceinline__ void best_prior_scan(const float *P, int W, int lane,
     const int nvec = (W - head) >> 2;
     if (lane < head) take(P[lane], lane);
     const float4 *P4 = reinterpret_cast<const float4 *>(P + head);
-    for (int v = lane; v < nvec; v += 32) {
-        const float4 q = P4[v];
-        const int s0 = head + 4 * v;
-        take(q.x, s0);
-        take(q.y, s0 + 1);
-        take(q.z, s0 + 2);
-        take(q.w, s0 + 3);
+    for (int v0 = 0; v0 < nvec; v0 += 128) {  // four 16-byte groups per lane per pass, every load issued before the first compare
+        float4 q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j] = P4[min(v0 + lane + 32 * j, nvec - 1)];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = v0 + lane + 32 * j;
+            if (v >= nvec) continue;
+            const int s0 = head + 4 * v;
+            take(q[j].x, s0);
+            take(q[j].y, s0 + 1);
+            take(q[j].z, s0 + 2);
+            take(q[j].w, s0 + 3);
+        }
     }
     const int tail0 = head + 4 * nvec;
     if (tail0 + lane < W) take(P[tail0 + lane], tail0 + lane);
@@ -249,7 +259,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
         const bool force = depth == 0;
         float best = -INFINITY;
         int best_s = 0x7fffffff, best_e = -1;
-        auto consider = [&](int e, int slot, float prior, float q, int visits) {
+        int best_child = kNoNode, best_action = 0;  // of the lane's best edge: the winner's come along through shuffles, no second load
+        auto consider = [&](int e, int slot, float prior, float q, int visits, int child_, int action_) {
             const float n = (float)visits;
             float u = (q - qmin) * qscale + prior_c * prior * (sq / (1.0f + n));
             if (force && n > 0.0f && n < ceilf(sqrtf(d.forced_k * prior * (float)Ns))) u = INFINITY;
@@ -257,17 +268,21 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
                 best = u;
                 best_s = slot;
                 best_e = e;
+                best_child = child_;
+                best_action = action_;
             }
         };
         if (cached) {
 #pragma unroll
             for (int i = 0; i < kEdgeCache; ++i)
-                if (ea[i].x == node) consider(lane + 32 * i, ea[i].y, __int_as_float(ea[i].z), __int_as_float(ea[i].w), en[i]);
+                if (ea[i].x == node)
+                    consider(lane + 32 * i, ea[i].y, __int_as_float(ea[i].z), __int_as_float(ea[i].w), en[i], edges[lane + 32 * i].child,
+                             edges[lane + 32 * i].pad[0]);
         } else {
             for (int e = lane; e < ne; e += 32) {
                 const Edge ed = edges[e];
                 if (ed.parent != node) continue;
-                consider(e, ed.slot, ed.prior, ed.q, ed.n);
+                consider(e, ed.slot, ed.prior, ed.q, ed.n, ed.child, ed.pad[0]);
             }
         }
         const int2 bu = a.bu[(size_t)t * d.M + node];
@@ -282,6 +297,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
         {
             const int win = warp_argmax_lowest_slot(best, best_s, best, best_s);
             best_e = __shfl_sync(0xffffffffu, best_e, win);
+            best_child = __shfl_sync(0xffffffffu, best_child, win);
+            best_action = __shfl_sync(0xffffffffu, best_action, win);
         }
         int child = kNoNode;
         if (best_e < 0) {
@@ -302,14 +319,14 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             warp_argmax_lowest_slot(bp, bs, bp, bs);
             if (lane == 0) a.bu[(size_t)t * d.M + node] = make_int2(bp >= 0.0f ? bs : -1, __float_as_int(bp));
         } else {
-            child = edges[best_e].child;
+            child = best_child;
         }
         if (child != kNoNode) {
             // a visited edge whose child exists: its action id was cached when the child was created, the child's header has the
             // rest — no slot decode, no poses, no cost on the way down
             if (lane == 0) {
                 a.path_edge[(size_t)t * d.max_path + len] = best_e;
-                a.path_action[(size_t)t * d.max_path + len] = edges[best_e].pad[0];
+                a.path_action[(size_t)t * d.max_path + len] = best_action;
             }
             ++len;
             node = child;
@@ -568,6 +585,39 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
         int n_valid = 0;
         const double half_res = __dmul_rn(0.5, p.res);
         const int N = p.X * p.Y;
+        if (node != 0 && a.tables_ok) {
+            // a lattice node: geometry from the per-level slot tables (22 KB, cache resident), lanes over consecutive slots
+            const float *dist_row = a.slot_dist + (size_t)lvl * d.W;
+            // four slots per lane per pass, every load of a pass issued before the first use: a pass costs one memory round
+            // trip, not four (the evaluator's prior row streams from HBM; invalid slots are read too, then masked)
+            const float *prow = priors_window ? priors_window + (size_t)t * d.W : nullptr;
+            for (int s0 = 0; s0 < d.W; s0 += 128) {
+                int inf[4];
+                float dst[4], prv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sl = min(s0 + lane + 32 * j, d.W - 1);
+                    inf[j] = __ldg(a.slot_info + sl);
+                    dst[j] = __ldg(dist_row + sl);
+                    prv[j] = prow ? __ldg(prow + sl) : 1.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sl = s0 + lane + 32 * j;
+                    if (sl >= d.W) continue;
+                    const int l = inf[j] & 255, col = ccol + ((inf[j] >> 8) & 255) - d.r, row = crow + (inf[j] >> 16) - d.r;
+                    const float dist = dst[j];
+                    float pr = -1.0f;
+                    if (col >= 0 && col < p.X && row >= 0 && row < p.Y && dist > 0.0f && dist <= budget && dist < d.max_dist) {
+                        pr = (!prow && priors_dense) ? priors_dense[(size_t)t * num_actions + l * N + p.X * col + row] : prv[j];
+                        pr = fmaxf(pr, 0.0f);
+                        sum += pr;
+                        ++n_valid;
+                    }
+                    P[sl] = pr;
+                }
+            }
+        } else
         for (int b0 = 0; b0 < d.D; b0 += 32) {
             const int b = b0 + lane;
             const int row = crow + b - d.r;
@@ -625,14 +675,21 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
                 const int nvec = (d.W - head) >> 2;
                 if (lane < head) P[lane] = norm(P[lane], lane);
                 float4 *P4 = reinterpret_cast<float4 *>(P + head);
-                for (int v = lane; v < nvec; v += 32) {
-                    float4 q = P4[v];
-                    const int s0 = head + 4 * v;
-                    q.x = norm(q.x, s0);
-                    q.y = norm(q.y, s0 + 1);
-                    q.z = norm(q.z, s0 + 2);
-                    q.w = norm(q.w, s0 + 3);
-                    P4[v] = q;
+                for (int v0 = 0; v0 < nvec; v0 += 128) {  // four 16-byte groups per lane per pass, loads first
+                    float4 q[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) q[j] = P4[min(v0 + lane + 32 * j, nvec - 1)];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int v = v0 + lane + 32 * j;
+                        if (v >= nvec) continue;
+                        const int s0 = head + 4 * v;
+                        q[j].x = norm(q[j].x, s0);
+                        q[j].y = norm(q[j].y, s0 + 1);
+                        q[j].z = norm(q[j].z, s0 + 2);
+                        q[j].w = norm(q[j].w, s0 + 3);
+                        P4[v] = q[j];
+                    }
                 }
                 const int tail0 = head + 4 * nvec;
                 if (tail0 + lane < d.W) P[tail0 + lane] = norm(P[tail0 + lane], tail0 + lane);
@@ -711,6 +768,25 @@ __global__ void mcts_root_export_kernel(const __grid_constant__ StepParams p, Tr
         if (nsa) nsa[o] = ed.n;
     }
     if (ns && threadIdx.x == 0) ns[t] = h.z;
+}
+
+// Window geometry of a lattice node: slot -> (level, column, row) indices and its distance to the node, per node level.  Same
+// expressions as the expansion's general path (slot_pose / job_dist), evaluated at offsets: identical bits whenever res * cell
+// + res / 2 is exact in fp64 (resolutions with a float32 mantissa; checked by the host), so that pose differences depend on
+// the cell offsets only.
+__global__ void slot_table_kernel(TreeDims d, const StepParams p, int *info, float *dist) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= d.W) return;
+    const int DD = d.D * d.D;
+    const int l = s / DD, rem = s - l * DD, a_ = rem / d.D, b = rem - a_ * d.D;
+    info[s] = l | (a_ << 8) | (b << 16);
+    const float dx = (float)__dmul_rn(p.res, (double)(a_ - d.r));
+    const float dy = (float)__dmul_rn(p.res, (double)(b - d.r));
+    for (int ln = 0; ln < d.L; ++ln) {
+        const float dz = (float)(p.lut[l].alt - p.lut[ln].alt);
+        const float dyz = fmaf(dy, dy, dz * dz);
+        dist[(size_t)ln * d.W + s] = fast_sqrt(fmaf(dx, dx, dyz));
+    }
 }
 
 // the visit-count dependent factors of compute_uct (mcts.py:280-296), tabulated once per search object
@@ -844,6 +920,18 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
     if ((rc = malloc_dev(m, &a.overlay, TM * (size_t)a.tile)) || (rc = malloc_dev(m, &a.puct, (size_t)d.M + 1))) return bail(rc);
     puct_table_kernel<<<(d.M + 256) / 256, 256, 0, m->stream>>>(a.puct, d.M + 1, d.c_init, d.c_base);
     m->launches++;
+    {
+        int *info_tab = nullptr;
+        float *dist_tab = nullptr;
+        if ((rc = malloc_dev(m, &info_tab, (size_t)d.W)) || (rc = malloc_dev(m, &dist_tab, (size_t)d.L * d.W))) return bail(rc);
+        slot_table_kernel<<<(d.W + 255) / 256, 256, 0, m->stream>>>(d, m->sp, info_tab, dist_tab);
+        m->launches++;
+        a.slot_info = info_tab;
+        a.slot_dist = dist_tab;
+        // pose differences depend on cell offsets only when res * cell + res / 2 is exact in fp64: resolutions with a float32
+        // mantissa (24 bits + 12 bits of cell index); window indices must fit the 8-bit fields
+        a.tables_ok = (m->sp.res == (double)(float)m->sp.res) && d.D <= 255 && d.L <= 255 && getenv("IPP_MCTS_NO_TABLES") == nullptr;
+    }
     iota_kernel<<<(d.T + 255) / 256, 256, 0, m->stream>>>(m->d_env_index, d.T, d.first_env);
     m->launches++;
     if (cudaStreamSynchronize(m->stream) != cudaSuccess) return bail(mfail(m, IPP_ERR_CUDA, "ipp_mcts_create: device initialisation failed"));
@@ -873,6 +961,14 @@ extern "C" int ipp_mcts_get_info(const ipp_mcts *m, ipp_mcts_info *out) {
     out->simulations = m->simulations;
     out->device_bytes = m->device_bytes;
     out->launches = m->launches;
+    if (m->begun) {  // edges of all pools (a 4-byte counter per tree, read back on demand)
+        std::vector<int> ne((size_t)m->d.T);
+        if (cudaMemcpyAsync(ne.data(), m->a.n_edges, ne.size() * sizeof(int), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess &&
+            cudaStreamSynchronize(m->stream) == cudaSuccess)
+            for (int v : ne) out->edges += (uint64_t)v;
+        else
+            cudaGetLastError();
+    }
     return IPP_OK;
 }
 

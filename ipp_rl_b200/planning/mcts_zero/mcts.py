@@ -203,6 +203,14 @@ class BatchedMCTS:
         self._ck(self._lib.ipp_mcts_simulate_end(self._h, _ptr(pw), _ptr(pd), _ptr(v), _ptr(rn), 0))
         return leaf
 
+    def simulate_device(self, priors_window_ptr: int = 0, priors_dense_ptr: int = 0, values_ptr: int = 0, root_noise_ptr: int = 0) -> None:
+        """One lock-step simulation with the evaluator's outputs already in device memory (raw pointers, 0 = absent: uniform
+        priors / zero values): float32 (n_trees, window_slots) or (n_trees, num_actions) priors, (n_trees,) values.  Nothing
+        crosses the host: the form a GPU-resident policy / value network uses."""
+        self._ck(self._lib.ipp_mcts_simulate_begin(self._h, None))
+        vp = lambda p: C.c_void_p(p) if p else None  # noqa: E731
+        self._ck(self._lib.ipp_mcts_simulate_end(self._h, vp(priors_window_ptr), vp(priors_dense_ptr), vp(values_ptr), vp(root_noise_ptr), 1))
+
     def paths(self):
         """(actions, rewards) of the simulation in flight — callable from an evaluator: action ids root -> leaf (-1 padded)
         and the rewards of their prediction steps, both (n_trees, max_path)."""

@@ -106,9 +106,11 @@ def test_memoised_search_rollouts_equal_whole_path_rollouts(layout, adaptive, re
             mcts.begin(budgets, prev)
             for _ in range(S):
                 mcts.simulate(ev)
+            n_computed = int(mcts.info.edges)
         m1, v1 = eng.get_state()
     assert np.array_equal(m1, mean0) and np.array_equal(v1, var0)
     assert checked[0] > 3 * T * S // 2 and checked[1] >= 3, checked  # deep paths were exercised
+    assert 0 < n_computed <= T * (S - 1) < checked[0]  # at most one prediction step computed per simulation (the first expands the root)
 
 
 def _dense_stub_evaluator(mcts, root_prev, budget0, num_actions, res, altitudes):
