@@ -62,7 +62,9 @@ constexpr int kNoNode = -1;
 
 struct TreeArrays {
     int4 *hdr;       // [T][M]  {packed position, budget bits, Ns, depth | expanded << 8}
-    float *P;        // [T][M][W]  masked normalised priors; -1 invalid, -2 visited (prior moved into the edge)
+    float *P;        // [T][M][W]  masked priors BEFORE normalisation (policy * mask, root: mixed with the noise); -1 invalid, -2 visited
+                     //            (prior moved into the edge).  Normalised prior = P * pscale (mcts.py:228-234).
+    float *pscale;   // [T][M]     1 / sum of the node's row; negative: the row sums to 0 and every valid action has prior -pscale
     int2 *bu;        // [T][M]  best unvisited slot of the node {slot (-1: none), prior bits}
     Edge *edges;     // [T][E]
     int *n_edges;    // [T]
@@ -180,8 +182,13 @@ __device__ __forceinline__ void mcts_rollout_body(const StepParams &p, const Tre
 
 // The rollout of the path's new prediction step (mcts_rollout_body, below) runs at the end of the same launch: it needs nothing
 // but the path this warp has just walked, and its memory latency hides under the other warps' descents.
+#ifndef IPP_MCTS_SELECT_MINBLOCKS
+#define IPP_MCTS_SELECT_MINBLOCKS 8  // resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * this) = 64): 10 / 12 / 16 spill and are slower
+#endif
 template <int LAYOUT>
-__global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a, uint32_t flags) {
+__global__ void __launch_bounds__(kTreeWarps * 32, IPP_MCTS_SELECT_MINBLOCKS) mcts_select_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a, uint32_t flags,
+                                                                      int stage_edges) {
+    extern __shared__ int4 s_pool[];                        // [kTreeWarps][E][2]: the trees' edge pools (stage_edges != 0)
     __shared__ int4 s_rect[kTreeWarps][IPP_MCTS_MAX_PATH];  // {xl, yu, nx, ny} of the nodes on the path (rollout)
     __shared__ int s_node[kTreeWarps][IPP_MCTS_MAX_PATH];
     const int lane = threadIdx.x & 31;
@@ -197,6 +204,23 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
     constexpr int kEdgeCache = 4;
     Edge *edges = a.edges + (size_t)t * d.E;
     const int ne = a.n_edges[t];
+    // Experiment switch (stage_edges, off by default — see the launch site): the pool does not change while the warp walks down
+    // and every level scans all of it, so it can be copied into shared memory once per simulation.
+    const Edge *pool = edges;
+    if (stage_edges) {
+        int4 *mine = s_pool + (size_t)(threadIdx.x >> 5) * d.E * 2;
+        const int4 *src = reinterpret_cast<const int4 *>(edges);
+        for (int i0 = 0; i0 < 2 * ne; i0 += 128) {
+            int4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = src[min(i0 + lane + 32 * j, 2 * ne - 1)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + lane + 32 * j < 2 * ne) mine[i0 + lane + 32 * j] = v[j];
+        }
+        __syncwarp();
+        pool = reinterpret_cast<const Edge *>(mine);
+    }
     const bool cached = (IPP_MCTS_EDGE_CACHE != 0) && ne <= 32 * kEdgeCache;
     int4 ea[kEdgeCache];
     int en[kEdgeCache];
@@ -239,8 +263,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             }
         } else {
             for (int e = lane; e < ne; e += 32) {
-                if (edges[e].parent != node) continue;
-                const float q = edges[e].q;
+                if (pool[e].parent != node) continue;
+                const float q = pool[e].q;
                 qmin = fminf(qmin, q);
                 qmax = fmaxf(qmax, q);
             }
@@ -280,7 +304,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
                              edges[lane + 32 * i].pad[0]);
         } else {
             for (int e = lane; e < ne; e += 32) {
-                const Edge ed = edges[e];
+                const Edge ed = pool[e];
                 if (ed.parent != node) continue;
                 consider(e, ed.slot, ed.prior, ed.q, ed.n, ed.child, ed.pad[0]);
             }
@@ -317,7 +341,10 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_select_kernel(const __gr
             int bs = 0x7fffffff;
             best_prior_scan(P, d.W, lane, bp, bs);
             warp_argmax_lowest_slot(bp, bs, bp, bs);
-            if (lane == 0) a.bu[(size_t)t * d.M + node] = make_int2(bp >= 0.0f ? bs : -1, __float_as_int(bp));
+            if (lane == 0) {
+                const float sc = a.pscale[(size_t)t * d.M + node];  // rows hold unnormalised priors
+                a.bu[(size_t)t * d.M + node] = make_int2(bp >= 0.0f ? bs : -1, __float_as_int(bp >= 0.0f ? (sc > 0.0f ? bp * sc : -sc) : bp));
+            }
         } else {
             child = best_child;
         }
@@ -555,7 +582,10 @@ __device__ __forceinline__ void mcts_rollout_body(const StepParams &p, const Tre
 // ------------------------------------------------------------------------------------------------
 // expansion + backup
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a,
+#ifndef IPP_MCTS_EXPAND_MINBLOCKS
+#define IPP_MCTS_EXPAND_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(kTreeWarps * 32, IPP_MCTS_EXPAND_MINBLOCKS) mcts_expand_kernel(const __grid_constant__ StepParams p, TreeDims d, TreeArrays a,
                                                                       const float *priors_window, const float *priors_dense,
                                                                       const float *values, const float *root_noise, int num_actions) {
     const int lane = threadIdx.x & 31;
@@ -583,6 +613,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
         // even when costs are flight times (quirk, reproduced; the budget is decremented by the cost).
         float sum = 0.0f;
         int n_valid = 0;
+        float bp = -1.0f;  // best (largest prior, lowest slot) action of this lane's slots: the node's first unvisited candidate
+        int bs = 0x7fffffff;
         const double half_res = __dmul_rn(0.5, p.res);
         const int N = p.X * p.Y;
         if (node != 0 && a.tables_ok) {
@@ -613,6 +645,10 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
                         pr = fmaxf(pr, 0.0f);
                         sum += pr;
                         ++n_valid;
+                        if (pr > bp || (pr == bp && sl < bs)) {
+                            bp = pr;
+                            bs = sl;
+                        }
                     }
                     P[sl] = pr;
                 }
@@ -641,6 +677,10 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
                         sum += pr;
                         if (noisy) pr += d.dir_eps * root_noise[(size_t)t * d.W + sl];
                         ++n_valid;
+                        if (pr > bp || (pr == bp && sl < bs)) {
+                            bp = pr;
+                            bs = sl;
+                        }
                     }
                     if (b < d.D) P[sl] = pr;
                 }
@@ -655,49 +695,17 @@ __global__ void __launch_bounds__(kTreeWarps * 32) mcts_expand_kernel(const __gr
         if (n_valid > 0) {  // else: simulate() returns 0 and the node stays a leaf (mcts.py:197-199)
             // Ps /= sum(Ps) (mcts.py:228-234).  With exploration noise the sum runs over ALL actions, invalid ones
             // included (noise is added after masking, mcts.py:160-164,225-226): (1-eps) * sum_valid(p) + eps * 1.
+            // The row keeps the masked priors as they are; the node keeps 1 / sum (or, for a row that sums to 0, the uniform
+            // prior of its valid actions), and every reader scales: no second pass over the row.  The arg max is taken on the
+            // unscaled values (scaling is monotone; the reference compares in fp64, where distinct priors stay distinct).
             const float total = noisy ? sum + d.dir_eps : sum;
             const float scale = total > 0.0f ? 1.0f / total : 0.0f;
             const float uniform = 1.0f / (float)n_valid;
-            float bp = -1.0f;  // best (largest prior, lowest slot) action: the node's first unvisited candidate
-            int bs = 0x7fffffff;
-            {  // in place, 16-byte accesses over the aligned middle of the row
-                const bool use_scale = total > 0.0f;
-                auto norm = [&](float pr, int s) -> float {
-                    if (pr < 0.0f) return pr;
-                    pr = use_scale ? pr * scale : uniform;
-                    if (pr > bp || (pr == bp && s < bs)) {
-                        bp = pr;
-                        bs = s;
-                    }
-                    return pr;
-                };
-                const int head = min(d.W, (int)((4u - (unsigned)(((uintptr_t)P >> 2) & 3u)) & 3u));
-                const int nvec = (d.W - head) >> 2;
-                if (lane < head) P[lane] = norm(P[lane], lane);
-                float4 *P4 = reinterpret_cast<float4 *>(P + head);
-                for (int v0 = 0; v0 < nvec; v0 += 128) {  // four 16-byte groups per lane per pass, loads first
-                    float4 q[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) q[j] = P4[min(v0 + lane + 32 * j, nvec - 1)];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int v = v0 + lane + 32 * j;
-                        if (v >= nvec) continue;
-                        const int s0 = head + 4 * v;
-                        q[j].x = norm(q[j].x, s0);
-                        q[j].y = norm(q[j].y, s0 + 1);
-                        q[j].z = norm(q[j].z, s0 + 2);
-                        q[j].w = norm(q[j].w, s0 + 3);
-                        P4[v] = q[j];
-                    }
-                }
-                const int tail0 = head + 4 * nvec;
-                if (tail0 + lane < d.W) P[tail0 + lane] = norm(P[tail0 + lane], tail0 + lane);
-            }
             warp_argmax_lowest_slot(bp, bs, bp, bs);
             if (lane == 0) {
                 hdr[node] = make_int4(h.x, h.y, 0, (h.w & 0xFF) | (1 << 8));
-                a.bu[(size_t)t * d.M + node] = make_int2(bs, __float_as_int(bp));
+                a.pscale[(size_t)t * d.M + node] = total > 0.0f ? scale : -uniform;
+                a.bu[(size_t)t * d.M + node] = make_int2(bs, __float_as_int(total > 0.0f ? bp * scale : uniform));
             }
             value = values ? values[t] : 0.0f;
         }
@@ -747,11 +755,16 @@ __global__ void mcts_root_export_kernel(const __grid_constant__ StepParams p, Tr
     int ccol, crow, lvl;
     unpack_pos(h.x, ccol, crow, lvl);
     const bool expanded = ((h.w >> 8) & 1) != 0;
+    const float sc = a.pscale[(size_t)t * d.M];
     const size_t base = (size_t)t * d.M * d.W;
     for (int s = threadIdx.x; s < d.W; s += blockDim.x) {
         const Slot c = slot_cell(d, p, s, ccol, crow);
         const size_t o = (size_t)t * d.W + s;
-        if (ps) ps[o] = expanded ? a.P[base + s] : -1.0f;
+        if (ps) {
+            float pv = expanded ? a.P[base + s] : -1.0f;
+            if (pv >= 0.0f) pv = sc > 0.0f ? pv * sc : -sc;  // rows hold unnormalised priors
+            ps[o] = pv;
+        }
         if (qsa) qsa[o] = 0.0f;
         if (nsa) nsa[o] = 0;
         if (ids) ids[o] = c.in_grid ? c.lvl * (p.X * p.Y) + p.X * c.col + c.row : -1;
@@ -907,7 +920,7 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
     const size_t TM = (size_t)d.T * d.M, TMW = TM * d.W, TP = (size_t)d.T * d.max_path;
     int rc;
     TreeArrays &a = m->a;
-    if ((rc = malloc_dev(m, &a.hdr, TM)) || (rc = malloc_dev(m, &a.P, TMW)) || (rc = malloc_dev(m, &a.bu, TM)) ||
+    if ((rc = malloc_dev(m, &a.hdr, TM)) || (rc = malloc_dev(m, &a.P, TMW)) || (rc = malloc_dev(m, &a.pscale, TM)) || (rc = malloc_dev(m, &a.bu, TM)) ||
         (rc = malloc_dev(m, &a.edges, (size_t)d.T * d.E)) || (rc = malloc_dev(m, &a.n_edges, (size_t)d.T)) ||
         (rc = malloc_dev(m, &a.n_nodes, (size_t)d.T)) || (rc = malloc_dev(m, &a.root_pose, 3 * (size_t)d.T)) ||
         (rc = malloc_dev(m, &a.path_edge, TP)) || (rc = malloc_dev(m, &a.path_action, TP)) ||
@@ -1008,13 +1021,19 @@ extern "C" int ipp_mcts_simulate_begin(ipp_mcts *m, int32_t *leaf_info) {
     {
         const uint32_t fl = m->cfg.step_flags & (IPP_REWARD_MASK | IPP_FLAG_ADAPTIVE);
         const int layout = ipp_internal_layout(m->env);
-        void (*kern)(const StepParams, TreeDims, TreeArrays, uint32_t) =
+        void (*kern)(const StepParams, TreeDims, TreeArrays, uint32_t, int) =
             layout == IPP_LAYOUT_TILED   ? mcts_select_kernel<IPP_LAYOUT_TILED>
             : layout == IPP_LAYOUT_SUPER ? mcts_select_kernel<IPP_LAYOUT_SUPER>
             : layout == IPP_LAYOUT_SPLIT ? mcts_select_kernel<IPP_LAYOUT_SPLIT>
             : layout == IPP_LAYOUT_MV    ? mcts_select_kernel<IPP_LAYOUT_MV>
                                          : mcts_select_kernel<IPP_LAYOUT_PLANES>;
-        kern<<<blocks, kTreeWarps * 32, 0, m->stream>>>(m->sp, d, m->a, fl);
+        // experiment switch (IPP_MCTS_STAGE_EDGES=1): the trees' edge pools staged in shared memory once per simulation (they fit
+        // beside 8 resident CTAs per SM up to 192 edges per tree) — measured 1.5 % slower on growing trees (0.1940 vs 0.1907 ms per
+        // simulation): the scans' loads were not what the descent waits for
+        const size_t pool_bytes = (size_t)kTreeWarps * d.E * sizeof(Edge);
+        const char *st_env = getenv("IPP_MCTS_STAGE_EDGES");
+        const int stage = pool_bytes <= 24 * 1024 && st_env != nullptr && st_env[0] == '1';
+        kern<<<blocks, kTreeWarps * 32, stage ? pool_bytes : 0, m->stream>>>(m->sp, d, m->a, fl, stage);
         m->launches++;
         MCU(m, cudaGetLastError());
     }
