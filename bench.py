@@ -466,49 +466,66 @@ def run_ours(args, rank, world, local_rank):
             for t in range(4):
                 meng.step_device(action_ids_ptr=ids_dev[t % POOL].data_ptr(), reward_ptr=reward_dev.data_ptr(), reward_mode=capi.REWARD_TRACE)
             meng.sync()
+
+        def search_leg(mcts, pri, val, tag):
+            """Two passes of one search: host-synchronous to count its path edges / expansions (it is deterministic), then timed."""
+            step = (lambda leaf: mcts.simulate_device(priors_window_ptr=pri.data_ptr(), values_ptr=val.data_ptr(), want_leaf=leaf)) if pri is not None \
+                else (lambda leaf: mcts.simulate(lambda lf: (None, None)) if leaf else mcts.simulate(None))
+            mcts.begin(budgets)
+            edges, expansions = 0, 0
+            for i in range(Sm):
+                leaf = step(True)
+                edges += int(leaf.path_len.sum())
+                expansions += int(leaf.needs_eval.sum())
+            mcts.begin(budgets)
+            l0 = mcts.launches
+            barrier()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nvtx.range_push(tag)
+            m0.record(stream)
+            for i in range(Sm):
+                step(False)
+            m1.record(stream)
+            barrier()
+            nvtx.range_pop()
+            ms_m = max_over_ranks(m0.elapsed_time(m1))
+            launches = int(mcts.launches - l0)
+            st = mcts.root_stats()
+            assert np.all(st["Ns"] == Sm - 1)
+            # algorithmic bytes of the memoised search: per COMPUTED prediction step (= new edge) its footprint's variance read and
+            # its overlay written (4 + 4 B per cell; mean footprint of the 3-altitude set, unclipped), per expansion one row of
+            # evaluator priors read and one row of masked priors written, 32 B per path edge walked.  `prediction_steps` counts
+            # what the reference computes for the same search: one simulate_prediction_step per level of every simulation
+            # (mcts.py:239-246).
+            mean_cells = float(np.mean([float((2 * r + 1) ** 2) for r in radii]))
+            computed = int(mcts.info.edges)
+            alg = 8.0 * mean_cells * computed + (8.0 if pri is not None else 4.0) * mcts.window_slots * expansions + 32.0 * edges
+            return {"tree_simulations_per_sec": world * Tm * Sm / (ms_m * 1e-3), "ms_per_lockstep_simulation": ms_m / Sm,
+                    "prediction_steps_per_sec": world * edges / (ms_m * 1e-3), "prediction_steps": edges, "prediction_steps_computed": computed,
+                    "expansions": expansions, "edges_per_tree": computed / Tm, "gpu_launches": launches,
+                    "algorithmic_bytes": alg, "achieved_gbs": alg / (ms_m * 1e-3) / 1e9}
+
         with torch.cuda.stream(stream):
             with BatchedMCTS(meng, hyper, meta, n_trees=Tm) as mcts:
-                # pass 1 (untimed, host-synchronous): count the prediction steps / expansions of the search (it is deterministic)
-                mcts.begin(budgets)
-                edges, expansions, path_cells = 0, 0, 0.0
-                cells_by_level = np.array([float((2 * r + 1) ** 2) for r in radii])
-                for i in range(Sm):
-                    leaf = mcts.simulate(lambda lf: (None, None))
-                    edges += int(leaf.path_len.sum())
-                    expansions += int(leaf.needs_eval.sum())
-                # pass 2 (timed): device-only loop, CUDA events on the engine stream
-                mcts.begin(budgets)
-                l0 = mcts.launches
-                barrier()
-                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                nvtx.range_push("mcts")
-                m0.record(stream)
-                for i in range(Sm):
-                    mcts.simulate(None)
-                m1.record(stream)
-                barrier()
-                nvtx.range_pop()
-                ms_m = max_over_ranks(m0.elapsed_time(m1))
-                st = mcts.root_stats()
-                assert np.all(st["Ns"] == Sm - 1)
-                # algorithmic bytes of the memoised search: per COMPUTED prediction step (= new edge) its footprint's variance read and
-                # its overlay written (4 + 4 B per cell; mean footprint of the 3-altitude set, unclipped), one window row of priors
-                # written per expansion, 32 B per path edge walked.  `prediction_steps` counts what the reference computes for the
-                # same search: one simulate_prediction_step per level of every simulation (mcts.py:239-246).
-                mean_cells = float(cells_by_level.mean())
-                computed = int(mcts.info.edges)
-                alg_mcts = 8.0 * mean_cells * computed + 4.0 * mcts.window_slots * expansions + 32.0 * edges
-                mcts_res = {"trees_per_gpu": Tm, "simulations": Sm, "episode_horizon": 5, "window_slots": mcts.window_slots,
-                            "tree_simulations_per_sec": world * Tm * Sm / (ms_m * 1e-3),
-                            "prediction_steps_per_sec": world * edges / (ms_m * 1e-3), "prediction_steps": edges,
-                            "prediction_steps_computed": computed, "expansions": expansions,
-                            "ms_per_lockstep_simulation": ms_m / Sm, "gpu_launches": int(mcts.launches - l0),
-                            "algorithmic_bytes": alg_mcts, "achieved_gbs": alg_mcts / (ms_m * 1e-3) / 1e9,
-                            "tree_bytes_per_gpu": int(mcts.info.device_bytes),
-                            "layout": args.search_layout,
-                            "rollouts": "memoised: an edge caches its reward, a node the variances its prediction step left behind; a simulation "
-                                        "computes at most ONE prediction step (the reference replays one per level: prediction_steps counts those)",
-                            "evaluator": "uniform priors, zero values (network outside this library)"}
+                # (1) growing trees: synthetic network outputs resident in device memory — peaked priors (soft-max of random logits
+                #     per tree) and small random values: about one new edge, one rollout and one expansion per simulation, as under
+                #     a trained policy / value network;  (2) no evaluator: uniform priors, zero values — the search then exploits ONE
+                #     path per tree (6 edges after 100 simulations) and measures the descent / backup alone (round 1's configuration)
+                g = torch.Generator(device="cuda").manual_seed(5 + rank)
+                pri = torch.softmax(4.0 * torch.randn(Tm, mcts.window_slots, device="cuda", generator=g), dim=1).contiguous()
+                val = (0.05 * torch.rand(Tm, device="cuda", generator=g)).contiguous()
+                torch.cuda.synchronize()
+                mcts_res = {"trees_per_gpu": Tm, "simulations": Sm, "episode_horizon": 5, "window_slots": mcts.window_slots}
+                mcts_res.update(search_leg(mcts, pri, val, "mcts[growing]"))
+                mcts_res.update({
+                    "evaluator": "synthetic network outputs in device memory: soft-max(4 * N(0,1)) priors over the window, values U(0, 0.05) "
+                                 "(the policy / value network is outside this library)",
+                    "no_evaluator": dict(search_leg(mcts, None, None, "mcts[uniform]"),
+                                         evaluator="none: uniform priors, zero values (the search exploits one path per tree)"),
+                    "tree_bytes_per_gpu": int(mcts.info.device_bytes), "layout": args.search_layout,
+                    "rollouts": "memoised: an edge caches its reward, a node the variances its prediction step left behind; a simulation "
+                                "computes at most ONE prediction step (the reference replays one per level: prediction_steps counts those)"})
+                del pri, val
     if seng is not eng:
         seng.close()
 

@@ -203,13 +203,21 @@ class BatchedMCTS:
         self._ck(self._lib.ipp_mcts_simulate_end(self._h, _ptr(pw), _ptr(pd), _ptr(v), _ptr(rn), 0))
         return leaf
 
-    def simulate_device(self, priors_window_ptr: int = 0, priors_dense_ptr: int = 0, values_ptr: int = 0, root_noise_ptr: int = 0) -> None:
+    def _leaf_batch(self) -> "LeafBatch":
+        lf = self._leaf
+        return LeafBatch(kind=lf[:, 0].copy(), node=lf[:, 1].copy(), col=lf[:, 2].copy(), row=lf[:, 3].copy(), level=lf[:, 4].copy(),
+                         depth=lf[:, 5].copy(), budget=lf[:, 6].copy().view(np.float32), path_len=lf[:, 7].copy(), mcts=self)
+
+    def simulate_device(self, priors_window_ptr: int = 0, priors_dense_ptr: int = 0, values_ptr: int = 0, root_noise_ptr: int = 0,
+                        want_leaf: bool = False) -> Optional["LeafBatch"]:
         """One lock-step simulation with the evaluator's outputs already in device memory (raw pointers, 0 = absent: uniform
         priors / zero values): float32 (n_trees, window_slots) or (n_trees, num_actions) priors, (n_trees,) values.  Nothing
-        crosses the host: the form a GPU-resident policy / value network uses."""
-        self._ck(self._lib.ipp_mcts_simulate_begin(self._h, None))
+        crosses the host (unless ``want_leaf`` asks for the leaf records): the form a GPU-resident policy / value network uses."""
+        self._ck(self._lib.ipp_mcts_simulate_begin(self._h, _ptr(self._leaf) if want_leaf else None))
+        leaf = self._leaf_batch() if want_leaf else None
         vp = lambda p: C.c_void_p(p) if p else None  # noqa: E731
         self._ck(self._lib.ipp_mcts_simulate_end(self._h, vp(priors_window_ptr), vp(priors_dense_ptr), vp(values_ptr), vp(root_noise_ptr), 1))
+        return leaf
 
     def paths(self):
         """(actions, rewards) of the simulation in flight — callable from an evaluator: action ids root -> leaf (-1 padded)
