@@ -82,11 +82,12 @@ if os.path.exists(rep2):
     for tool, suffix, args in (("ncu_summary.py", "ncu_summary", []), ("ncu_lines.py", "hotlines", ["ipp_step_bulk_kernelILi1ELb0ELb0ELb0ELb1E", "60"])):
         txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), rep2] + args, capture_output=True, text=True).stdout
         open(os.path.join(P, f"{out}_predict_split_{suffix}.txt"), "w").write(txt)
-rep3 = os.path.join(G, f"{tag}_mcts_select.ncu-rep")
-if os.path.exists(rep3):
-    for tool, suffix, args in (("ncu_summary.py", "ncu_summary", []), ("ncu_lines.py", "hotlines", ["mcts_select_kernelILi4E", "50"])):
-        txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), rep3] + args, capture_output=True, text=True).stdout
-        open(os.path.join(P, f"{out}_mcts_select_{suffix}.txt"), "w").write(txt)
+for kname, mangled in (("select", "mcts_select_kernelILi4E"), ("expand", "mcts_expand_kernel")):
+    rep3 = os.path.join(G, f"{tag}_mcts_{kname}.ncu-rep")
+    if os.path.exists(rep3):
+        for tool, suffix, args in (("ncu_summary.py", "ncu_summary", []), ("ncu_lines.py", "hotlines", [mangled, "50"])):
+            txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), rep3] + args, capture_output=True, text=True).stdout
+            open(os.path.join(P, f"{out}_mcts_{kname}_{suffix}.txt"), "w").write(txt)
 
 # full capture of the step kernel
 rep = os.path.join(G, f"{tag}_bulk_step.ncu-rep")
@@ -100,7 +101,7 @@ mm = defaultdict(lambda: defaultdict(list))
 for r in rows(os.path.join(G, f"{tag}_mcts_launches.csv")):
     mm[r["Kernel Name"].split("(")[0]][r["Metric Name"]].append(val(r))
 with open(os.path.join(P, f"{out}_mcts_launches.txt"), "w") as f:
-    f.write("# per launch, 16 384 trees, bench.py --mcts-sims 24 (search leg on the SPLIT-layout search engine; the rollout runs inside the select launch); ncu --clock-control none, mean (max) over the launches\n")
+    f.write("# per launch, 16 384 growing trees (tools/mcts_probe.py split 100 peaked: the 100 simulations of the first search; the rollout runs inside the select launch); ncu --clock-control none, mean (max) over the launches\n")
     for k, d in mm.items():
         f.write(f"{k}\n")
         for name, xs in d.items():

@@ -18,14 +18,18 @@ timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
   --log-file $O/${T}_traffic_predict_split.csv python tools/predict_probe.py split > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ipp_step_bulk -s 116 -c 1 -f -o $O/${T}_predict_split \
   python tools/predict_probe.py split > $O/${T}_ncu_predict.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mcts_select -s 150 -c 1 -f -o $O/${T}_mcts_select \
-  python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 2 --mcts-sims 100 > /dev/null 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct --clock-control none -k regex:"mcts_|rollout" -c 120 --csv --log-file $O/${T}_mcts_launches.csv \
-   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 2 --mcts-sims 24 > /dev/null 2>&1
+# the search kernels on growing trees (simulation 60 of tools/mcts_probe.py ... peaked)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mcts_select -s 60 -c 1 -f -o $O/${T}_mcts_select \
+  python tools/mcts_probe.py split 100 peaked > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mcts_expand -s 60 -c 1 -f -o $O/${T}_mcts_expand \
+  python tools/mcts_probe.py split 100 peaked > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct --clock-control none -k regex:"mcts_(select|expand)" -c 200 --csv --log-file $O/${T}_mcts_launches.csv \
+   python tools/mcts_probe.py split 100 peaked > /dev/null 2>&1
 timeout 300 python tools/predict_probe.py split > $O/${T}_predict_probe_split.txt 2>&1
 timeout 300 python tools/predict_probe.py super > $O/${T}_predict_probe_super.txt 2>&1
 timeout 300 python tools/e2e_ab.py > $O/${T}_e2e_ab.txt 2>&1
-timeout 300 python tools/mcts_probe.py split > $O/${T}_mcts_probe.txt 2>&1
+timeout 300 python tools/mcts_probe.py split 100 uniform > $O/${T}_mcts_probe.txt 2>&1
+timeout 300 python tools/mcts_probe.py split 100 peaked >> $O/${T}_mcts_probe.txt 2>&1
 timeout 600 python tools/bench_configs.py > $O/${T}_configs_throughput.jsonl 2>&1
 python bench.py --impl reference --steps 5 --warmup 3 > $O/${T}_bench_ref.json 2>/dev/null; cut -c1-200 $O/${T}_bench_ref.json
 python bench.py --steps 20 --warmup 5 > $O/${T}_bench_k20.json 2> $O/${T}_bench_k20.err; cut -c1-200 $O/${T}_bench_k20.json
