@@ -58,6 +58,31 @@ def test_ctypes_structs_match_the_header(tmp_path):
                      _capi.ipp_ring_info.pushed.offset]
 
 
+def test_header_constants_match_the_ctypes_module():
+    """Every numeric #define of the headers that _capi mirrors (layouts, flags, options, zero-copy bits, pointers) has the same
+    value on both sides — a renumbered option would otherwise go unnoticed until a GPU run."""
+    import re
+
+    from ipp_rl_b200 import _capi
+
+    defines = {}
+    for h in HEADERS:
+        for m in re.finditer(r"^#define\s+(IPP_[A-Z0-9_]+)\s+(-?\d+)u?\b", open(h).read(), re.M):
+            defines[m.group(1)] = int(m.group(2))
+    assert defines["IPP_LAYOUT_SPLIT"] == 4 and len(defines) > 30
+    checked = 0
+    for name, value in vars(_capi).items():
+        if not name.isupper() or not isinstance(value, int) or isinstance(value, bool):
+            continue
+        for cname in ("IPP_" + name, "IPP_FLAG_" + name.replace("FLAG_", ""), "IPP_" + name.replace("MCTS_", "MCTS_")):
+            if cname in defines:
+                assert defines[cname] == value, (name, cname, value, defines[cname])
+                checked += 1
+                break
+    assert checked >= 25, checked
+    assert _capi.LAYOUT_NAMES == {"planes": 0, "mv": 1, "tiled": 2, "super": 3, "split": 4}
+
+
 def test_missing_library_fails_loudly(tmp_path):
     from ipp_rl_b200 import _capi
 
