@@ -74,12 +74,12 @@ def test_header_constants_match_the_ctypes_module():
     for name, value in vars(_capi).items():
         if not name.isupper() or not isinstance(value, int) or isinstance(value, bool):
             continue
-        for cname in ("IPP_" + name, "IPP_FLAG_" + name.replace("FLAG_", ""), "IPP_" + name.replace("MCTS_", "MCTS_")):
+        for cname in (name, "IPP_" + name):
             if cname in defines:
                 assert defines[cname] == value, (name, cname, value, defines[cname])
                 checked += 1
                 break
-    assert checked >= 25, checked
+    assert checked >= 50, checked
     assert _capi.LAYOUT_NAMES == {"planes": 0, "mv": 1, "tiled": 2, "super": 3, "split": 4}
 
 
