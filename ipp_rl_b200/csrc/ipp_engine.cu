@@ -347,14 +347,58 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, c
     auto mo = [&](size_t b) -> size_t { return split ? b + (b & ~(size_t)15) : b * es; };
     auto gi_of = [&](size_t i) -> size_t { return tiled ? tiled_gt_index_rt(d.txg, d.ts_gt, d.gw_shift, (int)(i / d.X), (int)(i % d.X)) : i; };
 
+    // Rows of whole 4-cell groups (x_dim % 4 == 0): a thread takes four consecutive cells of a row — contiguous in every layout
+    // (a tile row is four cells) — with 16-byte loads and no per-cell index arithmetic; any other width goes cell by cell.
+    const bool vec = (d.X & 3) == 0;
+    const int X4 = d.X >> 2, nvec = d.Y * X4;
+    auto load4 = [&](int R, int C0, float (&gv)[4], float (&mvv)[4], float (&vv)[4]) {
+        if (layout == IPP_LAYOUT_PLANES) {
+            const size_t k = (size_t)R * d.X + C0;
+            const float4 g4 = *reinterpret_cast<const float4 *>(g + k), m4 = *reinterpret_cast<const float4 *>(m + k),
+                         v4 = *reinterpret_cast<const float4 *>(v + k);
+            gv[0] = g4.x, gv[1] = g4.y, gv[2] = g4.z, gv[3] = g4.w;
+            mvv[0] = m4.x, mvv[1] = m4.y, mvv[2] = m4.z, mvv[3] = m4.w;
+            vv[0] = v4.x, vv[1] = v4.y, vv[2] = v4.z, vv[3] = v4.w;
+            return;
+        }
+        const size_t kb = tiled ? tiled_mv_index_rt(d.txm, d.ts_mv, R, C0) : (size_t)R * d.X + C0;
+        const size_t kg = tiled ? tiled_gt_index_rt(d.txg, d.ts_gt, d.gw_shift, R, C0) : (size_t)R * d.X + C0;
+        const float4 g4 = *reinterpret_cast<const float4 *>(g + kg);
+        gv[0] = g4.x, gv[1] = g4.y, gv[2] = g4.z, gv[3] = g4.w;
+        if (split) {
+            const float4 m4 = *reinterpret_cast<const float4 *>(m + mo(kb)), v4 = *reinterpret_cast<const float4 *>(v + kb);
+            mvv[0] = m4.x, mvv[1] = m4.y, mvv[2] = m4.z, mvv[3] = m4.w;
+            vv[0] = v4.x, vv[1] = v4.y, vv[2] = v4.z, vv[3] = v4.w;
+        } else {  // interleaved {mean, var}
+            const float4 t0 = *reinterpret_cast<const float4 *>(m + 2 * kb), t1 = *reinterpret_cast<const float4 *>(m + 2 * kb + 4);
+            mvv[0] = t0.x, vv[0] = t0.y, mvv[1] = t0.z, vv[1] = t0.w, mvv[2] = t1.x, vv[2] = t1.y, mvv[3] = t1.z, vv[3] = t1.w;
+        }
+    };
+
     // pass 1: min(gt), min(mean), max(gt), sum(gt)
     double a[4] = {1e300, 1e300, -1e300, 0.0};
-    for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
-        const double gi = g[gi_of(i)], mi = m[mo(bi(i))];
-        a[0] = fmin(a[0], gi);
-        a[1] = fmin(a[1], mi);
-        a[2] = fmax(a[2], gi);
-        a[3] += gi;
+    if (vec) {
+        for (int i = threadIdx.x; i < nvec; i += kEvalThreads) {
+            const int R = i / X4, C0 = (i - R * X4) << 2;
+            float gv[4], mvv[4], vv[4];
+            load4(R, C0, gv, mvv, vv);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double gi = gv[c], mi = mvv[c];
+                a[0] = fmin(a[0], gi);
+                a[1] = fmin(a[1], mi);
+                a[2] = fmax(a[2], gi);
+                a[3] += gi;
+            }
+        }
+    } else {
+        for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
+            const double gi = g[gi_of(i)], mi = m[mo(bi(i))];
+            a[0] = fmin(a[0], gi);
+            a[1] = fmin(a[1], mi);
+            a[2] = fmax(a[2], gi);
+            a[3] += gi;
+        }
     }
     block_reduce<4>(a, smem, true, true);
     const double gmin = a[0], mmin = a[1], gmax = a[2], gsum = a[3];
@@ -364,9 +408,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, c
 
     // pass 2
     double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
-        const size_t b = bi(i);
-        const double gi = g[gi_of(i)], mi = m[mo(b)], vi = v[b * es];
+    auto accumulate = [&](double gi, double mi, double vi) {
         const double sq = (gi - mi) * (gi - mi);
         const double w = ((gi - mmin) / range) / wsum;
         const double ll = 0.5 * log(2.0 * 3.141592653589793 * vi) + sq / 2.0 * vi;  // (:44) multiplies by P_ii
@@ -380,6 +422,20 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const float *mean, c
         s[6] += in ? 0.0 : vi;
         s[7] += in ? 1.0 : 0.0;
         s[8] += in ? sq : 0.0;
+    };
+    if (vec) {
+        for (int i = threadIdx.x; i < nvec; i += kEvalThreads) {
+            const int R = i / X4, C0 = (i - R * X4) << 2;
+            float gv[4], mvv[4], vv[4];
+            load4(R, C0, gv, mvv, vv);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) accumulate((double)gv[c], (double)mvv[c], (double)vv[c]);
+        }
+    } else {
+        for (size_t i = threadIdx.x; i < plane; i += kEvalThreads) {
+            const size_t b = bi(i);
+            accumulate((double)g[gi_of(i)], (double)m[mo(b)], (double)v[b * es]);
+        }
     }
     block_reduce<10>(s, smem, false, false);
     if (threadIdx.x == 0) {

@@ -164,3 +164,28 @@ def test_device_shuffled_priors(layout):
     a = rng.normal(0.3, 0.3, (X * Y, X * Y))
     d = np.einsum("ij,ij->i", a, a) / np.linalg.norm(a)
     assert abs(d.mean() - np.sqrt(2) * 0.3) < 0.01 and abs(d.std() / d.mean() - np.sqrt(6.0 / (X * Y)) / 2) < 0.01
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", [0, 1, 2, 3, 4])
+def test_observation_planes_vector_path_equals_generic_path(layout, monkeypatch):
+    """The 16-byte path of ipp_observe (x_dim % 4 == 0) writes the bits of the one-cell-per-thread kernel: all six planes, with
+    and without the adaptive mask, poses on and off the lattice."""
+    params = make_params(48, 40, 1.0, 8, 20, 6, kappa=0.3, thr=0.5)
+    B = 6
+    rng = np.random.RandomState(3)
+    mean0 = rng.uniform(0, 1, (B, 40, 48)).astype(np.float32)
+    var0 = rng.uniform(0.05, 2.0, (B, 40, 48)).astype(np.float32)
+    poses = np.stack([rng.uniform(0, 48, B), rng.uniform(0, 40, B), rng.choice([8.0, 14.0, 20.0], B)], axis=1)
+    budget = rng.uniform(0.1, 1.0, B).astype(np.float32)
+    with _engine(params, B, layout=layout) as eng:
+        eng.reset(0.5, 1.0)
+        eng.set_state(mean0, var0)
+        for adaptive in (False, True):
+            fast = eng.observe(0, B, poses=poses, budget_ratio=budget, adaptive=adaptive)
+            monkeypatch.setenv("IPP_OBS_GENERIC", "1")
+            slow = eng.observe(0, B, poses=poses, budget_ratio=budget, adaptive=adaptive)
+            monkeypatch.delenv("IPP_OBS_GENERIC")
+            assert fast.shape == (B, 6, 40, 48) and np.array_equal(fast, slow), adaptive
+            five = eng.observe(0, B, poses=poses, budget_ratio=budget, adaptive=adaptive, action_costs=False)
+            assert np.array_equal(five, fast[:, :5])
