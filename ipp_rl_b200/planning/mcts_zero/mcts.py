@@ -222,7 +222,7 @@ class BatchedMCTS:
     def paths(self):
         """(actions, rewards) of the simulation in flight — callable from an evaluator: action ids root -> leaf (-1 padded)
         and the rewards of their prediction steps, both (n_trees, max_path)."""
-        P = self.info.max_path
+        P = self.max_path
         a, r = np.empty((self.n_trees, P), np.int32), np.empty((self.n_trees, P), np.float32)
         self._ck(self._lib.ipp_mcts_get_paths(self._h, _ptr(a), _ptr(r)))
         return a, r
