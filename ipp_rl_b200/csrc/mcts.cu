@@ -45,6 +45,7 @@ constexpr int kTreeWarps = 4;  // trees per CTA
 
 struct TreeDims {
     int T, M, W, D, r, L, H;  // trees, nodes per tree, window slots, window width, radius, levels, episode horizon
+    int Wp;                   // W rounded up to whole 16-byte groups: stride of a node's prior row and of the slot tables
     int E;                    // edge-pool capacity per tree
     int max_path;             // H + 1
     int first_env;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, IPP_MCTS_SELECT_MINBLOCKS) mc
             kind = IPP_MCTS_LEAF_EVAL;
             break;
         }
-        float *P = a.P + ((size_t)t * d.M + node) * d.W;
+        float *P = a.P + ((size_t)t * d.M + node) * d.Wp;
         // normalize_q_values (mcts.py:267-278) over the dense action vector: every action that is not an edge has Q = 0
         float qmin = 0.0f, qmax = 0.0f;
         if (cached) {
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, IPP_MCTS_EXPAND_MINBLOCKS) mc
         const float budget = __int_as_float(h.y);
         double nx, ny, nh;
         node_pose(p, a, t, node, ccol, crow, lvl, nx, ny, nh);
-        float *P = a.P + ((size_t)t * d.M + node) * d.W;
+        float *P = a.P + ((size_t)t * d.M + node) * d.Wp;
         const bool noisy = node == 0 && root_noise != nullptr && d.dir_eps > 0.0f;
         // get_next_actions_mask (mcts.py:148-158) and policy * mask (mcts.py:220).  Slot s = (lvl * D + a) * D + b is the cell
         // (ccol + a - r, crow + b - r) at altitude level lvl: lanes run over b, the warp over (lvl, a), so the column part of
@@ -620,38 +621,52 @@ __global__ void __launch_bounds__(kTreeWarps * 32, IPP_MCTS_EXPAND_MINBLOCKS) mc
         const int N = p.X * p.Y;
         if (node != 0 && a.tables_ok) {
             // a lattice node: geometry from the per-level slot tables (22 KB, cache resident), lanes over consecutive slots
-            const float *dist_row = a.slot_dist + (size_t)lvl * d.W;
-            // four slots per lane per pass, every load of a pass issued before the first use: a pass costs one memory round
-            // trip, not four (the evaluator's prior row streams from HBM; invalid slots are read too, then masked)
+            const float4 *dist_row = reinterpret_cast<const float4 *>(a.slot_dist + (size_t)lvl * d.Wp);
+            const int4 *info_row = reinterpret_cast<const int4 *>(a.slot_info);
+            // a lane takes four consecutive slots (one 16-byte group of the tables and of the node's row), two groups per pass with
+            // every load issued before the first use (the evaluator's prior row streams from HBM at any 4-byte alignment: scalar
+            // loads; invalid slots are read too, then masked)
             const float *prow = priors_window ? priors_window + (size_t)t * d.W : nullptr;
-            for (int s0 = 0; s0 < d.W; s0 += 128) {
-                int inf[4];
-                float dst[4], prv[4];
+            const int nv = d.Wp >> 2;
+            float4 *P4 = reinterpret_cast<float4 *>(P);
+            for (int v0 = 0; v0 < nv; v0 += 64) {
+                int4 inf[2];
+                float4 dst[2];
+                float prv[2][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int sl = min(s0 + lane + 32 * j, d.W - 1);
-                    inf[j] = __ldg(a.slot_info + sl);
-                    dst[j] = __ldg(dist_row + sl);
-                    prv[j] = prow ? __ldg(prow + sl) : 1.0f;
+                for (int j = 0; j < 2; ++j) {
+                    const int v = min(v0 + lane + 32 * j, nv - 1);
+                    inf[j] = __ldg(info_row + v);
+                    dst[j] = __ldg(dist_row + v);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) prv[j][c] = prow ? __ldg(prow + min(4 * v + c, d.W - 1)) : 1.0f;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int sl = s0 + lane + 32 * j;
-                    if (sl >= d.W) continue;
-                    const int l = inf[j] & 255, col = ccol + ((inf[j] >> 8) & 255) - d.r, row = crow + (inf[j] >> 16) - d.r;
-                    const float dist = dst[j];
-                    float pr = -1.0f;
-                    if (col >= 0 && col < p.X && row >= 0 && row < p.Y && dist > 0.0f && dist <= budget && dist < d.max_dist) {
-                        pr = (!prow && priors_dense) ? priors_dense[(size_t)t * num_actions + l * N + p.X * col + row] : prv[j];
-                        pr = fmaxf(pr, 0.0f);
-                        sum += pr;
-                        ++n_valid;
-                        if (pr > bp || (pr == bp && sl < bs)) {
-                            bp = pr;
-                            bs = sl;
+                for (int j = 0; j < 2; ++j) {
+                    const int v = v0 + lane + 32 * j;
+                    if (v >= nv) continue;
+                    const int infs[4] = {inf[j].x, inf[j].y, inf[j].z, inf[j].w};
+                    const float dsts[4] = {dst[j].x, dst[j].y, dst[j].z, dst[j].w};
+                    float out[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int sl = 4 * v + c;
+                        const int l = infs[c] & 255, col = ccol + ((infs[c] >> 8) & 255) - d.r, row = crow + (infs[c] >> 16) - d.r;
+                        const float dist = dsts[c];  // 0 in the padding of the last group
+                        float pr = -1.0f;
+                        if (col >= 0 && col < p.X && row >= 0 && row < p.Y && dist > 0.0f && dist <= budget && dist < d.max_dist) {
+                            pr = (!prow && priors_dense) ? priors_dense[(size_t)t * num_actions + l * N + p.X * col + row] : prv[j][c];
+                            pr = fmaxf(pr, 0.0f);
+                            sum += pr;
+                            ++n_valid;
+                            if (pr > bp || (pr == bp && sl < bs)) {
+                                bp = pr;
+                                bs = sl;
+                            }
                         }
+                        out[c] = pr;
                     }
-                    P[sl] = pr;
+                    P4[v] = make_float4(out[0], out[1], out[2], out[3]);
                 }
             }
         } else
@@ -757,7 +772,7 @@ __global__ void mcts_root_export_kernel(const __grid_constant__ StepParams p, Tr
     unpack_pos(h.x, ccol, crow, lvl);
     const bool expanded = ((h.w >> 8) & 1) != 0;
     const float sc = a.pscale[(size_t)t * d.M];
-    const size_t base = (size_t)t * d.M * d.W;
+    const size_t base = (size_t)t * d.M * d.Wp;
     for (int s = threadIdx.x; s < d.W; s += blockDim.x) {
         const Slot c = slot_cell(d, p, s, ccol, crow);
         const size_t o = (size_t)t * d.W + s;
@@ -790,7 +805,12 @@ __global__ void mcts_root_export_kernel(const __grid_constant__ StepParams p, Tr
 // the cell offsets only.
 __global__ void slot_table_kernel(TreeDims d, const StepParams p, int *info, float *dist) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= d.W) return;
+    if (s >= d.Wp) return;
+    if (s >= d.W) {  // padding of the last 16-byte group: distance 0 = never a valid action
+        info[s] = 0;
+        for (int ln = 0; ln < d.L; ++ln) dist[(size_t)ln * d.Wp + s] = 0.0f;
+        return;
+    }
     const int DD = d.D * d.D;
     const int l = s / DD, rem = s - l * DD, a_ = rem / d.D, b = rem - a_ * d.D;
     info[s] = l | (a_ << 8) | (b << 16);
@@ -799,7 +819,7 @@ __global__ void slot_table_kernel(TreeDims d, const StepParams p, int *info, flo
     for (int ln = 0; ln < d.L; ++ln) {
         const float dz = (float)(p.lut[l].alt - p.lut[ln].alt);
         const float dyz = fmaf(dy, dy, dz * dz);
-        dist[(size_t)ln * d.W + s] = fast_sqrt(fmaf(dx, dx, dyz));
+        dist[(size_t)ln * d.Wp + s] = fast_sqrt(fmaf(dx, dx, dyz));
     }
 }
 
@@ -903,6 +923,7 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
     d.r = (int)std::floor(cfg->max_valid_action_distance / m->sp.res) + 1;
     d.D = 2 * d.r + 1;
     d.W = d.L * d.D * d.D;
+    d.Wp = (d.W + 3) & ~3;
     d.H = cfg->episode_horizon;
     d.max_path = d.H + 1;
     d.first_env = cfg->first_env;
@@ -918,7 +939,7 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
         ipp_mcts_destroy(m);
         return rc;
     };
-    const size_t TM = (size_t)d.T * d.M, TMW = TM * d.W, TP = (size_t)d.T * d.max_path;
+    const size_t TM = (size_t)d.T * d.M, TMW = TM * d.Wp, TP = (size_t)d.T * d.max_path;
     int rc;
     TreeArrays &a = m->a;
     if ((rc = malloc_dev(m, &a.hdr, TM)) || (rc = malloc_dev(m, &a.P, TMW)) || (rc = malloc_dev(m, &a.pscale, TM)) || (rc = malloc_dev(m, &a.bu, TM)) ||
@@ -937,8 +958,8 @@ extern "C" int ipp_mcts_create(ipp_engine *env, const ipp_mcts_config *cfg, ipp_
     {
         int *info_tab = nullptr;
         float *dist_tab = nullptr;
-        if ((rc = malloc_dev(m, &info_tab, (size_t)d.W)) || (rc = malloc_dev(m, &dist_tab, (size_t)d.L * d.W))) return bail(rc);
-        slot_table_kernel<<<(d.W + 255) / 256, 256, 0, m->stream>>>(d, m->sp, info_tab, dist_tab);
+        if ((rc = malloc_dev(m, &info_tab, (size_t)d.Wp)) || (rc = malloc_dev(m, &dist_tab, (size_t)d.L * d.Wp))) return bail(rc);
+        slot_table_kernel<<<(d.Wp + 255) / 256, 256, 0, m->stream>>>(d, m->sp, info_tab, dist_tab);
         m->launches++;
         a.slot_info = info_tab;
         a.slot_dist = dist_tab;
