@@ -60,7 +60,8 @@ typedef struct ipp_mcts_info {
     uint64_t device_bytes;  /* HBM held by the trees */
     uint64_t launches;      /* kernels launched by this object (rollouts included) */
     uint64_t edges;         /* edges in the trees' pools = prediction steps actually computed since ipp_mcts_begin (the rollouts are
-                               memoised: one per new edge; the reference replays one per level of every simulation) */
+                               memoised: one per new edge; the reference replays one per level of every simulation).  Filling it
+                               reads n_trees counters back: ipp_mcts_get_info synchronises the engine's stream once begun */
 } ipp_mcts_info;
 
 /* leaf record per tree, int32[8]: {kind, node, centre col, centre row, level (-1: root off-lattice), depth,
